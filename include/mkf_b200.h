@@ -1,0 +1,191 @@
+/* mkf_b200.h -- C ABI of libmkf_b200.so: the B200-native (sm_100a) implementation of the
+ * per-frame filtering hot path of mgb45/mkfbodytracker_pdaf.
+ *
+ * The reference has no FFI/plugin boundary: the path is ordinary C++ classes linked into the
+ * `poseTracker` node (CMakeLists.txt:29) and called from PFTracker (src/pfPose.cpp:58-71,
+ * 222-223, 241-242, 300-301, 325-326, 347-348).  This header is the boundary a maintainer
+ * would bind instead; every entry point cites the reference interface it replaces
+ * (file:line relative to the reference repository).  include/mkf_shims.hpp layers the
+ * reference's own class names (KF_model, my_gmm, state_params, ParticleFilter) on top.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types; 0 = success, negative MKF_E_* = failure
+ *    (the reference signals errors with cv::Exception; no exception crosses this boundary);
+ *    mkf_last_error() returns a thread-local message.
+ *  - the caller owns every buffer it passes; the library owns device memory behind the
+ *    opaque handles.  Every data pointer may be host or device memory (`mem` argument).
+ *  - work is enqueued on the batch's CUDA stream; functions that fill HOST buffers
+ *    synchronise that stream before returning, all others are asynchronous
+ *    (mkf_batch_sync waits).  One handle = one host thread at a time.
+ *  - "track" = one ParticleFilter (one arm filter), "slot" = one particle (one Gaussian
+ *    (x, P) of dimension d).  All reals are IEEE double, as in the reference (CV_64F).
+ *  - uniform draws are INPUTS (the reference seeds cv::RNG from the clock inside resample,
+ *    src/pf2DRao.cpp:179, which is not reproducible); seeds only feed the degenerate
+ *    random-index fallback (src/pf2DRao.cpp:184-192).
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    MKF_E_CUDA.
+ */
+#ifndef MKF_B200_H
+#define MKF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKF_ABI_VERSION 1
+
+/* error codes */
+#define MKF_OK 0
+#define MKF_E_INVALID (-1)     /* bad argument (what cv::Exception size/type asserts would catch) */
+#define MKF_E_CUDA (-2)        /* CUDA runtime failure / no device */
+#define MKF_E_NOMEM (-3)       /* host or device allocation failed */
+#define MKF_E_IO (-4)          /* model file unreadable */
+#define MKF_E_PARSE (-5)       /* model file malformed */
+#define MKF_E_UNSUPPORTED (-6) /* valid in the reference but not built here */
+
+/* semantics switches; defaults in mkf_params_default */
+#define MKF_CHOL_CV24_LITERAL 0 /* ParticleFilter::chol as it behaves on OpenCV 2.4 (src/pf2DRao.cpp:34-53) */
+#define MKF_CHOL_CV3_LITERAL 1  /* ... on OpenCV >= 3.0 (diagonal convention of cv::Cholesky differs) */
+#define MKF_CHOL_EXACT 2        /* true upper Cholesky factor (MATLAB mvnpdf, the evident intent) */
+#define MKF_ALIAS_INDEPENDENT 0 /* each slot owns its Gaussian (north_star: one KF per particle) */
+#define MKF_ALIAS_CV_SHALLOW_LITERAL 1 /* quirk B3 (src/pf2DRao.cpp:155); not built: MKF_E_UNSUPPORTED */
+
+/* memory space of caller pointers */
+#define MKF_MEM_AUTO 0 /* ask the driver (cudaPointerGetAttributes) */
+#define MKF_MEM_HOST 1
+#define MKF_MEM_DEVICE 2
+
+/* measurement layouts accepted by mkf_batch_update */
+#define MKF_MEAS_SHARED 0   /* T x 6       : one column per track, replicated to its N slots */
+#define MKF_MEAS_PER_SLOT 1 /* T x 6 x N   : the reference's 6 x N cv::Mat per track (src/pf2DRao.cpp:125) */
+
+/* per-track status bits (mkf_batch_download / mkf_batch_status) */
+#define MKF_ST_IND_FALLBACK 0x1u    /* indicator resample resolved by the exact sequential loop */
+#define MKF_ST_POST_FALLBACK 0x2u   /* posterior resample resolved by the exact sequential loop */
+#define MKF_ST_POST_DEGENERATE 0x4u /* max weight 0/NaN: random-index fallback taken (src/pf2DRao.cpp:184-192) */
+#define MKF_ST_CHOL_FAIL 0x8u       /* cv::Cholesky failed for at least one slot (src/pf2DRao.cpp:37) */
+#define MKF_ST_CAND_FALLBACK 0x10u  /* candidate resample resolved by the exact sequential loop */
+#define MKF_ST_CAND_DEGENERATE 0x20u /* no candidate passed the gate: random candidates (quirk B11) */
+#define MKF_ST_IND_WRAP 0x40u       /* indicator resample wrapped past the last component */
+
+typedef struct mkf_model mkf_model; /* one arm model: GMM prior + per-component KF constants */
+typedef struct mkf_batch mkf_batch; /* T independent tracks x N slots on one GPU */
+
+/* every hard-coded literal of the reference on this path, with the reference value as default */
+typedef struct mkf_params {
+    int chol_mode;         /* MKF_CHOL_*                                  default CV24_LITERAL */
+    int alias_mode;        /* MKF_ALIAS_*                                 default INDEPENDENT  */
+    double meas_noise_var; /* R = 100 * I6              src/my_gmm.cpp:54                      */
+    double assoc_pa;       /* Pa = 0.05                 src/pfPose.cpp:247                     */
+    double assoc_clutter;  /* 1e-4                      src/pfPose.cpp:261                     */
+    double proposal_spread;/* 0.8 (x roi width)         src/pf2DRao.cpp:90,114                 */
+    double neck_offset;    /* 1.65 (x roi height)       src/pfPose.cpp:313                     */
+    int img_rows, img_cols;/* 480 x 640 gate            src/pfPose.cpp:251                     */
+} mkf_params;
+void mkf_params_default(mkf_params* p);
+
+const char* mkf_last_error(void);
+int mkf_abi_version(void);
+/* number of CUDA devices visible (0 when there is none; never fails) */
+int mkf_device_count(void);
+
+/* ---- model: my_gmm::loadGaussian for all K components (src/my_gmm.cpp:45-75, src/pfPose.cpp:61-65) ----
+ * means K x d, covs K x d x d (the reference's stacked (K*d) x d matrix), weights K, gamma K,
+ * pca_proj d x D, pca_mean D (already widened to f64 as src/pfPose.cpp:44-51 does).  Host pointers.
+ * Supported: d in {10, 12} with 6 measurement rows, K <= 64, 14 <= D <= 32. */
+int mkf_model_create(mkf_model** out, int K, int d, int D, const double* means, const double* covs,
+                     const double* weights, const double* gamma, const double* pca_proj, const double* pca_mean,
+                     const mkf_params* params);
+/* cv::FileStorage load of one arm model (src/pfPose.cpp:34-55): keys means, covs, weights,
+ * pca_proj, pca_mean, gamma in OpenCV-YAML-1.0.  gamma_path: file to take `gamma` from, NULL =
+ * same file.  (The reference reads BOTH arms' gamma from the right-arm file, src/pfPose.cpp:52-53,
+ * quirk B4: pass the right-arm path here to reproduce it.) */
+int mkf_model_load_yaml(mkf_model** out, const char* path, const char* gamma_path, const mkf_params* params);
+void mkf_model_destroy(mkf_model* m);
+int mkf_model_dims(const mkf_model* m, int* K, int* d, int* D);
+/* copies of the model arrays (any pointer may be NULL): the loaded GMM and the derived
+ * KF_model members Q (K x d x d), B (K x d), H (6 x d), BH (6) of src/my_gmm.cpp:53-72 */
+int mkf_model_get(const mkf_model* m, double* means, double* covs, double* weights, double* gamma, double* pca_proj,
+                  double* pca_mean, double* Q, double* B, double* H, double* BH);
+
+/* ---- batch of tracks ---- */
+/* replaces `new ParticleFilter(numParticles)` x T (src/pfPose.cpp:57-59).  stream: a cudaStream_t
+ * to enqueue on (e.g. torch's current stream) or NULL for a private stream. */
+int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, int N, int device, void* stream);
+void mkf_batch_destroy(mkf_batch* b);
+int mkf_batch_sync(mkf_batch* b);
+
+/* bins = resample(gmm.weight, N); gmm.resetTracker(bins)  (src/pfPose.cpp:68-71, src/my_gmm.cpp:30-42).
+ * u_init: T uniform draws in [0,1). */
+int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem);
+
+/* ParticleFilter::update for every track (src/pf2DRao.cpp:125-158): indicator resample (K->N),
+ * per-slot KF_model::predict (src/KF_model.cpp:11-15), innovation likelihood mvnpdf/chol
+ * (src/pf2DRao.cpp:34-67), KF_model::update (src/KF_model.cpp:17-25), weight normalisation and
+ * systematic resampling (src/pf2DRao.cpp:175-210).
+ * meas: layout per meas_layout; u_ind, u_post: T draws each; seeds: T x 2 uint64 for the
+ * degenerate fallback (NULL: seed 1 as cv::RNG(1)). */
+int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layout, const double* u_ind, const double* u_post,
+                     const uint64_t* seeds, int mem);
+
+/* ParticleFilter::getEstimator (src/pf2DRao.cpp:23-31) and e = pca_proj^T xbar + pca_mean^T
+ * (src/pfPose.cpp:347-348).  xbar T x d, pose T x D; either may be NULL. */
+int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int mem);
+
+/* association ("PDAF") step of PFTracker::getMeasurementProposal for T persons
+ * (src/pfPose.cpp:238-323; densities src/pf2DRao.cpp:69-83,105-122): gate, L/Z weights,
+ * normalisation, C->N systematic resample and assembly of the per-slot measurement columns,
+ * followed by ParticleFilter::update of both arms (src/pfPose.cpp:325-326) when do_update != 0.
+ * arm[0]/arm[1]: the two arm batches (same T, N, device, stream).
+ * cand_xy T x 2 hands x 2 (x row, y row) x C; cand_L T x 2 x C (likelihood-image samples,
+ * uint8); roi T x 4 (x, y, w, h); u_cand T x 2; u_ind/u_post T x 2 (arm-major pairs). */
+int mkf_batch_associate(mkf_batch* arm0, mkf_batch* arm1, int C, const double* cand_xy, const uint8_t* cand_L,
+                        const double* roi, const double* u_cand, const double* u_ind, const double* u_post,
+                        const uint64_t* seeds, int do_update, int mem);
+/* results of the last mkf_batch_associate on arm0: gate T x 2 x C (0/1), weights T x 2 x C
+ * (normalised), bins T x 2 x N; any may be NULL. */
+int mkf_batch_assoc_results(mkf_batch* arm0, uint8_t* gate, double* weights, int32_t* bins, int mem);
+
+/* state access in the reference's coordinates (parity tests, checkpoint/resume):
+ * x T x N x d, P T x N x d x d (row-major full matrices, as gmm.tracks[j].state/.cov,
+ * src/my_gmm.h:9-18), w_raw / w_norm T x N (weights of the last update before / after division
+ * by wsum), indicators / parents T x N (component draw and resampled parent of the last
+ * update), wsum T, status T.  Any pointer may be NULL. */
+int mkf_batch_download(mkf_batch* b, double* x, double* P, double* w_raw, double* w_norm, int32_t* indicators,
+                       int32_t* parents, double* wsum, uint32_t* status, int mem);
+int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, int mem);
+
+/* ParticleFilter::resample for one weight vector (src/pf2DRao.cpp:175-210) on the device:
+ * w[L] (host), N outputs, u < 0 draws from cv::RNG(seed) as the reference does. */
+int mkf_resample(const double* w, int L, int N, double u, uint64_t seed, int32_t* out, int device);
+
+/* ---- legacy plain particle filter (src/pf2D.{h,cpp}, "particle likelihoods") ---- */
+typedef struct mkf_pf2d mkf_pf2d;
+/* T independent filters of N particles over d >= 8 dims with a K-component GMM prior
+ * (my_gmm::loadGaussian, src/pf2D.cpp:28-37: means K x d, covs K x d x d, weights K). */
+int mkf_pf2d_create(mkf_pf2d** out, int64_t T, int N, int d, int K, const double* means, const double* covs,
+                    const double* weights, int device, void* stream);
+void mkf_pf2d_destroy(mkf_pf2d* p);
+int mkf_pf2d_set_particles(mkf_pf2d* p, const double* particles /* T x N x d */, int mem);
+int mkf_pf2d_get(mkf_pf2d* p, double* particles, double* w_norm, int32_t* parents, int mem);
+/* ParticleFilter::update of src/pf2D.cpp:148-210: weights (GMM prior with float expf x two
+ * isotropic 2-D likelihoods), normalise, systematic resample, random-walk predict.
+ * meas T x 2 x 2, u T, noise T x N x d standard normals (NULL: no predict noise). */
+int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u, const double* noise, int mem);
+int mkf_pf2d_sync(mkf_pf2d* p);
+
+/* ---- synthetic workload (include/mkf_synth.h), generated on the device ---- */
+/* fills meas (device, layout per meas_layout) and u_ind/u_post (device, T each) for `frame` */
+int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint64_t frame, int jitter, int meas_layout,
+                   double* meas_dev, double* u_ind_dev, double* u_post_dev);
+
+/* number of kernel launches issued through this library since load (bench.py "gpu_launches") */
+uint64_t mkf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MKF_B200_H */

@@ -1,0 +1,621 @@
+// mkf_api.cu -- C-ABI entry points of libmkf_b200.so that touch the device.
+// See include/mkf_b200.h for the contract and the reference interfaces each call replaces.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "mkf_internal.h"
+#include "mkf_kernels.cuh"
+
+static std::atomic<uint64_t> g_launches{0};
+extern "C" uint64_t mkf_launch_count(void) { return g_launches.load(); }
+#define MKF_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            mkf_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+            return MKF_E_CUDA;                                                                            \
+        }                                                                                                 \
+    } while (0)
+
+extern "C" int mkf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return MKF_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            mkf_set_error("cudaMalloc(%zu) failed", bytes);
+            return MKF_E_NOMEM;
+        }
+        cap = bytes;
+        return MKF_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct mkf_batch {
+    const mkf_model* m = nullptr;
+    long long T = 0;
+    int N = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    mkf_layout lay;
+    long long total = 0, n_tiles = 0;
+    // device state
+    double2* st[2] = {nullptr, nullptr};
+    int cur = 0; // st[cur] holds the children of the last update (read through `parent`)
+    int32_t* parent = nullptr;
+    int32_t* bounds = nullptr;
+    double* w_raw = nullptr;
+    double* wsum = nullptr;
+    uint32_t* status = nullptr;
+    uint32_t* need_fb = nullptr;
+    // model constants on this device
+    double *d_comp = nullptr, *d_init = nullptr, *d_cw_hi = nullptr, *d_cw_lo = nullptr, *d_wprior = nullptr,
+           *d_recon = nullptr, *d_pmean = nullptr, *d_tm = nullptr, *d_tinv = nullptr;
+    // staging
+    DevBuf in_meas, in_u0, in_u1, in_seed, out_a, out_b, in_x, in_p;
+    // association scratch (arm0 owns)
+    DevBuf as_cand, as_L, as_roi, as_u, as_w, as_gate, as_bins, as_meas, as_wsum, as_hand;
+    int as_C = 0;
+};
+
+static bool is_device_ptr(const void* p, int mem)
+{
+    if (mem == MKF_MEM_DEVICE) return true;
+    if (mem == MKF_MEM_HOST) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// input pointer -> device pointer (copying through `stage` when it is host memory)
+template <class Tp>
+static int in_ptr(mkf_batch* b, const Tp* p, size_t count, int mem, DevBuf& stage, const Tp** out)
+{
+    if (!p) {
+        *out = nullptr;
+        return MKF_OK;
+    }
+    if (is_device_ptr(p, mem)) {
+        *out = p;
+        return MKF_OK;
+    }
+    int rc = stage.ensure(count * sizeof(Tp));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(stage.p, p, count * sizeof(Tp), cudaMemcpyHostToDevice, b->stream));
+    *out = (const Tp*)stage.p;
+    return MKF_OK;
+}
+
+// output helper: kernels write to dev(); finish() copies back when the user pointer is host memory
+template <class Tp>
+struct OutPtr {
+    Tp* user = nullptr;
+    Tp* devp = nullptr;
+    size_t count = 0;
+    bool host = false;
+    int init(mkf_batch* b, Tp* p, size_t n, int mem, DevBuf& stage)
+    {
+        (void)b;
+        user = p;
+        count = n;
+        if (!p) return MKF_OK;
+        if (is_device_ptr(p, mem)) {
+            devp = p;
+            return MKF_OK;
+        }
+        host = true;
+        int rc = stage.ensure(n * sizeof(Tp));
+        if (rc) return rc;
+        devp = (Tp*)stage.p;
+        return MKF_OK;
+    }
+    int finish(mkf_batch* b)
+    {
+        if (user && host) CK(cudaMemcpyAsync(user, devp, count * sizeof(Tp), cudaMemcpyDeviceToHost, b->stream));
+        return MKF_OK;
+    }
+};
+
+static int upload_const(const std::vector<double>& v, double** d)
+{
+    CK(cudaMalloc((void**)d, v.size() * sizeof(double)));
+    CK(cudaMemcpy(*d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return MKF_OK;
+}
+
+extern "C" void mkf_batch_destroy(mkf_batch* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (int i = 0; i < 2; i++)
+        if (b->st[i]) cudaFree(b->st[i]);
+    void* ptrs[] = {b->parent, b->bounds, b->w_raw, b->wsum,   b->status, b->need_fb, b->d_comp, b->d_init,
+                    b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    DevBuf* bufs[] = {&b->in_meas, &b->in_u0, &b->in_u1, &b->in_seed, &b->out_a,   &b->out_b,  &b->in_x,   &b->in_p,
+                      &b->as_cand, &b->as_L,  &b->as_roi, &b->as_u,   &b->as_w,    &b->as_gate, &b->as_bins,
+                      &b->as_meas, &b->as_wsum, &b->as_hand};
+    for (DevBuf* d : bufs) d->release();
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, int N, int device, void* stream)
+{
+    if (!out || !m || T <= 0 || N <= 0) {
+        mkf_set_error("mkf_batch_create: invalid argument (T=%lld N=%d)", (long long)T, N);
+        return MKF_E_INVALID;
+    }
+    *out = nullptr;
+    if ((long long)T * N > (1ll << 40)) {
+        mkf_set_error("mkf_batch_create: T*N too large");
+        return MKF_E_INVALID;
+    }
+    int ndev = mkf_device_count();
+    if (ndev <= 0) {
+        mkf_set_error("no CUDA device available: libmkf_b200 has no CPU fallback");
+        return MKF_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        mkf_set_error("mkf_batch_create: device %d out of range (%d visible)", device, ndev);
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    mkf_batch* b = new (std::nothrow) mkf_batch;
+    if (!b) return MKF_E_NOMEM;
+    b->m = m;
+    b->T = T;
+    b->N = N;
+    b->device = device;
+    b->lay = m->lay;
+    b->total = (long long)T * N;
+    b->n_tiles = (b->total + 31) / 32;
+    int rc = MKF_OK;
+    auto fail = [&](int code) {
+        mkf_batch_destroy(b);
+        return code;
+    };
+    if (stream) {
+        b->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            mkf_set_error("cudaStreamCreate failed");
+            return fail(MKF_E_CUDA);
+        }
+        b->own_stream = true;
+    }
+    const size_t tile_bytes = (size_t)b->lay.np * 32 * sizeof(double2);
+    auto dmalloc = [&](void** p, size_t bytes) {
+        if (cudaMalloc(p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            mkf_set_error("cudaMalloc(%zu bytes) failed for a batch of T=%lld N=%d", bytes, (long long)T, N);
+            return MKF_E_NOMEM;
+        }
+        return MKF_OK;
+    };
+    for (int i = 0; i < 2; i++)
+        if ((rc = dmalloc((void**)&b->st[i], (size_t)b->n_tiles * tile_bytes))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->parent, (size_t)b->total * sizeof(int32_t)))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->bounds, (size_t)T * (m->K + 2) * sizeof(int32_t)))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->w_raw, (size_t)b->total * sizeof(double)))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->wsum, (size_t)T * sizeof(double)))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->status, (size_t)T * sizeof(uint32_t)))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->need_fb, (size_t)T * sizeof(uint32_t)))) return fail(rc);
+    // the tail lanes of the last tile are read by nobody but keep them defined
+    if (cudaMemset(b->st[0], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
+        cudaMemset(b->st[1], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
+        cudaMemset(b->status, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemset(b->need_fb, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemset(b->w_raw, 0, (size_t)b->total * sizeof(double)) != cudaSuccess ||
+        cudaMemset(b->wsum, 0, (size_t)T * sizeof(double)) != cudaSuccess ||
+        cudaMemset(b->parent, 0, (size_t)b->total * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemset(b->bounds, 0, (size_t)T * (m->K + 2) * sizeof(int32_t)) != cudaSuccess) {
+        mkf_set_error("cudaMemset failed");
+        return fail(MKF_E_CUDA);
+    }
+    if ((rc = upload_const(m->comp_const, &b->d_comp)) || (rc = upload_const(m->init_const, &b->d_init)) ||
+        (rc = upload_const(m->cw_hi, &b->d_cw_hi)) || (rc = upload_const(m->cw_lo, &b->d_cw_lo)) ||
+        (rc = upload_const(m->weights, &b->d_wprior)) || (rc = upload_const(m->recon, &b->d_recon)) ||
+        (rc = upload_const(m->pmean, &b->d_pmean)) || (rc = upload_const(m->Tm, &b->d_tm)) ||
+        (rc = upload_const(m->Tinv, &b->d_tinv)))
+        return fail(rc);
+    *out = b;
+    return MKF_OK;
+}
+
+extern "C" int mkf_batch_sync(mkf_batch* b)
+{
+    if (!b) {
+        mkf_set_error("null batch");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    return MKF_OK;
+}
+
+static inline unsigned grid_for(long long n, int bt) { return (unsigned)((n + bt - 1) / bt); }
+
+static int launch_bounds_kernel(mkf_batch* b, const double* d_u)
+{
+    const mkf_model* m = b->m;
+    k_indicator_bounds<<<grid_for(b->T, 128), 128, 0, b->stream>>>(d_u, b->T, b->N, m->K, b->d_cw_hi, b->d_cw_lo,
+                                                                    b->d_wprior, m->prior_wmax, b->bounds, b->status);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    return MKF_OK;
+}
+
+extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
+{
+    if (!b || !u_init) {
+        mkf_set_error("mkf_batch_reset: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    const double* d_u;
+    int rc = in_ptr(b, u_init, (size_t)b->T, mem, b->in_u0, &d_u);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(b->status, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
+    if ((rc = launch_bounds_kernel(b, d_u))) return rc;
+    b->cur = 0;
+    if (b->m->d == 12)
+        k_reset<12><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
+                                                                    b->total, b->N, b->m->K);
+    else
+        k_reset<10><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
+                                                                    b->total, b->N, b->m->K);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    return MKF_OK;
+}
+
+// weight normalisation + systematic resampling of T tracks: w (T x L) -> out (T x N)
+static int run_resample(mkf_batch* b, const double* d_w, int L, int N, const double* d_u, int u_stride, int normalise,
+                        double* d_wsum, int32_t* d_out, uint32_t* d_status, const uint64_t* d_seeds, int seed_stride,
+                        int seed_off, uint32_t bit_fb, uint32_t bit_deg)
+{
+    if (L <= 64 && N <= 64) {
+        k_resample_small<<<grid_for(b->T, 128), 128, 0, b->stream>>>(d_w, b->T, L, N, d_u, u_stride, normalise, d_wsum,
+                                                                      d_out, d_status, 1, b->need_fb, bit_deg);
+    } else {
+        k_resample_block<128, 4><<<(unsigned)b->T, 128, 0, b->stream>>>(d_w, L, N, d_u, u_stride, normalise, d_wsum,
+                                                                         d_out, d_status, 1, b->need_fb, bit_fb,
+                                                                         bit_deg);
+    }
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    k_resample_fallback<<<grid_for(b->T, 128), 128, 0, b->stream>>>(d_w, b->T, L, N, d_u, u_stride, normalise, d_wsum,
+                                                                     d_out, d_seeds, seed_stride, seed_off, b->need_fb);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    return MKF_OK;
+}
+
+// the frame pipeline on device pointers
+static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, const double* d_uind,
+                         const double* d_upost, int u_stride, const uint64_t* d_seeds, int seed_stride, int seed_off)
+{
+    const mkf_model* m = b->m;
+    int rc;
+    if (u_stride != 1) {
+        mkf_set_error("internal: strided u_ind unsupported");
+        return MKF_E_INVALID;
+    }
+    if ((rc = launch_bounds_kernel(b, d_uind))) return rc;
+    SlotArgs a;
+    a.st_in = b->st[b->cur];
+    a.st_out = b->st[b->cur ^ 1];
+    a.parent = b->parent;
+    a.bounds = b->bounds;
+    a.meas = d_meas;
+    a.comp_const = b->d_comp;
+    a.w_raw = b->w_raw;
+    a.status = b->status;
+    a.total = b->total;
+    a.N = b->N;
+    a.K = m->K;
+    a.meas_layout = meas_layout;
+    a.chol_mode = m->prm.chol_mode;
+    for (int r = 0; r < MKF_M; r++) a.bh[r] = m->BH[r];
+    a.r = m->prm.meas_noise_var;
+    const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
+    if (m->d == 12) {
+        static bool attr12 = false;
+        if (!attr12 && smem > 48 * 1024) {
+            CK(cudaFuncSetAttribute(k_slot_update<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr12 = true;
+        }
+        k_slot_update<12><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
+    } else {
+        static bool attr10 = false;
+        if (!attr10 && smem > 48 * 1024) {
+            CK(cudaFuncSetAttribute(k_slot_update<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr10 = true;
+        }
+        k_slot_update<10><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
+    }
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    b->cur ^= 1;
+    return run_resample(b, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status, d_seeds, seed_stride,
+                        seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE);
+}
+
+extern "C" int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layout, const double* u_ind,
+                                const double* u_post, const uint64_t* seeds, int mem)
+{
+    if (!b || !meas || !u_ind || !u_post) {
+        mkf_set_error("mkf_batch_update: null argument");
+        return MKF_E_INVALID;
+    }
+    if (meas_layout != MKF_MEAS_SHARED && meas_layout != MKF_MEAS_PER_SLOT) {
+        mkf_set_error("mkf_batch_update: unknown measurement layout %d", meas_layout);
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    const size_t nmeas = (size_t)b->T * MKF_M * (meas_layout == MKF_MEAS_PER_SLOT ? (size_t)b->N : 1);
+    const double *d_meas, *d_ui, *d_up;
+    const uint64_t* d_seeds;
+    int rc;
+    if ((rc = in_ptr(b, meas, nmeas, mem, b->in_meas, &d_meas))) return rc;
+    if ((rc = in_ptr(b, u_ind, (size_t)b->T, mem, b->in_u0, &d_ui))) return rc;
+    if ((rc = in_ptr(b, u_post, (size_t)b->T, mem, b->in_u1, &d_up))) return rc;
+    if ((rc = in_ptr(b, seeds, (size_t)b->T * 2, mem, b->in_seed, &d_seeds))) return rc;
+    CK(cudaMemsetAsync(b->status, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
+    return update_device(b, d_meas, meas_layout, d_ui, d_up, 1, d_seeds, 2, 1);
+}
+
+extern "C" int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int mem)
+{
+    if (!b) {
+        mkf_set_error("null batch");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    const mkf_model* m = b->m;
+    OutPtr<double> ox, op;
+    int rc;
+    if ((rc = ox.init(b, xbar, (size_t)b->T * m->d, mem, b->out_a))) return rc;
+    if ((rc = op.init(b, pose, (size_t)b->T * m->D, mem, b->out_b))) return rc;
+    const double2* st = b->st[b->cur];
+#define LAUNCH_EST(DD, BT)                                                                                   \
+    k_estimate<DD, BT><<<(unsigned)b->T, BT, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean, \
+                                                              b->d_tinv, ox.devp, op.devp)
+    if (m->d == 12) {
+        if (b->N <= 64)
+            LAUNCH_EST(12, 32);
+        else
+            LAUNCH_EST(12, 128);
+    } else {
+        if (b->N <= 64)
+            LAUNCH_EST(10, 32);
+        else
+            LAUNCH_EST(10, 128);
+    }
+#undef LAUNCH_EST
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if ((rc = ox.finish(b)) || (rc = op.finish(b))) return rc;
+    if (ox.host || op.host) CK(cudaStreamSynchronize(b->stream));
+    return MKF_OK;
+}
+
+extern "C" int mkf_batch_download(mkf_batch* b, double* x, double* P, double* w_raw, double* w_norm,
+                                  int32_t* indicators, int32_t* parents, double* wsum, uint32_t* status, int mem)
+{
+    if (!b) {
+        mkf_set_error("null batch");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    const mkf_model* m = b->m;
+    const int d = m->d;
+    const size_t tot = (size_t)b->total;
+    DevBuf sx, sp, sw, si; // temporaries for host-bound outputs (freed on return)
+    OutPtr<double> ox, op, own;
+    OutPtr<int32_t> oi;
+    int rc = MKF_OK;
+    auto done = [&](int code) {
+        sx.release();
+        sp.release();
+        sw.release();
+        si.release();
+        return code;
+    };
+    if ((rc = ox.init(b, x, tot * d, mem, sx)) || (rc = op.init(b, P, tot * d * d, mem, sp)) ||
+        (rc = own.init(b, w_norm, tot, mem, sw)) || (rc = oi.init(b, indicators, tot, mem, si)))
+        return done(rc);
+    if (x || P) {
+        if (d == 12)
+            k_download<12><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[b->cur], b->parent, b->d_tinv, ox.devp,
+                                                                          op.devp, b->total, b->N);
+        else
+            k_download<10><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[b->cur], b->parent, b->d_tinv, ox.devp,
+                                                                          op.devp, b->total, b->N);
+        MKF_LAUNCHED();
+        if (cudaGetLastError() != cudaSuccess) {
+            mkf_set_error("k_download launch failed");
+            return done(MKF_E_CUDA);
+        }
+    }
+    if (w_norm || indicators) {
+        k_aux_outputs<<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->w_raw, b->wsum, b->bounds, b->total, b->N,
+                                                                       m->K, own.devp, oi.devp);
+        MKF_LAUNCHED();
+        if (cudaGetLastError() != cudaSuccess) {
+            mkf_set_error("k_aux_outputs launch failed");
+            return done(MKF_E_CUDA);
+        }
+    }
+    if ((rc = ox.finish(b)) || (rc = op.finish(b)) || (rc = own.finish(b)) || (rc = oi.finish(b))) return done(rc);
+    auto copy_out = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!dst) return MKF_OK;
+        cudaMemcpyKind kind = is_device_ptr(dst, mem) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (cudaMemcpyAsync(dst, src, bytes, kind, b->stream) != cudaSuccess) {
+            mkf_set_error("cudaMemcpyAsync failed in mkf_batch_download");
+            return MKF_E_CUDA;
+        }
+        return MKF_OK;
+    };
+    if ((rc = copy_out(w_raw, b->w_raw, tot * sizeof(double))) ||
+        (rc = copy_out(parents, b->parent, tot * sizeof(int32_t))) ||
+        (rc = copy_out(wsum, b->wsum, (size_t)b->T * sizeof(double))) ||
+        (rc = copy_out(status, b->status, (size_t)b->T * sizeof(uint32_t))))
+        return done(rc);
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
+        mkf_set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return done(MKF_E_CUDA);
+    }
+    return done(MKF_OK);
+}
+
+extern "C" int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, int mem)
+{
+    if (!b || !x || !P) {
+        mkf_set_error("mkf_batch_upload: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    const int d = b->m->d;
+    const double *dx, *dP;
+    int rc;
+    if ((rc = in_ptr(b, x, (size_t)b->total * d, mem, b->in_x, &dx))) return rc;
+    if ((rc = in_ptr(b, P, (size_t)b->total * d * d, mem, b->in_p, &dP))) return rc;
+    b->cur = 0;
+    if (d == 12)
+        k_upload<12><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[0], b->parent, dx, dP, b->d_tm, b->total, b->N);
+    else
+        k_upload<10><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[0], b->parent, dx, dP, b->d_tm, b->total, b->N);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(b->stream));
+    b->in_x.release();
+    b->in_p.release();
+    return MKF_OK;
+}
+
+// single weight vector, through the same kernels (one "track")
+extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t seed, int32_t* out, int device)
+{
+    if (!w || !out || L <= 0 || N <= 0) {
+        mkf_set_error("mkf_resample: invalid argument");
+        return MKF_E_INVALID;
+    }
+    int ndev = mkf_device_count();
+    if (ndev <= 0) {
+        mkf_set_error("no CUDA device available: libmkf_b200 has no CPU fallback");
+        return MKF_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        mkf_set_error("mkf_resample: bad device");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    double uu = u;
+    if (u < 0.0) { // the reference's own draw order: one discarded int, then uniform(0.0, 1.0)
+        uint64_t st = seed ? seed : 0xffffffffull;
+        auto next = [&]() {
+            st = (uint64_t)(unsigned)st * 4164903690u + (unsigned)(st >> 32);
+            return (unsigned)st;
+        };
+        (void)next();
+        unsigned t = next();
+        uu = (double)(((uint64_t)t << 32) | next()) * 5.4210108624275221700372640043497e-20;
+    }
+    double *d_w = nullptr, *d_u = nullptr, *d_ws = nullptr;
+    int32_t* d_out = nullptr;
+    uint32_t *d_st = nullptr, *d_fb = nullptr;
+    uint64_t* d_seed = nullptr;
+    int rc = MKF_OK;
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc((void**)&d_w, (size_t)L * 8)) || (e = cudaMalloc((void**)&d_u, 8)) ||
+        (e = cudaMalloc((void**)&d_ws, 8)) || (e = cudaMalloc((void**)&d_out, (size_t)N * 4)) ||
+        (e = cudaMalloc((void**)&d_st, 4)) || (e = cudaMalloc((void**)&d_fb, 4)) ||
+        (e = cudaMalloc((void**)&d_seed, 8))) {
+        rc = MKF_E_NOMEM;
+    }
+    if (!rc) {
+        cudaMemcpy(d_w, w, (size_t)L * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_u, &uu, 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_seed, &seed, 8, cudaMemcpyHostToDevice);
+        cudaMemset(d_st, 0, 4);
+        cudaMemset(d_fb, 0, 4);
+        // the reference applies resample() to already-normalised weights: no division here
+        if (L <= 64 && N <= 64)
+            k_resample_small<<<1, 32>>>(d_w, 1, L, N, d_u, 1, 0, d_ws, d_out, d_st, 1, d_fb, MKF_ST_POST_DEGENERATE);
+        else
+            k_resample_block<128, 4><<<1, 128>>>(d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, 1, d_fb,
+                                                 MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE);
+        MKF_LAUNCHED();
+        k_resample_fallback<<<1, 32>>>(d_w, 1, L, N, d_u, 1, 0, d_ws, d_out, d_seed, 1, 0, d_fb);
+        MKF_LAUNCHED();
+        e = cudaMemcpy(out, d_out, (size_t)N * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            mkf_set_error("mkf_resample: %s", cudaGetErrorString(e));
+            rc = MKF_E_CUDA;
+        }
+        uint32_t st = 0;
+        cudaMemcpy(&st, d_st, 4, cudaMemcpyDeviceToHost);
+        if (!rc) rc = (st & MKF_ST_POST_DEGENERATE) ? 1 : 0; // like orc_resample: 1 = degenerate fallback taken
+    } else {
+        mkf_set_error("mkf_resample: cudaMalloc failed");
+    }
+    void* ptrs[] = {d_w, d_u, d_ws, d_out, d_st, d_fb, d_seed};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    return rc;
+}
+
+extern "C" int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint64_t frame, int jitter,
+                              int meas_layout, double* meas_dev, double* u_ind_dev, double* u_post_dev)
+{
+    if (!b || !meas_dev) {
+        mkf_set_error("mkf_synth_fill: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    const long long n = meas_layout == MKF_MEAS_SHARED ? b->T : b->total;
+    k_synth_fill<<<grid_for(n, 256), 256, 0, b->stream>>>(seed, track0, frame, jitter, meas_layout, b->T, b->N,
+                                                          meas_dev, u_ind_dev, u_post_dev);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    return MKF_OK;
+}
+
+#include "mkf_assoc.cuh"
+#include "mkf_pf2d.cuh"

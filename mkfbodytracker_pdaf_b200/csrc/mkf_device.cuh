@@ -1,0 +1,236 @@
+// mkf_device.cuh -- device-side building blocks: double-double arithmetic, the exact
+// systematic-resampling count, TMA (1-D bulk copy) + mbarrier helpers, block scans.
+#ifndef MKF_DEVICE_CUH
+#define MKF_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// ---------------------------------------------------------------------------------------------
+// double-double (error-free transformations; no FMA contraction can alter pure add/sub chains)
+// ---------------------------------------------------------------------------------------------
+struct dd {
+    double hi, lo;
+};
+
+__device__ __forceinline__ dd dd_make(double a)
+{
+    dd r;
+    r.hi = a;
+    r.lo = 0.0;
+    return r;
+}
+__device__ __forceinline__ dd dd_two_sum(double a, double b)
+{
+    dd r;
+    r.hi = __dadd_rn(a, b);
+    double bb = __dsub_rn(r.hi, a);
+    r.lo = __dadd_rn(__dsub_rn(a, __dsub_rn(r.hi, bb)), __dsub_rn(b, bb));
+    return r;
+}
+__device__ __forceinline__ dd dd_fast_two_sum(double a, double b) // |a| >= |b|
+{
+    dd r;
+    r.hi = __dadd_rn(a, b);
+    r.lo = __dsub_rn(b, __dsub_rn(r.hi, a));
+    return r;
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b)
+{
+    dd s = dd_two_sum(a.hi, b.hi);
+    s.lo = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
+    return dd_fast_two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ dd dd_add_d(dd a, double b)
+{
+    dd s = dd_two_sum(a.hi, b);
+    s.lo = __dadd_rn(s.lo, a.lo);
+    return dd_fast_two_sum(s.hi, s.lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact systematic resampling count (src/pf2DRao.cpp:195-207 in closed form)
+//
+// The reference walks thresholds T_i = beta0 + i*step (beta0 = fl(u*step), step = fl(1/N)) over the
+// running sum of the weights.  In exact arithmetic, parent k receives the outputs i with
+// C_{k-1} < T_i <= C_k, so with e_k = #{ i in [0,N) : T_i <= C_k } parent k owns [e_{k-1}, e_k).
+// count_le returns e for a prefix sum C held in double-double and reports `amb` when a valid
+// threshold lies within `tol` of C -- tol bounds the rounding error the reference's sequential
+// `beta -= w; beta += step` loop can have accumulated, so outside that band the loop provably takes
+// the same decision.  Ambiguous tracks are re-run by the exact sequential kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mkf_count_le(dd C, double beta0, double step, int N, double tol, bool& amb)
+{
+    dd df = dd_add_d(C, -beta0);
+    double qi = floor(__ddiv_rn(df.hi, step));
+    double rem = __dadd_rn(__fma_rn(-qi, step, df.hi), df.lo); // C - T_qi
+    if (rem < 0.0) {
+        qi -= 1.0;
+        rem = __dadd_rn(__fma_rn(-qi, step, df.hi), df.lo);
+    } else if (rem >= step) {
+        qi += 1.0;
+        rem = __dadd_rn(__fma_rn(-qi, step, df.hi), df.lo);
+    }
+    // T_qi <= C < T_{qi+1}; distances rem and step - rem
+    const double nm1 = (double)(N - 1);
+    if (qi >= 0.0 && qi <= nm1 && rem <= tol) amb = true;
+    if (qi + 1.0 >= 0.0 && qi + 1.0 <= nm1 && (step - rem) <= tol) amb = true;
+    if (!(rem >= 0.0 && rem < step)) amb = true; // NaN / failed correction: let the exact loop decide
+    double cnt = qi + 1.0;
+    if (!(cnt > 0.0)) return 0;
+    if (cnt >= (double)N) return N;
+    return (int)cnt;
+}
+
+// bound on the rounding error accumulated by the reference loop: every one of its <= N+L
+// add/subtract results is <= wmax + step, each rounded with relative error 2^-53
+__device__ __forceinline__ double mkf_resample_tol(int N, int L, double wmax, double step)
+{
+    return 1.0625 * 1.1102230246251565e-16 * (double)(N + L) * (wmax + step);
+}
+
+// cv::RNG (multiply-with-carry) as used by the degenerate fallback (src/pf2DRao.cpp:179-192)
+struct mkf_cvrng {
+    uint64_t state;
+    __device__ __forceinline__ explicit mkf_cvrng(uint64_t s) : state(s ? s : 0xffffffffull) {}
+    __device__ __forceinline__ unsigned next()
+    {
+        state = (uint64_t)(unsigned)state * 4164903690u + (unsigned)(state >> 32);
+        return (unsigned)state;
+    }
+    __device__ __forceinline__ int uniform_int(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + a); }
+    __device__ __forceinline__ double uniform_dbl()
+    {
+        unsigned t = next();
+        return __dmul_rn((double)(((uint64_t)t << 32) | next()), 5.4210108624275221700372640043497e-20);
+    }
+};
+
+// the literal sequential loop (bit-exact by construction); w(i) yields the i-th weight
+template <class WF>
+__device__ __forceinline__ void mkf_resample_sequential(WF w, int L, int N, double u, int32_t* out)
+{
+    int idx = 0;
+    const double step = __ddiv_rn(1.0, (double)N);
+    double beta = __dmul_rn(u, step);
+    double wi = w(0);
+    for (int i = 0; i < N; i++) {
+        while (beta > wi) {
+            beta = __dsub_rn(beta, wi);
+            idx = (idx + 1) % L;
+            wi = w(idx);
+        }
+        beta = __dadd_rn(beta, step);
+        out[i] = idx;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy global -> shared with mbarrier completion (sm_90+/sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mkf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mkf_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mkf_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mkf_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mkf_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mkf_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     mkf_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(mkf_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mkf_mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    uint32_t ok = 0;
+    const uint32_t a = mkf_smem_u32(bar);
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, "
+                     "p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(a), "r"(phase)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp / block collectives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ dd dd_shfl_up(dd v, int delta)
+{
+    dd r;
+    r.hi = __shfl_up_sync(0xffffffffu, v.hi, delta);
+    r.lo = __shfl_up_sync(0xffffffffu, v.lo, delta);
+    return r;
+}
+__device__ __forceinline__ dd dd_shfl_xor(dd v, int m)
+{
+    dd r;
+    r.hi = __shfl_xor_sync(0xffffffffu, v.hi, m);
+    r.lo = __shfl_xor_sync(0xffffffffu, v.lo, m);
+    return r;
+}
+
+// block-wide exclusive scan of one dd per thread; also returns the block total.
+// scratch: BT/32 dd entries of shared memory.  All BT threads must call.
+template <int BT>
+__device__ __forceinline__ dd mkf_block_excl_scan_dd(dd v, dd* scratch, dd& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    dd inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        dd n = dd_shfl_up(inc, o);
+        if (lane >= o) inc = dd_add(n, inc);
+    }
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    dd pre = dd_make(0.0), tot = dd_make(0.0);
+#pragma unroll
+    for (int w = 0; w < BT / 32; w++) {
+        dd s = scratch[w];
+        if (w < wid) pre = dd_add(pre, s);
+        tot = dd_add(tot, s);
+    }
+    __syncthreads();
+    total = tot;
+    dd prev = dd_shfl_up(inc, 1);
+    if (lane == 0) prev = dd_make(0.0);
+    return dd_add(pre, prev);
+}
+
+// block-wide exclusive max-scan of one int per thread (identity -1); returns block max in total
+template <int BT>
+__device__ __forceinline__ int mkf_block_excl_scan_max(int v, int* scratch, int& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, n);
+    }
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    int pre = -1, tot = -1;
+#pragma unroll
+    for (int w = 0; w < BT / 32; w++) {
+        int s = scratch[w];
+        if (w < wid) pre = max(pre, s);
+        tot = max(tot, s);
+    }
+    __syncthreads();
+    total = tot;
+    int prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prev = -1;
+    return max(pre, prev);
+}
+
+#endif

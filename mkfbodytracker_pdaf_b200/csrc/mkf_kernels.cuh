@@ -1,0 +1,751 @@
+// mkf_kernels.cuh -- sm_100a kernels of the RBPF hot path (included by mkf_api.cu).
+//
+//   k_indicator_bounds  K->N systematic resample of the GMM prior weights     src/pf2DRao.cpp:128
+//   k_slot_update       fused gather-by-parent + KF predict + innovation      src/pf2DRao.cpp:134-142
+//                       likelihood + KF update, one thread per slot           src/KF_model.cpp:11-25
+//                                                                              src/pf2DRao.cpp:34-67
+//   k_resample_block    weight sum/normalise + N->N (or C->N) resample        src/pf2DRao.cpp:145-152,175-210
+//   k_resample_small    same, one thread per track, literal loop (small N)
+//   k_resample_fallback literal loop / cv::RNG fallback for flagged tracks    src/pf2DRao.cpp:184-207
+//   k_estimate          getEstimator + PCA reconstruction                      src/pf2DRao.cpp:23-31, src/pfPose.cpp:347-348
+//   k_reset / k_upload / k_download / k_aux_outputs : state I/O in reference coordinates
+//
+// Data layout: slot state lives in "tiles" of 32 consecutive global slots,
+// tile[pair p][lane] as double2, so a warp reading pair p of 32 neighbouring slots touches
+// 512 contiguous bytes.  Global slot index s = track * N + j.
+#ifndef MKF_KERNELS_CUH
+#define MKF_KERNELS_CUH
+
+#include <float.h>
+
+#include "mkf_device.cuh"
+#include "../../include/mkf_synth.h"
+
+#define MKF_M 6
+
+template <int D>
+struct SlotLay {
+    static constexpr int M = MKF_M;
+    static constexpr int D2 = D - M;
+    static constexpr int NA = M * (M + 1) / 2;
+    static constexpr int NB = D2 * M;
+    static constexpr int NC = D2 * (D2 + 1) / 2;
+    static constexpr int NE = D + NA + NB + NC;
+    static constexpr int NP = (NE + 1) / 2;
+    static constexpr int OA = D;
+    static constexpr int OB = D + NA;
+    static constexpr int OC = D + NA + NB;
+    static constexpr int CS = (2 + NE + 1) / 2 * 2;
+};
+
+__host__ __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; } // i >= j
+
+struct SlotArgs {
+    const double2* __restrict__ st_in;
+    double2* __restrict__ st_out;
+    const int32_t* __restrict__ parent; // T*N, local index of the parent slot
+    const int32_t* __restrict__ bounds; // T x (K+2): e_0..e_{K-1}, wrap_from, wrap_k
+    const double* __restrict__ meas;
+    const double* __restrict__ comp_const; // K x CS (global; staged to shared memory by TMA)
+    double* __restrict__ w_raw;
+    uint32_t* __restrict__ status;
+    long long total; // T*N
+    int N, K, meas_layout, chol_mode;
+    double bh[MKF_M];
+    double r; // measurement noise variance (R = r * I)
+};
+
+// -----------------------------------------------------------------------------------------
+// the per-slot arithmetic in the measurement-aligned basis (H' = [I 0]):
+//   predict      x <- g x + b',  P <- g^2 P + Q'
+//   innovation   y = (z - BH) - x1,  S = A + r I   (A = P11)
+//   likelihood   pseudo-Cholesky of src/pf2DRao.cpp:34-67 (chol_mode)
+//   update       W = S^-1; x1 += y - r W y; x2 += B W y;
+//                A <- r I - r^2 W;  B <- r (W B^T)^T;  C <- C - B W B^T
+// returns false when cv::Cholesky would have failed (pivot < DBL_EPSILON)
+// -----------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ bool slot_math(double (&v)[SlotLay<D>::NE], const double* __restrict__ c,
+                                          const double (&zc)[MKF_M], const double r, const int chol_mode, double& w_out)
+{
+    using L = SlotLay<D>;
+    constexpr int M = MKF_M;
+#define A_(i, j) v[L::OA + tri((i), (j))]
+#define B_(i, a) v[L::OB + (i) * M + (a)]
+#define C_(i, j) v[L::OC + tri((i), (j))]
+    const double g = c[0], g2 = c[1];
+#pragma unroll
+    for (int e = 0; e < D; e++) v[e] = fma(g, v[e], c[2 + e]);
+#pragma unroll
+    for (int e = D; e < L::NE; e++) v[e] = fma(g2, v[e], c[2 + e]);
+
+    double y[M];
+#pragma unroll
+    for (int a = 0; a < M; a++) y[a] = zc[a] - v[a];
+
+    // Cholesky of S = A + r I: Lm lower (strict), inv[i] = 1/L_ii  (cv::Cholesky, CholImpl)
+    double Lm[L::NA], inv[M];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+            double s = A_(i, j);
+#pragma unroll
+            for (int k = 0; k < j; k++) s = fma(-Lm[tri(i, k)], Lm[tri(j, k)], s);
+            Lm[tri(i, j)] = s * inv[j];
+        }
+        double s = A_(i, i) + r;
+#pragma unroll
+        for (int k = 0; k < i; k++) s = fma(-Lm[tri(i, k)], Lm[tri(i, k)], s);
+        if (s < DBL_EPSILON) ok = false;
+        inv[i] = rsqrt(s);
+        Lm[tri(i, i)] = s * inv[i]; // L_ii
+    }
+
+    // likelihood: v = y^T Rt^-1 by forward substitution, w = exp(-q/2 - sum log Rt_ee - 3 log 2pi)
+    {
+        double vv[M], ve[M], q = 0.0, pinv = 1.0;
+        if (chol_mode == MKF_CHOL_EXACT) {
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                double acc = y[j];
+#pragma unroll
+                for (int e = 0; e < j; e++) acc = fma(-vv[e], Lm[tri(j, e)], acc);
+                vv[j] = acc * inv[j];
+                q = fma(vv[j], vv[j], q);
+                pinv *= inv[j];
+            }
+        } else {
+            // Rt_ee = 1/elem_e, Rt_ej = S_ej * elem_e (j > e); elem = 1/L_ee (OpenCV 2.4) or L_ee (>= 3.0)
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                const double elem = (chol_mode == MKF_CHOL_CV24_LITERAL) ? inv[j] : Lm[tri(j, j)];
+                double acc = y[j];
+#pragma unroll
+                for (int e = 0; e < j; e++) acc = fma(-ve[e], A_(j, e), acc);
+                vv[j] = acc * elem;
+                ve[j] = vv[j] * elem;
+                q = fma(vv[j], vv[j], q);
+                pinv *= elem;
+            }
+        }
+        // sum_e log Rt_ee = -log(prod elem)
+        w_out = exp(fma(-0.5, q, log(pinv)) - 5.5136311992280356); // 3*log(2*pi)
+    }
+
+    // W = S^-1 = Linv^T Linv
+    double Li[L::NA], W[L::NA];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        Li[tri(i, i)] = inv[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = j; k < i; k++) s = fma(Lm[tri(i, k)], Li[tri(k, j)], s);
+            Li[tri(i, j)] = -s * inv[i];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < M; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = a; k < M; k++) s = fma(Li[tri(k, a)], Li[tri(k, b)], s);
+            W[tri(a, b)] = s;
+        }
+#define W_(a, b) W[((a) >= (b)) ? tri((a), (b)) : tri((b), (a))]
+
+    // state mean
+    double t[M];
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < M; b++) s = fma(W_(a, b), y[b], s);
+        t[a] = s;
+    }
+#pragma unroll
+    for (int a = 0; a < M; a++) v[a] += fma(-r, t[a], y[a]);
+#pragma unroll
+    for (int i = 0; i < L::D2; i++) {
+        double s = v[M + i];
+#pragma unroll
+        for (int a = 0; a < M; a++) s = fma(B_(i, a), t[a], s);
+        v[M + i] = s;
+    }
+
+    // covariance
+#pragma unroll
+    for (int j = 0; j < L::D2; j++) {
+        double G[M];
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < M; b++) s = fma(W_(a, b), B_(j, b), s);
+            G[a] = s;
+        }
+#pragma unroll
+        for (int i = j; i < L::D2; i++) {
+            double s = C_(i, j);
+#pragma unroll
+            for (int a = 0; a < M; a++) s = fma(-B_(i, a), G[a], s);
+            C_(i, j) = s;
+        }
+#pragma unroll
+        for (int a = 0; a < M; a++) B_(j, a) = r * G[a];
+    }
+    const double r2 = r * r;
+#pragma unroll
+    for (int a = 0; a < M; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) A_(a, b) = fma(-r2, W[tri(a, b)], (a == b) ? r : 0.0);
+#undef A_
+#undef B_
+#undef C_
+#undef W_
+    return ok;
+}
+
+// component of local slot j from the run boundaries written by k_indicator_bounds
+__device__ __forceinline__ int mkf_component_of(const int32_t* __restrict__ bt, int K, int j)
+{
+    int k = 0;
+    for (int q = 0; q < K - 1; q++) k += (j >= __ldg(bt + q)) ? 1 : 0;
+    if (j >= __ldg(bt + K)) k = __ldg(bt + K + 1);
+    return k;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
+{
+    using L = SlotLay<D>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cst = reinterpret_cast<double*>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+
+    const uint32_t cbytes = (uint32_t)(a.K * L::CS * sizeof(double));
+    if (threadIdx.x == 0) mkf_mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mkf_mbar_expect_tx(&mbar, cbytes);
+        mkf_tma_load_1d(cst, a.comp_const, cbytes, &mbar);
+    }
+
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = s < a.total;
+    double v[L::NE];
+    double zc[MKF_M];
+    int k = 0;
+    long long t = 0;
+    if (active) {
+        t = s / a.N;
+        const int j = (int)(s - t * a.N);
+        const long long sp = t * a.N + __ldg(a.parent + s);
+        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+#pragma unroll
+        for (int p = 0; p < L::NP; p++) {
+            const double2 q = __ldg(src + p * 32);
+            v[2 * p] = q.x;
+            if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+        }
+        if (a.meas_layout == MKF_MEAS_SHARED) {
+#pragma unroll
+            for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + t * MKF_M + r) - a.bh[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + (t * MKF_M + r) * a.N + j) - a.bh[r];
+        }
+        k = mkf_component_of(a.bounds + t * (a.K + 2), a.K, j);
+    }
+    mkf_mbar_wait(&mbar, 0);
+    if (!active) return;
+
+    double w;
+    const bool ok = slot_math<D>(v, cst + k * L::CS, zc, a.r, a.chol_mode, w);
+    if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+
+    double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+#pragma unroll
+    for (int p = 0; p < L::NP; p++) {
+        double2 q;
+        q.x = v[2 * p];
+        q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+        __stcs(dst + p * 32, q);
+    }
+    a.w_raw[s] = w;
+}
+
+// -----------------------------------------------------------------------------------------
+// K -> N indicator resample: per-track run boundaries e_k = #{j : indicator_j <= k}
+// one thread per track.  bounds[t] = { e_0..e_{K-1}, wrap_from, wrap_k }
+// -----------------------------------------------------------------------------------------
+__global__ void k_indicator_bounds(const double* __restrict__ u, long long T, int N, int K,
+                                   const double* __restrict__ cw_hi, const double* __restrict__ cw_lo,
+                                   const double* __restrict__ wprior, double wmax, int32_t* __restrict__ bounds,
+                                   uint32_t* __restrict__ status)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const double step = __ddiv_rn(1.0, (double)N);
+    const double uu = u[t];
+    const double beta0 = __dmul_rn(uu, step);
+    const double tol = mkf_resample_tol(N, K, wmax, step);
+    int32_t* bt = bounds + t * (K + 2);
+    bool amb = false;
+    int e = 0;
+    for (int k = 0; k < K; k++) {
+        dd C;
+        C.hi = cw_hi[k];
+        C.lo = cw_lo[k];
+        e = mkf_count_le(C, beta0, step, N, tol, amb);
+        bt[k] = e;
+    }
+    bt[K] = N;
+    bt[K + 1] = 0;
+    if (e < N) amb = true; // thresholds beyond the total prior mass: the literal loop wraps around
+    if (!amb) return;
+    // literal loop (src/pf2DRao.cpp:195-207) -> counts per component
+    uint32_t st = MKF_ST_IND_FALLBACK;
+    for (int k = 0; k < K; k++) bt[k] = 0;
+    int idx = 0, wraps = 0, wrap_from = N, wrap_k = 0;
+    double beta = beta0;
+    double wi = wprior[0];
+    for (int i = 0; i < N; i++) {
+        while (beta > wi) {
+            beta = __dsub_rn(beta, wi);
+            idx++;
+            if (idx == K) {
+                idx = 0;
+                wraps++;
+            }
+            wi = wprior[idx];
+        }
+        beta = __dadd_rn(beta, step);
+        if (wraps == 0) {
+            bt[idx] = i + 1; // last output index + 1 holding component <= idx (filled below)
+        } else if (wrap_from == N) {
+            wrap_from = i;
+            wrap_k = idx;
+            st |= MKF_ST_IND_WRAP;
+        }
+    }
+    // bt[k] currently: (last i with component k) + 1, or 0 if unused -> make cumulative
+    int run = 0;
+    for (int k = 0; k < K; k++) {
+        if (bt[k] > run) run = bt[k];
+        bt[k] = run;
+    }
+    for (int k = 0; k < K; k++)
+        if (bt[k] > wrap_from) bt[k] = wrap_from;
+    bt[K - 1] = (wrap_from < N) ? wrap_from : N;
+    bt[K] = wrap_from;
+    bt[K + 1] = wrap_k;
+    atomicOr(status + t, st);
+}
+
+// -----------------------------------------------------------------------------------------
+// per-track weight normalisation + systematic resampling, one CTA per track
+//   w_raw : T x L raw weights; out: T x N parents; wsum: T
+// -----------------------------------------------------------------------------------------
+template <int BT, int ITEMS>
+__global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict__ w_all, int L, int N,
+                                                        const double* __restrict__ u, int u_stride, int normalise,
+                                                        double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
+                                                        uint32_t* __restrict__ status, int status_stride,
+                                                        uint32_t* __restrict__ need_fb, uint32_t bit_fb,
+                                                        uint32_t bit_deg)
+{
+    __shared__ dd sc_dd[BT / 32];
+    __shared__ int sc_i[BT / 32];
+    __shared__ double sc_d[BT / 32];
+    __shared__ int sh_flag;
+    const long long t = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double* __restrict__ w = w_all + t * L;
+    int32_t* __restrict__ out = out_all + t * N;
+
+    // pass 1: exact (double-double) sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172)
+    dd acc = dd_make(0.0);
+    double mx = 0.0;
+    for (int i = tid; i < L; i += BT) {
+        const double x = w[i];
+        acc = dd_add_d(acc, x);
+        if (x > mx) mx = x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc = dd_add(acc, dd_shfl_xor(acc, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+        sc_dd[wid] = acc;
+        sc_d[wid] = mx;
+    }
+    if (tid == 0) sh_flag = 0;
+    __syncthreads();
+    acc = dd_make(0.0);
+    mx = 0.0;
+#pragma unroll
+    for (int q = 0; q < BT / 32; q++) {
+        acc = dd_add(acc, sc_dd[q]);
+        mx = fmax(mx, sc_d[q]);
+    }
+    __syncthreads();
+    const double wsum = normalise ? acc.hi : 1.0;
+    if (tid == 0 && wsum_out) wsum_out[t] = acc.hi;
+    const double wmax_n = normalise ? __ddiv_rn(mx, wsum) : mx;
+    if (!(wmax_n > 0.0)) { // max weight 0 / NaN -> random-index fallback (src/pf2DRao.cpp:184-192)
+        if (tid == 0) {
+            need_fb[t] = 1u;
+            atomicOr(status + t * status_stride, bit_deg);
+        }
+        return;
+    }
+    const double step = __ddiv_rn(1.0, (double)N);
+    const double beta0 = __dmul_rn(u[t * u_stride], step);
+    const double tol = mkf_resample_tol(N, L, wmax_n, step);
+
+    for (int i = tid; i < N; i += BT) out[i] = -1;
+    __syncthreads();
+
+    // pass 2: double-double prefix sums of the normalised weights -> child ranges
+    dd carry = dd_make(0.0);
+    bool amb = false;
+    for (int base = 0; base < L; base += BT * ITEMS) {
+        const int i0 = base + tid * ITEMS;
+        dd pre[ITEMS];
+        dd run = dd_make(0.0);
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) {
+            double x = (i0 + q < L) ? w[i0 + q] : 0.0;
+            if (normalise) x = __ddiv_rn(x, wsum);
+            run = dd_add_d(run, x);
+            pre[q] = run;
+        }
+        dd tile_tot;
+        dd excl = mkf_block_excl_scan_dd<BT>(run, sc_dd, tile_tot);
+        const dd start = dd_add(carry, excl);
+        int e_prev = 0; // e_{-1} = 0 by definition: no output precedes the first weight
+        if (i0 > 0 && i0 < L) e_prev = mkf_count_le(start, beta0, step, N, tol, amb);
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) {
+            if (i0 + q < L) {
+                const int e = mkf_count_le(dd_add(start, pre[q]), beta0, step, N, tol, amb);
+                if (e > e_prev) out[e_prev] = i0 + q;
+                if (i0 + q == L - 1 && e < N) amb = true; // literal loop would wrap past the last weight
+                e_prev = e;
+            }
+        }
+        carry = dd_add(carry, tile_tot);
+    }
+    if (amb) sh_flag = 1;
+    __syncthreads();
+    if (sh_flag) {
+        if (tid == 0) {
+            need_fb[t] = 1u;
+            atomicOr(status + t * status_stride, bit_fb);
+        }
+        return;
+    }
+    // fill: inclusive max-scan of the head markers
+    int carry_max = -1;
+    for (int base = 0; base < N; base += BT * ITEMS) {
+        const int i0 = base + tid * ITEMS;
+        int loc[ITEMS];
+        int run = -1;
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) {
+            const int h = (i0 + q < N) ? out[i0 + q] : -1;
+            run = max(run, h);
+            loc[q] = run;
+        }
+        int tile_max;
+        const int excl = mkf_block_excl_scan_max<BT>(run, sc_i, tile_max);
+        const int pre = max(carry_max, excl);
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++)
+            if (i0 + q < N) out[i0 + q] = max(pre, loc[q]);
+        carry_max = max(carry_max, tile_max);
+    }
+}
+
+// one thread per track, literal sequential semantics throughout (sequential wsum as the
+// reference, src/pf2DRao.cpp:139; then the loop of :195-207).  Used when N and L are small.
+__global__ void k_resample_small(const double* __restrict__ w_all, long long T, int L, int N,
+                                 const double* __restrict__ u, int u_stride, int normalise,
+                                 double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
+                                 uint32_t* __restrict__ status, int status_stride, uint32_t* __restrict__ need_fb,
+                                 uint32_t bit_deg)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const double* __restrict__ w = w_all + t * L;
+    double wsum = 0.0;
+    for (int i = 0; i < L; i++) wsum = __dadd_rn(wsum, w[i]);
+    if (wsum_out) wsum_out[t] = wsum;
+    if (!normalise) wsum = 1.0;
+    double mw = 0.0;
+    for (int i = 0; i < L; i++) {
+        const double x = normalise ? __ddiv_rn(w[i], wsum) : w[i];
+        if (x > mw) mw = x;
+    }
+    if (!(mw > 0.0)) {
+        need_fb[t] = 1u;
+        atomicOr(status + t * status_stride, bit_deg);
+        return;
+    }
+    auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
+    mkf_resample_sequential(wf, L, N, u[t * u_stride], out_all + t * N);
+}
+
+// flagged tracks: literal loop on the same normalised weights, or the cv::RNG random-index
+// fallback when the maximum weight is 0 / NaN.  One thread per track.
+__global__ void k_resample_fallback(const double* __restrict__ w_all, long long T, int L, int N,
+                                    const double* __restrict__ u, int u_stride, int normalise,
+                                    const double* __restrict__ wsum_in, int32_t* __restrict__ out_all,
+                                    const uint64_t* __restrict__ seeds, int seed_stride, int seed_off,
+                                    uint32_t* __restrict__ need_fb)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T || !need_fb[t]) return;
+    need_fb[t] = 0u;
+    const double* __restrict__ w = w_all + t * L;
+    int32_t* out = out_all + t * N;
+    const double wsum = normalise ? wsum_in[t] : 1.0;
+    double mw = 0.0;
+    for (int i = 0; i < L; i++) {
+        const double x = normalise ? __ddiv_rn(w[i], wsum) : w[i];
+        if (x > mw) mw = x;
+    }
+    if (!(mw > 0.0)) {
+        mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
+        (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
+        for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
+        return;
+    }
+    auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
+    mkf_resample_sequential(wf, L, N, u[t * u_stride], out);
+}
+
+// -----------------------------------------------------------------------------------------
+// getEstimator + reconstruction: one CTA per track
+// -----------------------------------------------------------------------------------------
+template <int D, int BT>
+__global__ void __launch_bounds__(BT) k_estimate(const double2* __restrict__ st, const int32_t* __restrict__ parent,
+                                                  int N, int Dpose, const double* __restrict__ recon,
+                                                  const double* __restrict__ pmean, const double* __restrict__ tinv,
+                                                  double* __restrict__ xbar_out, double* __restrict__ pose_out)
+{
+    using L = SlotLay<D>;
+    __shared__ double red[BT / 32][D];
+    __shared__ double xb[D];
+    const long long t = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double acc[D];
+#pragma unroll
+    for (int e = 0; e < D; e++) acc[e] = 0.0;
+    for (int j = tid; j < N; j += BT) {
+        const long long sp = t * N + __ldg(parent + t * N + j);
+        const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+#pragma unroll
+        for (int p = 0; p < D / 2; p++) {
+            const double2 q = __ldg(src + p * 32);
+            acc[2 * p] += q.x;
+            acc[2 * p + 1] += q.y;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < D; e++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < D; e++) red[wid][e] = acc[e];
+    }
+    __syncthreads();
+    if (tid < D) {
+        double s = 0.0;
+        for (int q = 0; q < BT / 32; q++) s += red[q][tid];
+        xb[tid] = s * (1.0 / (double)N);
+    }
+    __syncthreads();
+    if (pose_out && tid < Dpose) {
+        double s = 0.0;
+        for (int c = 0; c < D; c++) s = fma(recon[tid * D + c], xb[c], s);
+        pose_out[t * Dpose + tid] = s + pmean[tid];
+    }
+    if (xbar_out && tid < D) {
+        double s = 0.0;
+        for (int c = 0; c < D; c++) s = fma(tinv[tid * D + c], xb[c], s);
+        xbar_out[t * D + tid] = s;
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// state I/O
+// -----------------------------------------------------------------------------------------
+// resetTracker (src/my_gmm.cpp:30-42): slot j <- (mu_k, Sigma_k) of its drawn component
+template <int D>
+__global__ void k_reset(double2* __restrict__ st, int32_t* __restrict__ parent, const int32_t* __restrict__ bounds,
+                        const double* __restrict__ init_const, long long total, int N, int K)
+{
+    using L = SlotLay<D>;
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const long long t = s / N;
+    const int j = (int)(s - t * N);
+    const int k = mkf_component_of(bounds + t * (K + 2), K, j);
+    const double* __restrict__ ic = init_const + (long long)k * L::NE;
+    double2* __restrict__ dst = st + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+    for (int p = 0; p < L::NP; p++) {
+        double2 q;
+        q.x = ic[2 * p];
+        q.y = (2 * p + 1 < L::NE) ? ic[2 * p + 1] : 0.0;
+        dst[p * 32] = q;
+    }
+    parent[s] = j;
+}
+
+template <int D>
+__device__ __forceinline__ int packed_index_dev(int r, int c)
+{
+    using L = SlotLay<D>;
+    if (r < c) {
+        int tmp = r;
+        r = c;
+        c = tmp;
+    }
+    if (r < MKF_M) return tri(r, c);
+    if (c < MKF_M) return L::NA + (r - MKF_M) * MKF_M + c;
+    return L::NA + L::NB + tri(r - MKF_M, c - MKF_M);
+}
+
+// reference coordinates -> device layout:  x' = T x,  P' = T sym(P) T^T
+template <int D>
+__global__ void k_upload(double2* __restrict__ st, int32_t* __restrict__ parent, const double* __restrict__ x,
+                         const double* __restrict__ P, const double* __restrict__ Tm, long long total, int N)
+{
+    using L = SlotLay<D>;
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    double v[L::NP * 2];
+    v[L::NP * 2 - 1] = 0.0;
+    const double* xs = x + s * D;
+    const double* Ps = P + s * D * D;
+    for (int r = 0; r < D; r++) {
+        double acc = 0.0;
+        for (int c = 0; c < D; c++) acc = fma(Tm[r * D + c], xs[c], acc);
+        v[r] = acc;
+    }
+    double TP[D * D];
+    for (int r = 0; r < D; r++)
+        for (int c = 0; c < D; c++) {
+            double acc = 0.0;
+            for (int k = 0; k < D; k++) acc = fma(Tm[r * D + k], 0.5 * (Ps[k * D + c] + Ps[c * D + k]), acc);
+            TP[r * D + c] = acc;
+        }
+    for (int r = 0; r < D; r++)
+        for (int c = 0; c <= r; c++) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int k = 0; k < D; k++) {
+                a1 = fma(TP[r * D + k], Tm[c * D + k], a1);
+                a2 = fma(TP[c * D + k], Tm[r * D + k], a2);
+            }
+            v[D + packed_index_dev<D>(r, c)] = 0.5 * (a1 + a2);
+        }
+    double2* __restrict__ dst = st + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+    for (int p = 0; p < L::NP; p++) {
+        double2 q;
+        q.x = v[2 * p];
+        q.y = v[2 * p + 1];
+        dst[p * 32] = q;
+    }
+    parent[s] = (int)(s % N);
+}
+
+// device layout (through the parent gather) -> reference coordinates
+template <int D>
+__global__ void k_download(const double2* __restrict__ st, const int32_t* __restrict__ parent,
+                           const double* __restrict__ Ti, double* __restrict__ x, double* __restrict__ P,
+                           long long total, int N)
+{
+    using L = SlotLay<D>;
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const long long t = s / N;
+    const long long sp = t * N + parent[s];
+    const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+    double v[L::NP * 2];
+    for (int p = 0; p < L::NP; p++) {
+        const double2 q = src[p * 32];
+        v[2 * p] = q.x;
+        v[2 * p + 1] = q.y;
+    }
+    if (x) {
+        for (int r = 0; r < D; r++) {
+            double acc = 0.0;
+            for (int c = 0; c < D; c++) acc = fma(Ti[r * D + c], v[c], acc);
+            x[s * D + r] = acc;
+        }
+    }
+    if (P) {
+        double TP[D * D];
+        for (int r = 0; r < D; r++)
+            for (int c = 0; c < D; c++) {
+                double acc = 0.0;
+                for (int k = 0; k < D; k++) acc = fma(Ti[r * D + k], v[D + packed_index_dev<D>(k, c)], acc);
+                TP[r * D + c] = acc;
+            }
+        for (int r = 0; r < D; r++)
+            for (int c = 0; c < D; c++) {
+                double acc = 0.0;
+                for (int k = 0; k < D; k++) acc = fma(TP[r * D + k], Ti[c * D + k], acc);
+                P[(s * D + r) * D + c] = acc;
+            }
+    }
+}
+
+// w_norm = w_raw / wsum (src/pf2DRao.cpp:145-148) and the per-slot component indicators
+__global__ void k_aux_outputs(const double* __restrict__ w_raw, const double* __restrict__ wsum,
+                              const int32_t* __restrict__ bounds, long long total, int N, int K,
+                              double* __restrict__ w_norm, int32_t* __restrict__ indicators)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const long long t = s / N;
+    if (w_norm) w_norm[s] = __ddiv_rn(w_raw[s], wsum[t]);
+    if (indicators) indicators[s] = mkf_component_of(bounds + t * (K + 2), K, (int)(s - t * N));
+}
+
+// synthetic workload of include/mkf_synth.h generated in place (bench / large-batch tests)
+__global__ void k_synth_fill(uint64_t seed, long long track0, uint64_t frame, int jitter, int meas_layout, long long T,
+                             int N, double* __restrict__ meas, double* __restrict__ u_ind, double* __restrict__ u_post)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (meas_layout == MKF_MEAS_SHARED) {
+        if (i >= T) return;
+        double z[6];
+        mkf_synth_meas(seed, (uint64_t)(track0 + i), frame, -1, jitter, z);
+        for (int r = 0; r < 6; r++) meas[i * 6 + r] = z[r];
+        if (u_ind) u_ind[i] = mkf_synth_u(seed, (uint64_t)(track0 + i), frame, MKF_SYNTH_LANE_U_IND);
+        if (u_post) u_post[i] = mkf_synth_u(seed, (uint64_t)(track0 + i), frame, MKF_SYNTH_LANE_U_POST);
+    } else {
+        if (i >= T * N) return;
+        const long long t = i / N;
+        const int j = (int)(i - t * N);
+        double z[6];
+        mkf_synth_meas(seed, (uint64_t)(track0 + t), frame, j, jitter, z);
+        for (int r = 0; r < 6; r++) meas[(t * 6 + r) * N + j] = z[r];
+        if (j == 0) {
+            if (u_ind) u_ind[t] = mkf_synth_u(seed, (uint64_t)(track0 + t), frame, MKF_SYNTH_LANE_U_IND);
+            if (u_post) u_post[t] = mkf_synth_u(seed, (uint64_t)(track0 + t), frame, MKF_SYNTH_LANE_U_POST);
+        }
+    }
+}
+
+#endif

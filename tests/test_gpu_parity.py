@@ -1,0 +1,288 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, libmkf_b200.so) against the CPU oracle on
+identical inputs and identical uniform draws.  Tolerances from BASELINE.json:north_star: resampled
+indices bit-exact; means, covariances and weights within 1e-4 relative (helpers.RTOL)."""
+import os
+
+import numpy as np
+import pytest
+
+import mkf_oracle as orc
+import mkfbodytracker_pdaf_b200 as mk
+from helpers import RTOL, rel_err, rel_err_weights, synth_frame, synth_u_init
+from mkfbodytracker_pdaf_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def oracle_filters(arm, T, N, u_init, chol=orc.CHOL_CV24_LITERAL):
+    fs = [orc.Filter(arm.orc, N, chol_mode=chol) for _ in range(T)]
+    for f, u in zip(fs, u_init):
+        f.reset(u=u)
+    return fs
+
+
+def compare_frame(b, fs, res, check_state=True):
+    """compare one frame of GPU batch b with oracle results res (list of dicts)"""
+    d = b.download(state=check_state, cov=check_state)
+    T = len(fs)
+    stats = dict(idx_mismatch=0, ind_mismatch=0, w=0.0, x=0.0, P=0.0)
+    for t in range(T):
+        stats["ind_mismatch"] += int((d["indicators"][t] != res[t]["indicators"]).sum())
+        stats["idx_mismatch"] += int((d["parents"][t] != res[t]["parents"]).sum())
+        stats["w"] = max(stats["w"], rel_err_weights(d["w_raw"][t], res[t]["w_raw"]),
+                         rel_err_weights(d["w_norm"][t], res[t]["w_norm"]),
+                         abs(d["wsum"][t] - res[t]["wsum"]) / res[t]["wsum"])
+        if check_state:
+            xo, Po = fs[t].get_state()
+            stats["x"] = max(stats["x"], rel_err(d["x"][t], xo))
+            stats["P"] = max(stats["P"], rel_err(d["P"][t], Po))
+    return stats, d
+
+
+def assert_parity(stats):
+    assert stats["ind_mismatch"] == 0, stats
+    assert stats["idx_mismatch"] == 0, stats
+    assert stats["w"] <= RTOL and stats["x"] <= RTOL and stats["P"] <= RTOL, stats
+
+
+def test_reset_matches_oracle(left_arm):
+    T, N = 7, 500
+    u = np.linspace(0.03, 0.97, T)
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    b.reset(u)
+    d = b.download()
+    fs = oracle_filters(left_arm, T, N, u)
+    for t in range(T):
+        xo, Po = fs[t].get_state()
+        assert rel_err(d["x"][t], xo) <= 1e-12 and rel_err(d["P"][t], Po) <= 1e-12
+        want, _ = orc.resample(left_arm.np.weights, N, u[t])
+        assert np.array_equal(d["indicators"][t], want)
+        assert np.array_equal(d["parents"][t], np.arange(N))
+
+
+def test_upload_download_roundtrip(left_arm, rng):
+    T, N, d = 3, 70, 12
+    x = rng.standard_normal((T, N, d)) * 50
+    A = rng.standard_normal((T, N, d, d))
+    P = A @ A.transpose(0, 1, 3, 2) * 30 + np.eye(d)
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    b.upload(x, P)
+    out = b.download()
+    assert rel_err(out["x"], x) <= 1e-13 and rel_err(out["P"], P) <= 1e-13
+
+
+@pytest.mark.parametrize("N,shared", [(500, False), (500, True), (15, True), (33, False), (1200, True)])
+def test_teacher_forced_frames(left_arm, N, shared):
+    """T1: every frame starts from the oracle's state (uploaded), so errors cannot accumulate"""
+    T, seed = 5, 0x5EED0002
+    tracks = list(range(T))
+    u0 = synth_u_init(seed, tracks)
+    fs = oracle_filters(left_arm, T, N, u0)
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    worst = dict(w=0, x=0, P=0)
+    for fr in range(6):
+        xs, Ps = zip(*[f.get_state() for f in fs])
+        b.upload(np.stack(xs), np.stack(Ps))
+        meas, ui, up = synth_frame(seed, tracks, fr, None if shared else N)
+        res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+        b.update(meas, ui, up)
+        stats, d = compare_frame(b, fs, res)
+        assert_parity(stats)
+        assert not (d["status"] & (L.ST_POST_DEGENERATE | L.ST_CHOL_FAIL)).any()
+        for k in worst:
+            worst[k] = max(worst[k], stats[k])
+    print(f"teacher-forced N={N} shared={shared}: worst rel err {worst}")
+    assert worst["w"] < 1e-9 and worst["x"] < 1e-9 and worst["P"] < 1e-9  # expected ~1e-13; 1e-4 is the contract
+
+
+def test_config1_free_running_300_frames(left_arm):
+    """T2: BASELINE config 1 -- 1 track, N=500, 300 frames, per-slot columns, free-running"""
+    seed, N, frames = 0x5EED0001, 500, 300
+    u0 = synth_u_init(seed, [0])
+    fs = oracle_filters(left_arm, 1, N, u0)
+    b = mk.TrackBatch(left_arm.mk, 1, N)
+    b.reset(u0)
+    gold = np.load(os.path.join(GOLD, "config1_left.npz"))
+    mism = 0
+    worst = dict(w=0.0, x=0.0, P=0.0, pose=0.0)
+    for fr in range(frames):
+        meas, ui, up = synth_frame(seed, [0], fr, N, jitter=0)
+        res = [fs[0].update(meas[0], ui[0], up[0])]
+        b.update(meas, ui, up)
+        check_state = fr % 25 == 0 or fr == frames - 1
+        stats, d = compare_frame(b, fs, res, check_state)
+        mism += stats["idx_mismatch"] + stats["ind_mismatch"]
+        for k in ("w", "x", "P"):
+            worst[k] = max(worst[k], stats[k])
+        _, pose = b.estimate()
+        worst["pose"] = max(worst["pose"], float(np.abs(pose[0] - gold["pose"][fr]).max() / np.abs(gold["pose"][fr]).max()))
+        if f"parents_{fr}" in gold.files:
+            assert np.array_equal(d["parents"][0], gold[f"parents_{fr}"])
+            assert np.array_equal(d["indicators"][0], gold[f"indicators_{fr}"])
+            assert rel_err_weights(d["w_norm"][0], gold[f"w_norm_{fr}"]) <= RTOL
+    print(f"config 1 free-running: index mismatches {mism}, worst rel err {worst}")
+    assert mism == 0
+    assert max(worst.values()) <= RTOL
+    out = b.download()
+    assert rel_err(out["x"][0], gold["x_final"]) <= RTOL
+
+
+def test_config2_small_free_running(left_arm):
+    """config 2 at a size the oracle finishes in seconds: 48 tracks x N=500, shared column, free-running"""
+    seed, T, N, frames = 0x5EED0002, 48, 500, 12
+    tracks = list(range(100, 100 + T))
+    u0 = synth_u_init(seed, tracks)
+    fs = oracle_filters(left_arm, T, N, u0)
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    b.reset(u0)
+    for fr in range(frames):
+        meas, ui, up = synth_frame(seed, tracks, fr)
+        res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+        b.update(meas, ui, up)
+        stats, _ = compare_frame(b, fs, res, check_state=(fr == frames - 1))
+        assert_parity(stats)
+    xb, pose = b.estimate()
+    for t in range(T):
+        xo, po = fs[t].estimate()
+        assert rel_err(xb[t], xo) <= RTOL and rel_err(pose[t], po) <= RTOL
+
+
+def test_config5_bank_mode_right_arm(right_arm):
+    """config 5 shape: data23D model, N=15 slots per track, many tracks, shared column"""
+    seed, T, N, frames = 0x5EED0005, 300, 15, 10
+    tracks = list(range(T))
+    u0 = synth_u_init(seed, tracks)
+    fs = oracle_filters(right_arm, T, N, u0)
+    b = mk.TrackBatch(right_arm.mk, T, N)
+    b.reset(u0)
+    for fr in range(frames):
+        meas, ui, up = synth_frame(seed, tracks, fr)
+        res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+        b.update(meas, ui, up)
+        stats, _ = compare_frame(b, fs, res, check_state=(fr in (0, frames - 1)))
+        assert_parity(stats)
+
+
+def test_config4_large_n_one_track(left_arm):
+    """config 4 shape (per-slot columns, N = 16384 on 2 tracks; multi-tile block resampler)"""
+    seed, T, N = 0x5EED0004, 2, 16384
+    u0 = synth_u_init(seed, [0, 1])
+    fs = oracle_filters(left_arm, T, N, u0)
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    b.reset(u0)
+    rng = np.random.default_rng(3)
+    for fr in range(3):
+        hand = np.array([388.0 + 10 * fr, 250.0])
+        meas = np.zeros((T, 6, N))
+        meas[:, 0], meas[:, 1], meas[:, 4], meas[:, 5] = 323.5, 74.5, 323.5, 128.55
+        meas[:, 2] = hand[0] + 3 * rng.standard_normal((T, N))
+        meas[:, 3] = hand[1] + 3 * rng.standard_normal((T, N))
+        ui, up = rng.random(T), rng.random(T)
+        res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+        b.update(meas, ui, up)
+        stats, _ = compare_frame(b, fs, res, check_state=(fr == 2))
+        assert_parity(stats)
+
+
+@pytest.mark.parametrize("mode", [mk.CHOL_CV3_LITERAL, mk.CHOL_EXACT])
+def test_other_chol_modes(left_arm, mode):
+    a = left_arm.arrays
+    p = mk.default_params()
+    p.chol_mode = mode
+    m = mk.Model.from_arrays(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"], p)
+    T, N, seed = 3, 200, 0x5EED0002
+    u0 = synth_u_init(seed, range(T))
+    fs = oracle_filters(left_arm, T, N, u0, chol=mode)
+    b = mk.TrackBatch(m, T, N)
+    b.reset(u0)
+    meas, ui, up = synth_frame(seed, range(T), 0)
+    res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+    b.update(meas, ui, up)
+    d = b.download()
+    for t in range(T):
+        if mode == mk.CHOL_CV3_LITERAL:
+            # every weight underflows to 0 -> random-index fallback forever
+            assert res[t]["status"] & 2 and d["status"][t] & L.ST_POST_DEGENERATE
+            assert np.array_equal(d["parents"][t], res[t]["parents"])
+        else:
+            assert rel_err_weights(d["w_raw"][t], res[t]["w_raw"]) <= RTOL
+            assert np.array_equal(d["parents"][t], res[t]["parents"])
+
+
+def test_resample_kats_on_device(rng):
+    N = 500
+    out, deg = mk.resample(np.full(N, 1.0 / N), N, 0.5)
+    assert deg == 0 and np.array_equal(out, np.arange(N))
+    w = np.zeros(N)
+    w[123] = 1.0
+    out, deg = mk.resample(w, N, 0.25)
+    assert deg == 0 and np.all(out == 123)
+    for bad in (np.zeros(15), np.full(15, np.nan), np.zeros(300)):
+        out, deg = mk.resample(bad, 400, 0.5, seed=77)
+        want, wdeg = orc.resample(bad, 400, 0.5, seed=77)
+        assert deg == 1 and wdeg == 1 and np.array_equal(out, want)
+    out, _ = mk.resample(np.array([0.2, 0.5, 0.3]), 10, -1.0, seed=99)
+    want, _ = orc.resample(np.array([0.2, 0.5, 0.3]), 10, -1.0, seed=99)
+    assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("L_,N", [(15, 15), (15, 500), (500, 500), (17, 500), (5000, 500), (4096, 4096),
+                                  (65536, 65536), (300, 77), (1000, 3000)])
+def test_resample_random_weights_bit_exact(rng, L_, N):
+    for trial in range(6):
+        kind = trial % 3
+        if kind == 0:
+            w = rng.lognormal(0, 3, L_)
+        elif kind == 1:
+            w = rng.random(L_) ** 8
+            w[rng.integers(0, L_, L_ // 3)] = 0.0  # exact zeros (underflowed weights)
+        else:
+            w = np.zeros(L_)
+            w[rng.integers(0, L_, 3)] = rng.random(3) + 0.1  # collapsed: a few heavy parents
+        w = w / w.sum()
+        u = [rng.random(), 0.0, 1.0 - 2.0**-53][trial % 3] if trial >= 3 else rng.random()
+        out, deg = mk.resample(w, N, u)
+        want, wdeg = orc.resample(w, N, u)
+        assert deg == wdeg == 0
+        assert np.array_equal(out, want), f"L={L_} N={N} trial={trial}: {(out != want).sum()} mismatches"
+
+
+def test_full_size_properties_config2(left_arm):
+    """config 2 at BASELINE size (4096 x 500): size-independent properties instead of the oracle"""
+    torch = pytest.importorskip("torch")
+    seed, T, N = 0x5EED0002, 4096, 500
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    dev = torch.device("cuda:0")
+    meas = torch.empty((T, 6), dtype=torch.float64, device=dev)
+    ui = torch.empty(T, dtype=torch.float64, device=dev)
+    up = torch.empty(T, dtype=torch.float64, device=dev)
+    u0 = torch.tensor(synth_u_init(seed, range(64)).repeat(T // 64), dtype=torch.float64, device=dev)
+    b.reset(u0)
+    for fr in range(4):
+        b.synth_fill(seed, 0, fr, 1, mk.MEAS_SHARED, meas, ui, up)
+        b.update(meas, ui, up)
+    d = b.download(state=True, cov=False)
+    # device-generated inputs equal the CPU generator bit for bit
+    m_cpu, ui_cpu, up_cpu = synth_frame(seed, range(16), 3)
+    assert np.array_equal(meas[:16].cpu().numpy(), m_cpu) and np.array_equal(ui[:16].cpu().numpy(), ui_cpu)
+    assert np.array_equal(up[:16].cpu().numpy(), up_cpu)
+    par, wn = d["parents"], d["w_norm"]
+    assert np.all(np.diff(par, axis=1) >= 0)                       # sorted parents
+    assert par.min() >= 0 and par.max() < N
+    assert np.allclose(wn.sum(1), 1.0, rtol=0, atol=1e-12)          # normalised
+    cnt = np.stack([np.bincount(par[t], minlength=N) for t in range(0, T, 37)])
+    assert np.all(np.abs(cnt - N * wn[::37]) < 1 + 1e-9)            # systematic resampling property
+    assert np.all(np.diff(d["indicators"], axis=1) >= 0) and d["indicators"].max() < 15
+    assert np.isfinite(d["x"]).all() and not d["status"].any()
+    # spot-check 3 tracks of the full batch against the oracle (free-running, same draws)
+    for t in (0, 2049, 4095):
+        f = orc.Filter(left_arm.orc, N)
+        f.reset(u=float(u0[t].cpu()))
+        for fr in range(4):
+            mz, a_, c_ = synth_frame(seed, [t], fr)
+            r = f.update(mz[0], a_[0], c_[0])
+        assert np.array_equal(par[t], r["parents"])
+        xo, _ = f.get_state()
+        assert rel_err(d["x"][t], xo) <= RTOL
