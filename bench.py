@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric: batched tracker
+frame-updates/sec, GMM-KF + systematic resampling) on config 2: 4096 independent synthetic
+tracks x 500 slots per GPU, 15-component / 12-D PCA arm model, one shared measurement column
+per track-frame.
+
+One "step" = one frame: ParticleFilter::update for every track (K->N indicator resample, fused
+per-slot KF predict + innovation likelihood + KF update, weight normalisation, N->N systematic
+resample) followed by getEstimator + PCA reconstruction.
+
+  python bench.py [--gpus N --steps K --warmup W]            B200 arm (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                      the reference's CPU path (oracle/) on host cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job frame-updates/s with inputs resident in HBM;
+`e2e` = the same through the C ABI with pinned HOST buffers (H2D of the step's measurements and
+draws, D2H of the per-track pose) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched tracker frame-updates/sec (GMM-KF+PDAF)"
+UNIT = "frame-updates/s"
+SEED = 0x5EED0002
+BYTES_PER_SLOT_UPDATE = 1500  # read parent 720 + write child 720 + meas 48 + weight 8 + index 4
+
+
+def workload_name(T, N):
+    return (f"config 2: {T} independent synthetic tracks/GPU x {N} slots, data13D_PCA_100000_15_12 (K=15, d=12), "
+            "full GMM-KF bank + single-candidate (shared column) update")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """dram bytes per k_slot_update launch from the committed ncu --set full summary, if any"""
+    p = os.path.join(ROOT, "profiles", "slot_update_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def oracle_model():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mkf_oracle as orc
+    import mkfbodytracker_pdaf_b200 as mk
+    m = mk.Model.load(mk.LEFT_ARM_MODEL, mk.RIGHT_ARM_MODEL)
+    a = m.arrays()
+    return orc, orc.Model(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"])
+
+
+def cpu_baseline(N, budget_s=12.0):
+    """the oracle port on all host cores over a bounded sample of the same workload"""
+    orc, om = oracle_model()
+    cores = os.cpu_count() or 1
+    T_s = 8 * cores
+    secs, used, _ = orc.bench_tracks(om, T_s, N, 2, per_slot=False, seed=SEED, jitter=1)  # calibrate
+    rate = T_s * 2 / max(secs, 1e-9)
+    frames = int(max(2, min(400, budget_s * rate / T_s)))
+    secs, used, _ = orc.bench_tracks(om, T_s, N, frames, per_slot=False, seed=SEED, jitter=1)
+    fu = T_s * frames / secs
+    return {"value": fu, "unit": UNIT, "cores": used, "kind": "port",
+            "slot_updates_per_s": fu * N,
+            "sample": f"{T_s} tracks x {N} slots x {frames} frames of the same synthetic workload "
+                      f"(oracle/mkf_oracle.cpp, one track per task, OpenMP over tracks, {secs:.2f} s)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, om = oracle_model()
+    cores = os.cpu_count() or 1
+    N = args.slots
+    T_s = 8 * cores
+    for _ in range(args.warmup):
+        orc.bench_tracks(om, T_s, N, 1, per_slot=False, seed=SEED, jitter=1)
+    t0 = time.perf_counter()
+    used = cores
+    for k in range(args.steps):
+        _, used, _ = orc.bench_tracks(om, T_s, N, 1, per_slot=False, seed=SEED + k, jitter=1)
+    dt = time.perf_counter() - t0
+    val = T_s * args.steps / dt
+    sample = (f"each step = 1 frame over {T_s} tracks x {N} slots (of the {args.tracks}-track workload), fresh filters "
+              "per step, reset included")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args.tracks, N), "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "slot_updates_per_s": val * N, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tracks", type=int, default=4096, help="tracks per GPU")
+    ap.add_argument("--slots", type=int, default=500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mkfbodytracker_pdaf_b200 as mk
+    from mkfbodytracker_pdaf_b200.sharding import gather_summaries, pack_summary, shard_tracks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if mk.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (libmkf_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, N, K, W = args.tracks, args.slots, args.steps, args.warmup
+    F = K + W
+    model = mk.Model.load(mk.LEFT_ARM_MODEL, mk.RIGHT_ARM_MODEL)
+    stream = torch.cuda.current_stream()
+    batch = mk.TrackBatch(model, T, N, device=local, stream=stream.cuda_stream)
+    track0, _ = shard_tracks(world * T, world, rank)  # weak scaling: T tracks on every rank
+
+    # synthetic inputs of every frame, generated on the device by the shared counter-based generator
+    meas = torch.empty((F, T, 6), dtype=torch.float64, device=dev)
+    ui = torch.empty((F, T), dtype=torch.float64, device=dev)
+    up = torch.empty((F, T), dtype=torch.float64, device=dev)
+    for f in range(F):
+        batch.synth_fill(SEED, track0, f, 1, mk.MEAS_SHARED, meas[f], ui[f], up[f])
+    u0 = torch.empty(T, dtype=torch.float64, device=dev)
+    batch.synth_fill(SEED, track0, 0xFFFFFF, 1, mk.MEAS_SHARED, meas[0].clone(), u0, None)
+    pose = torch.empty((T, model.D), dtype=torch.float64, device=dev)
+    wsum_d = torch.empty(T, dtype=torch.float64, device=dev)
+    status_d = torch.empty(T, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(f):
+        batch.update(meas[f], ui[f], up[f])
+        batch.estimate_into(None, pose)
+
+    # ---------------- device-resident run ----------------
+    batch.reset(u0)
+    for f in range(W):
+        step(f)
+    barrier()
+    batch.profile(K)
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    launches0 = mk.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for f in range(W, F):
+        step(f)
+    # final per-track summaries {pose[D], wsum, status}; the only collective is this gather
+    batch.summary_into(wsum_d, status_d)
+    gathered = gather_summaries(pack_summary(pose, wsum_d, status_d), world)
+    e1.record()
+    barrier()
+    launches = mk.launch_count() - launches0
+    clocks = clk.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    prof = batch.profile_read()
+    batch.profile(0)
+    status_bad = int((batch.status() & (mk._lib.ST_POST_DEGENERATE | mk._lib.ST_CHOL_FAIL)).astype(bool).sum())
+
+    # ---------------- end to end through the C ABI with pinned host buffers ----------------
+    h_meas = [torch.empty((T, 6), dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_ui = [torch.empty(T, dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_up = [torch.empty(T, dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_pose = torch.empty((T, model.D), dtype=torch.float64).pin_memory()
+    meas_cpu, ui_cpu, up_cpu = meas.cpu(), ui.cpu(), up.cpu()
+    batch.reset(u0)
+
+    def e2e_step(f):
+        s = f & 1
+        h_meas[s].copy_(meas_cpu[f])  # the frame's inputs arrive in host memory
+        h_ui[s].copy_(ui_cpu[f])
+        h_up[s].copy_(up_cpu[f])
+        batch.update(h_meas[s].numpy(), h_ui[s].numpy(), h_up[s].numpy())
+        mk._lib.check(mk._lib.lib.mkf_batch_estimate(batch._h, None, h_pose.data_ptr(), mk.MEM_HOST))  # syncs
+
+    for f in range(W):
+        e2e_step(f)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for f in range(W, F):
+        e2e_step(f)
+    e3.record()
+    barrier()
+    ms_e2e = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e2e.item())
+    pose_check = float(h_pose[:, :2].mean())
+
+    if rank == 0:
+        value = world * T * K / (ms * 1e-3)
+        e2e_val = world * T * K / (ms_e2e * 1e-3)
+        peak, peak_src = load_peak()
+        slot_ms = prof["ms_slot_update"] / max(prof["n"], 1)
+        achieved = T * N * BYTES_PER_SLOT_UPDATE / (slot_ms * 1e-3) / 1e9 if slot_ms > 0 else None
+        tr = load_traffic()
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(T, N), "tracks_per_gpu": T, "slots": N, "components": model.K,
+                       "state_dim": model.d, "measurement": "shared column per track-frame", "chol_mode": "CV24_LITERAL",
+                       "alias_mode": "INDEPENDENT", "seed": hex(SEED),
+                       "l2": f"no flush: per-step working set {2 * T * N * 720 / 1e9:.2f} GB >> 126 MB L2",
+                       "parallelism": f"tracks sharded, {world} x {T}; one final NCCL all_gather of per-track summaries"},
+            "slot_updates_per_s": value * N,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                         "kernel": "k_slot_update<12>", "kernel_ms": slot_ms,
+                         "algorithmic_bytes_per_launch": T * N * BYTES_PER_SLOT_UPDATE, "peak_source": peak_src,
+                         "stage_ms": {"indicator_bounds": prof["ms_bounds"] / max(prof["n"], 1),
+                                      "slot_update": slot_ms,
+                                      "normalise_resample": prof["ms_resample"] / max(prof["n"], 1)}},
+            "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": world * T * 8 * 8, "d2h_bytes_per_step": world * T * model.D * 8},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "status_flagged_tracks": status_bad, "pose_check": pose_check, "gathered_rows": int(gathered.shape[0]),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(N)
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

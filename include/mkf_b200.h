@@ -141,7 +141,8 @@ int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int mem);
  * followed by ParticleFilter::update of both arms (src/pfPose.cpp:325-326) when do_update != 0.
  * arm[0]/arm[1]: the two arm batches (same T, N, device, stream).
  * cand_xy T x 2 hands x 2 (x row, y row) x C; cand_L T x 2 x C (likelihood-image samples,
- * uint8); roi T x 4 (x, y, w, h); u_cand T x 2; u_ind/u_post T x 2 (arm-major pairs). */
+ * uint8); roi T x 4 (x, y, w, h); u_cand T x 2; u_ind/u_post T x 2 (arm-major pairs);
+ * seeds T x 2 x 3 uint64 or NULL: per arm [candidate, indicator (unused), posterior] fallback seeds. */
 int mkf_batch_associate(mkf_batch* arm0, mkf_batch* arm1, int C, const double* cand_xy, const uint8_t* cand_L,
                         const double* roi, const double* u_cand, const double* u_ind, const double* u_post,
                         const uint64_t* seeds, int do_update, int mem);
@@ -181,6 +182,14 @@ int mkf_pf2d_sync(mkf_pf2d* p);
 /* fills meas (device, layout per meas_layout) and u_ind/u_post (device, T each) for `frame` */
 int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint64_t frame, int jitter, int meas_layout,
                    double* meas_dev, double* u_ind_dev, double* u_post_dev);
+
+/* per-kernel device timing of mkf_batch_update, CUDA events on the batch's stream (bench.py roofline):
+ * mkf_batch_profile arms recording for up to max_updates updates (0 disables);
+ * mkf_batch_profile_read synchronises and returns the summed milliseconds of the three stages
+ * (indicator bounds, fused slot update, normalise+resample) over n_updates updates, then rearms. */
+int mkf_batch_profile(mkf_batch* b, int max_updates);
+int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_update, double* ms_resample,
+                           int* n_updates);
 
 /* number of kernel launches issued through this library since load (bench.py "gpu_launches") */
 uint64_t mkf_launch_count(void);

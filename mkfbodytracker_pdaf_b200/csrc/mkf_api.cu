@@ -83,8 +83,13 @@ struct mkf_batch {
     // staging
     DevBuf in_meas, in_u0, in_u1, in_seed, out_a, out_b, in_x, in_p;
     // association scratch (arm0 owns)
-    DevBuf as_cand, as_L, as_roi, as_u, as_w, as_gate, as_bins, as_meas, as_wsum, as_hand;
+    DevBuf as_cand, as_L, as_roi, as_u, as_w, as_gate, as_bins, as_meas, as_wsum, as_hand, as_status, as_seed,
+        as_ui, as_up;
     int as_C = 0;
+    // optional per-kernel timing (mkf_batch_profile): 4 events per update
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_n = 0;
 };
 
 static bool is_device_ptr(const void* p, int mem)
@@ -168,8 +173,10 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
         if (p) cudaFree(p);
     DevBuf* bufs[] = {&b->in_meas, &b->in_u0, &b->in_u1, &b->in_seed, &b->out_a,   &b->out_b,  &b->in_x,   &b->in_p,
                       &b->as_cand, &b->as_L,  &b->as_roi, &b->as_u,   &b->as_w,    &b->as_gate, &b->as_bins,
-                      &b->as_meas, &b->as_wsum, &b->as_hand};
+                      &b->as_meas, &b->as_wsum, &b->as_hand, &b->as_status, &b->as_seed,
+                      &b->as_ui,   &b->as_up};
     for (DevBuf* d : bufs) d->release();
+    for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -234,12 +241,12 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     if ((rc = dmalloc((void**)&b->w_raw, (size_t)b->total * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->wsum, (size_t)T * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->status, (size_t)T * sizeof(uint32_t)))) return fail(rc);
-    if ((rc = dmalloc((void**)&b->need_fb, (size_t)T * sizeof(uint32_t)))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->need_fb, (size_t)2 * T * sizeof(uint32_t)))) return fail(rc);
     // the tail lanes of the last tile are read by nobody but keep them defined
     if (cudaMemset(b->st[0], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
         cudaMemset(b->st[1], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
         cudaMemset(b->status, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMemset(b->need_fb, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemset(b->need_fb, 0, (size_t)2 * T * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemset(b->w_raw, 0, (size_t)b->total * sizeof(double)) != cudaSuccess ||
         cudaMemset(b->wsum, 0, (size_t)T * sizeof(double)) != cudaSuccess ||
         cudaMemset(b->parent, 0, (size_t)b->total * sizeof(int32_t)) != cudaSuccess ||
@@ -304,23 +311,23 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     return MKF_OK;
 }
 
-// weight normalisation + systematic resampling of T tracks: w (T x L) -> out (T x N)
-static int run_resample(mkf_batch* b, const double* d_w, int L, int N, const double* d_u, int u_stride, int normalise,
-                        double* d_wsum, int32_t* d_out, uint32_t* d_status, const uint64_t* d_seeds, int seed_stride,
-                        int seed_off, uint32_t bit_fb, uint32_t bit_deg)
+// weight normalisation + systematic resampling of `nt` tracks: w (nt x L) -> out (nt x N)
+static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, const double* d_w, int L, int N,
+                        const double* d_u, int u_stride, int normalise, double* d_wsum, int32_t* d_out,
+                        uint32_t* d_status, const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb,
+                        uint32_t bit_deg)
 {
     if (L <= 64 && N <= 64) {
-        k_resample_small<<<grid_for(b->T, 128), 128, 0, b->stream>>>(d_w, b->T, L, N, d_u, u_stride, normalise, d_wsum,
-                                                                      d_out, d_status, 1, b->need_fb, bit_deg);
+        k_resample_small<<<grid_for(nt, 128), 128, 0, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
+                                                                 d_status, 1, need_fb, bit_deg);
     } else {
-        k_resample_block<128, 4><<<(unsigned)b->T, 128, 0, b->stream>>>(d_w, L, N, d_u, u_stride, normalise, d_wsum,
-                                                                         d_out, d_status, 1, b->need_fb, bit_fb,
-                                                                         bit_deg);
+        k_resample_block<128, 4><<<(unsigned)nt, 128, 0, stream>>>(d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out,
+                                                                    d_status, 1, need_fb, bit_fb, bit_deg);
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
-    k_resample_fallback<<<grid_for(b->T, 128), 128, 0, b->stream>>>(d_w, b->T, L, N, d_u, u_stride, normalise, d_wsum,
-                                                                     d_out, d_seeds, seed_stride, seed_off, b->need_fb);
+    k_resample_fallback<<<grid_for(nt, 128), 128, 0, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
+                                                                d_seeds, seed_stride, seed_off, need_fb);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     return MKF_OK;
@@ -336,7 +343,11 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         mkf_set_error("internal: strided u_ind unsupported");
         return MKF_E_INVALID;
     }
+    const bool prof = b->prof_on && (size_t)(b->prof_n + 1) * 4 <= b->prof_ev.size();
+    cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * 4] : nullptr;
+    if (prof) cudaEventRecord(pe[0], b->stream);
     if ((rc = launch_bounds_kernel(b, d_uind))) return rc;
+    if (prof) cudaEventRecord(pe[1], b->stream);
     SlotArgs a;
     a.st_in = b->st[b->cur];
     a.st_out = b->st[b->cur ^ 1];
@@ -371,9 +382,61 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    if (prof) cudaEventRecord(pe[2], b->stream);
     b->cur ^= 1;
-    return run_resample(b, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status, d_seeds, seed_stride,
-                        seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE);
+    rc = run_resample(b->stream, b->T, b->need_fb, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status,
+                      d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE);
+    if (prof) {
+        cudaEventRecord(pe[3], b->stream);
+        b->prof_n++;
+    }
+    return rc;
+}
+
+// per-kernel device timing of mkf_batch_update with CUDA events on the batch's stream
+extern "C" int mkf_batch_profile(mkf_batch* b, int max_updates)
+{
+    if (!b || max_updates < 0) {
+        mkf_set_error("mkf_batch_profile: invalid argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
+    b->prof_ev.clear();
+    b->prof_n = 0;
+    b->prof_on = max_updates > 0;
+    for (int i = 0; i < max_updates * 4; i++) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        b->prof_ev.push_back(e);
+    }
+    return MKF_OK;
+}
+
+extern "C" int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_update, double* ms_resample,
+                                      int* n_updates)
+{
+    if (!b) {
+        mkf_set_error("null batch");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    double acc[3] = {0, 0, 0};
+    for (int i = 0; i < b->prof_n; i++) {
+        for (int k = 0; k < 3; k++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, b->prof_ev[(size_t)i * 4 + k], b->prof_ev[(size_t)i * 4 + k + 1]));
+            acc[k] += ms;
+        }
+    }
+    if (ms_bounds) *ms_bounds = acc[0];
+    if (ms_slot_update) *ms_slot_update = acc[1];
+    if (ms_resample) *ms_resample = acc[2];
+    if (n_updates) *n_updates = b->prof_n;
+    b->prof_n = 0;
+    return MKF_OK;
 }
 
 extern "C" int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layout, const double* u_ind,

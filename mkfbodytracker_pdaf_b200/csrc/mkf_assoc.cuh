@@ -1,3 +1,303 @@
-// placeholder, replaced below
-extern "C" int mkf_batch_associate(mkf_batch*, mkf_batch*, int, const double*, const uint8_t*, const double*, const double*, const double*, const double*, const uint64_t*, int, int) { mkf_set_error("not built yet"); return MKF_E_UNSUPPORTED; }
-extern "C" int mkf_batch_assoc_results(mkf_batch*, uint8_t*, double*, int32_t*, int) { mkf_set_error("not built yet"); return MKF_E_UNSUPPORTED; }
+// mkf_assoc.cuh -- the sample-based association ("PDAF") step of
+// PFTracker::getMeasurementProposal (src/pfPose.cpp:238-326) for T persons, included by mkf_api.cu.
+//
+//   k_assoc_weights   one warp per (person, hand): gate (inside image, L != 0), proposal densities
+//                     under both arms (getSampleProb / mvnpdf_multiple, src/pf2DRao.cpp:69-83,105-122),
+//                     raw weight L / Z (src/pfPose.cpp:249-292)
+//   run_resample      sum + normalise (src/pfPose.cpp:294-298) and C -> N systematic resample (:300-301)
+//   k_assoc_meas      per-slot measurement columns (src/pfPose.cpp:303-323)
+//   update_device     pf1->update / pf2->update (src/pfPose.cpp:325-326)
+#ifndef MKF_ASSOC_CUH
+#define MKF_ASSOC_CUH
+
+struct AssocArgs {
+    const double* __restrict__ cand_xy; // T x 2 x 2 x C
+    const uint8_t* __restrict__ cand_L; // T x 2 x C
+    const double* __restrict__ roi;     // T x 4
+    const double* __restrict__ pose0;   // T x D0 (arm 0 reconstruction; [0],[1] = hand x,y)
+    const double* __restrict__ pose1;   // T x D1
+    double* __restrict__ w_raw;         // T x 2 x C
+    uint8_t* __restrict__ gate;         // T x 2 x C
+    long long T;
+    int C, D0, D1, chol_mode, img_rows, img_cols;
+    double pa, clutter, spread;
+};
+
+// 2-D isotropic proposal density exactly as mvnpdf_multiple evaluates it for cov = s2 * I:
+// chol() of a diagonal matrix, 2x2 closed-form inverse, exp(q*-0.5 + (-lsd - log 2pi))
+struct Iso2 {
+    double ri00, ri11, shift;
+};
+__device__ __forceinline__ Iso2 mkf_iso2_setup(double s2, int chol_mode)
+{
+    // cv::Cholesky on diag(s2, s2): diagonal 1/sqrt(s2); chol(): R_ee = 1/elem
+    const double inv = __ddiv_rn(1.0, sqrt(s2));
+    double R;
+    if (chol_mode == MKF_CHOL_CV3_LITERAL)
+        R = inv; // OpenCV >= 3 leaves L_ee on the diagonal, so elem = L_ee and R_ee = 1/L_ee
+    else if (chol_mode == MKF_CHOL_EXACT)
+        R = __ddiv_rn(1.0, inv);
+    else
+        R = __ddiv_rn(1.0, inv);
+    // cv::invert 2x2: d = 1/(R00*R11 - 0); inv00 = R11*d; inv11 = R00*d
+    const double d = __ddiv_rn(1.0, __dmul_rn(R, R));
+    Iso2 o;
+    o.ri00 = __dmul_rn(R, d);
+    o.ri11 = __dmul_rn(R, d);
+    const double lsd = __dadd_rn(log(R), log(R));
+    o.shift = __dsub_rn(-lsd, 1.8378770664093453); // 2*log(2*pi)/2
+    return o;
+}
+__device__ __forceinline__ double mkf_iso2_pdf(const Iso2& g, double x, double y, double ux, double uy)
+{
+    const double v0 = __dmul_rn(__dsub_rn(x, ux), g.ri00);
+    const double v1 = __dmul_rn(__dsub_rn(y, uy), g.ri11);
+    const double q = __dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1));
+    return exp(__dadd_rn(__dmul_rn(q, -0.5), g.shift));
+}
+
+__global__ void __launch_bounds__(128) k_assoc_weights(const AssocArgs a)
+{
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= a.T * 2) return;
+    const long long t = wid >> 1;
+    const int h = (int)(wid & 1);
+    const double scale = a.roi[t * 4 + 2]; // (double)msg->ROIs[0].width
+    const Iso2 g = mkf_iso2_setup(__dmul_rn(__dmul_rn(a.spread, scale), 1.0), a.chol_mode);
+    const double h0x = a.pose0[t * a.D0 + 0], h0y = a.pose0[t * a.D0 + 1];
+    const double h1x = a.pose1[t * a.D1 + 0], h1y = a.pose1[t * a.D1 + 1];
+    const double ownx = h ? h1x : h0x, owny = h ? h1y : h0y;
+    const double othx = h ? h0x : h1x, othy = h ? h0y : h1y;
+    const double zc = __dmul_rn(a.clutter, __dsub_rn(1.0, __dmul_rn(2.0, a.pa)));
+    const double* __restrict__ px = a.cand_xy + (t * 2 + h) * 2 * (long long)a.C;
+    const double* __restrict__ py = px + a.C;
+    const uint8_t* __restrict__ pl = a.cand_L + (t * 2 + h) * (long long)a.C;
+    double* __restrict__ wo = a.w_raw + (t * 2 + h) * (long long)a.C;
+    uint8_t* __restrict__ go = a.gate + (t * 2 + h) * (long long)a.C;
+    for (int c = lane; c < a.C; c += 32) {
+        const double x = px[c], y = py[c];
+        double w = 0.0;
+        uint8_t gt = 0;
+        if ((y > 0) && (y < (double)a.img_rows) && (x > 0) && (x < (double)a.img_cols)) {
+            const double Lk = __ddiv_rn((double)pl[c], 255.0);
+            if (Lk != 0.0) {
+                const double own = mkf_iso2_pdf(g, x, y, ownx, owny);
+                const double oth = mkf_iso2_pdf(g, x, y, othx, othy);
+                const double Z = __dadd_rn(__dadd_rn(__dmul_rn(own, a.pa), __dmul_rn(oth, a.pa)), zc);
+                w = __ddiv_rn(Lk, Z);
+                gt = 1;
+            }
+        }
+        wo[c] = w;
+        go[c] = gt;
+    }
+}
+
+// measurement[:, i] = [roi.x + w/2, roi.y + 0.5 h, cand_x(bins[i]), cand_y(bins[i]), roi.x + w/2, roi.y + 1.65 h]
+__global__ void k_assoc_meas(const double* __restrict__ cand_xy, const double* __restrict__ roi,
+                             const int32_t* __restrict__ bins, const uint32_t* __restrict__ as_status, long long T,
+                             int N, int C, double neck, double* __restrict__ meas0, double* __restrict__ meas1,
+                             uint32_t* __restrict__ status0, uint32_t* __restrict__ status1)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * 2 * N) return;
+    const long long th = i / N;
+    const int j = (int)(i - th * N);
+    const long long t = th >> 1;
+    const int h = (int)(th & 1);
+    const double rx = roi[t * 4 + 0], ry = roi[t * 4 + 1], rw = roi[t * 4 + 2], rh = roi[t * 4 + 3];
+    const int bsel = bins[th * N + j];
+    const double* __restrict__ px = cand_xy + th * 2 * (long long)C;
+    double* __restrict__ m = (h ? meas1 : meas0) + t * 6 * (long long)N;
+    const double cxv = __dadd_rn(rx, __ddiv_rn(rw, 2.0));
+    m[0 * N + j] = cxv;
+    m[1 * N + j] = __dadd_rn(ry, __dmul_rn(0.5, rh));
+    m[2 * N + j] = px[bsel];
+    m[3 * N + j] = px[C + bsel];
+    m[4 * N + j] = cxv;
+    m[5 * N + j] = __dadd_rn(ry, __dmul_rn(neck, rh));
+    if (j == 0) {
+        const uint32_t st = as_status[th];
+        if (st) atomicOr((h ? status1 : status0) + t, st);
+    }
+}
+
+static int estimate_pose_device(mkf_batch* b, double* d_pose)
+{
+    const mkf_model* m = b->m;
+    const double2* st = b->st[b->cur];
+#define LAUNCH_EST(DD, BT)                                                                                   \
+    k_estimate<DD, BT><<<(unsigned)b->T, BT, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean, \
+                                                              b->d_tinv, nullptr, d_pose)
+    if (m->d == 12) {
+        if (b->N <= 64)
+            LAUNCH_EST(12, 32);
+        else
+            LAUNCH_EST(12, 128);
+    } else {
+        if (b->N <= 64)
+            LAUNCH_EST(10, 32);
+        else
+            LAUNCH_EST(10, 128);
+    }
+#undef LAUNCH_EST
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    return MKF_OK;
+}
+
+extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const double* cand_xy, const uint8_t* cand_L,
+                                   const double* roi, const double* u_cand, const double* u_ind, const double* u_post,
+                                   const uint64_t* seeds, int do_update, int mem)
+{
+    if (!a0 || !a1 || !cand_xy || !cand_L || !roi || !u_cand || C <= 0) {
+        mkf_set_error("mkf_batch_associate: null or invalid argument");
+        return MKF_E_INVALID;
+    }
+    if (do_update && (!u_ind || !u_post)) {
+        mkf_set_error("mkf_batch_associate: u_ind/u_post required when do_update != 0");
+        return MKF_E_INVALID;
+    }
+    if (a0->T != a1->T || a0->N != a1->N || a0->device != a1->device || a0->stream != a1->stream) {
+        mkf_set_error("mkf_batch_associate: the two arm batches must share T, N, device and stream");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(a0->device));
+    mkf_batch* b = a0;
+    const long long T = b->T;
+    const int N = b->N;
+    const mkf_params& prm = b->m->prm;
+    int rc;
+    const double *d_cand, *d_roi, *d_uc, *d_ui = nullptr, *d_up = nullptr;
+    const uint8_t* d_L;
+    const uint64_t* d_seeds;
+    if ((rc = in_ptr(b, cand_xy, (size_t)T * 4 * C, mem, b->as_cand, &d_cand))) return rc;
+    if ((rc = in_ptr(b, cand_L, (size_t)T * 2 * C, mem, b->as_L, &d_L))) return rc;
+    if ((rc = in_ptr(b, roi, (size_t)T * 4, mem, b->as_roi, &d_roi))) return rc;
+    if ((rc = in_ptr(b, u_cand, (size_t)T * 2, mem, b->as_u, &d_uc))) return rc;
+    if ((rc = in_ptr(b, seeds, (size_t)T * 6, mem, b->as_seed, &d_seeds))) return rc;
+    if (do_update) {
+        if ((rc = in_ptr(b, u_ind, (size_t)T * 2, mem, b->as_ui, &d_ui))) return rc;
+        if ((rc = in_ptr(b, u_post, (size_t)T * 2, mem, b->as_up, &d_up))) return rc;
+    }
+    // keep the device copy of the candidates alive for mkf_batch_assoc_results / the measurement gather
+    if ((rc = b->as_w.ensure((size_t)T * 2 * C * sizeof(double))) || (rc = b->as_gate.ensure((size_t)T * 2 * C)) ||
+        (rc = b->as_bins.ensure((size_t)T * 2 * N * sizeof(int32_t))) ||
+        (rc = b->as_wsum.ensure((size_t)T * 2 * sizeof(double))) ||
+        (rc = b->as_status.ensure((size_t)T * 2 * sizeof(uint32_t))) ||
+        (rc = b->as_hand.ensure((size_t)T * (a0->m->D + a1->m->D) * sizeof(double))) ||
+        (rc = b->as_meas.ensure((size_t)T * 2 * 6 * N * sizeof(double))))
+        return rc;
+    b->as_C = C;
+    double* d_pose0 = (double*)b->as_hand.p;
+    double* d_pose1 = d_pose0 + (size_t)T * a0->m->D;
+    CK(cudaMemsetAsync(b->as_status.p, 0, (size_t)T * 2 * sizeof(uint32_t), b->stream));
+    CK(cudaMemsetAsync(a0->status, 0, (size_t)T * sizeof(uint32_t), b->stream));
+    CK(cudaMemsetAsync(a1->status, 0, (size_t)T * sizeof(uint32_t), b->stream));
+    // posterior hand position of both arms: rows 0..1 of pca_proj^T xbar + pca_mean^T (src/pf2DRao.cpp:111-116)
+    if ((rc = estimate_pose_device(a0, d_pose0)) || (rc = estimate_pose_device(a1, d_pose1))) return rc;
+    AssocArgs aa;
+    aa.cand_xy = d_cand;
+    aa.cand_L = d_L;
+    aa.roi = d_roi;
+    aa.pose0 = d_pose0;
+    aa.pose1 = d_pose1;
+    aa.w_raw = (double*)b->as_w.p;
+    aa.gate = (uint8_t*)b->as_gate.p;
+    aa.T = T;
+    aa.C = C;
+    aa.D0 = a0->m->D;
+    aa.D1 = a1->m->D;
+    aa.chol_mode = prm.chol_mode;
+    aa.img_rows = prm.img_rows;
+    aa.img_cols = prm.img_cols;
+    aa.pa = prm.assoc_pa;
+    aa.clutter = prm.assoc_clutter;
+    aa.spread = prm.proposal_spread;
+    k_assoc_weights<<<grid_for(T * 2 * 32, 128), 128, 0, b->stream>>>(aa);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if ((rc = run_resample(b->stream, T * 2, b->need_fb, (const double*)b->as_w.p, C, N, d_uc, 1, 1,
+                           (double*)b->as_wsum.p, (int32_t*)b->as_bins.p, (uint32_t*)b->as_status.p, d_seeds, 3, 0,
+                           MKF_ST_CAND_FALLBACK, MKF_ST_CAND_DEGENERATE)))
+        return rc;
+    double* d_meas0 = (double*)b->as_meas.p;
+    double* d_meas1 = d_meas0 + (size_t)T * 6 * N;
+    k_assoc_meas<<<grid_for(T * 2 * N, 256), 256, 0, b->stream>>>(d_cand, d_roi, (const int32_t*)b->as_bins.p,
+                                                                  (const uint32_t*)b->as_status.p, T, N, C,
+                                                                  prm.neck_offset, d_meas0, d_meas1, a0->status,
+                                                                  a1->status);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if (!do_update) return MKF_OK;
+    // u_ind / u_post / seeds arrive as arm-major pairs per person: de-interleave with strided 2-D copies
+    DevBuf& s0 = a0->in_u0;
+    DevBuf& s1 = a0->in_u1;
+    DevBuf& s2 = a1->in_u0;
+    DevBuf& s3 = a1->in_u1;
+    if ((rc = s0.ensure((size_t)T * 8)) || (rc = s1.ensure((size_t)T * 8)) || (rc = s2.ensure((size_t)T * 8)) ||
+        (rc = s3.ensure((size_t)T * 8)))
+        return rc;
+    CK(cudaMemcpy2DAsync(s0.p, 8, d_ui, 16, 8, (size_t)T, cudaMemcpyDeviceToDevice, b->stream));
+    CK(cudaMemcpy2DAsync(s2.p, 8, d_ui + 1, 16, 8, (size_t)T, cudaMemcpyDeviceToDevice, b->stream));
+    CK(cudaMemcpy2DAsync(s1.p, 8, d_up, 16, 8, (size_t)T, cudaMemcpyDeviceToDevice, b->stream));
+    CK(cudaMemcpy2DAsync(s3.p, 8, d_up + 1, 16, 8, (size_t)T, cudaMemcpyDeviceToDevice, b->stream));
+    // seeds layout T x 2 x 3: per arm [candidate resample, indicator resample (unused), posterior resample]
+    if ((rc = update_device(a0, d_meas0, MKF_MEAS_PER_SLOT, (const double*)s0.p, (const double*)s1.p, 1, d_seeds, 6, 2)))
+        return rc;
+    return update_device(a1, d_meas1, MKF_MEAS_PER_SLOT, (const double*)s2.p, (const double*)s3.p, 1, d_seeds, 6, 5);
+}
+
+extern "C" int mkf_batch_assoc_results(mkf_batch* b, uint8_t* gate, double* weights, int32_t* bins, int mem)
+{
+    if (!b || b->as_C <= 0) {
+        mkf_set_error("mkf_batch_assoc_results: no association has run on this batch");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    const size_t nc = (size_t)b->T * 2 * b->as_C;
+    DevBuf tmp;
+    int rc = MKF_OK;
+    if (weights) {
+        // normalised weights = raw / sum (src/pfPose.cpp:294-298); one "track" = one (person, hand)
+        OutPtr<double> ow;
+        if ((rc = ow.init(b, weights, nc, mem, tmp))) return rc;
+        k_aux_outputs<<<grid_for((long long)nc, 256), 256, 0, b->stream>>>((const double*)b->as_w.p,
+                                                                          (const double*)b->as_wsum.p, nullptr,
+                                                                          (long long)nc, b->as_C, 0, ow.devp, nullptr);
+        MKF_LAUNCHED();
+        if (cudaGetLastError() != cudaSuccess) {
+            tmp.release();
+            mkf_set_error("k_aux_outputs launch failed");
+            return MKF_E_CUDA;
+        }
+        if ((rc = ow.finish(b))) {
+            tmp.release();
+            return rc;
+        }
+    }
+    auto copy_out = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!dst) return MKF_OK;
+        cudaMemcpyKind kind = is_device_ptr(dst, mem) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (cudaMemcpyAsync(dst, src, bytes, kind, b->stream) != cudaSuccess) {
+            mkf_set_error("cudaMemcpyAsync failed in mkf_batch_assoc_results");
+            return MKF_E_CUDA;
+        }
+        return MKF_OK;
+    };
+    if ((rc = copy_out(gate, b->as_gate.p, nc)) ||
+        (rc = copy_out(bins, b->as_bins.p, (size_t)b->T * 2 * b->N * sizeof(int32_t)))) {
+        tmp.release();
+        return rc;
+    }
+    cudaError_t e = cudaStreamSynchronize(b->stream);
+    tmp.release();
+    if (e != cudaSuccess) {
+        mkf_set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+        return MKF_E_CUDA;
+    }
+    return MKF_OK;
+}
+
+#endif

@@ -1,8 +1,355 @@
-// placeholder, replaced below
-struct mkf_pf2d { int dummy; };
-extern "C" int mkf_pf2d_create(mkf_pf2d**, int64_t, int, int, int, const double*, const double*, const double*, int, void*) { mkf_set_error("not built yet"); return MKF_E_UNSUPPORTED; }
-extern "C" void mkf_pf2d_destroy(mkf_pf2d*) {}
-extern "C" int mkf_pf2d_set_particles(mkf_pf2d*, const double*, int) { return MKF_E_UNSUPPORTED; }
-extern "C" int mkf_pf2d_get(mkf_pf2d*, double*, double*, int32_t*, int) { return MKF_E_UNSUPPORTED; }
-extern "C" int mkf_pf2d_update(mkf_pf2d*, const double*, const double*, const double*, int) { return MKF_E_UNSUPPORTED; }
-extern "C" int mkf_pf2d_sync(mkf_pf2d*) { return MKF_E_UNSUPPORTED; }
+// mkf_pf2d.cuh -- the legacy plain particle filter (src/pf2D.{h,cpp}; not compiled by the reference's
+// CMakeLists.txt:29 but part of the path: "particle likelihoods/sec"), included by mkf_api.cu.
+//
+//   k_pf2d_weight           w_i = [sum_k w_k c_k expf(float(-1/2 d^T Sigma_k^-1 d))] * N2(p[6:8]-z0; 15 I) * N2(p[0:2]-z1; 15 I)
+//                           (src/pf2D.cpp:157-172, :105-109, :124-128) -- one thread per particle
+//   run_resample            normalise (:174-177) + systematic resample (:225-268)
+//   k_pf2d_resample_predict particles.row(i) = old.row(parent_i) (+ N(0,5) per dimension, :90-102)
+#ifndef MKF_PF2D_CUH
+#define MKF_PF2D_CUH
+
+#define MKF_PF2D_MAXD 12
+
+struct mkf_pf2d {
+    long long T = 0;
+    int N = 0, d = 0, K = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    double* part[2] = {nullptr, nullptr}; // T x N x d, ping-pong
+    int cur = 0;
+    double *w_raw = nullptr, *wsum = nullptr;
+    int32_t* parent = nullptr;
+    uint32_t *status = nullptr, *need_fb = nullptr;
+    double* gmm = nullptr; // K x (d + d*d + 2): mean, sigma_i, det_s, weight
+    int gstride = 0;
+    DevBuf in_meas, in_u, in_noise, in_part;
+};
+
+template <int D>
+__global__ void __launch_bounds__(128) k_pf2d_weight(const double* __restrict__ part, const double* __restrict__ meas,
+                                                      const double* __restrict__ gmm, int K, int gstride, long long T,
+                                                      int N, double* __restrict__ w_raw)
+{
+    extern __shared__ double sg[];
+    for (int i = threadIdx.x; i < K * gstride; i += blockDim.x) sg[i] = gmm[i];
+    __syncthreads();
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T * N) return;
+    const long long t = s / N;
+    double x[D];
+    const double2* __restrict__ src = reinterpret_cast<const double2*>(part + s * D);
+#pragma unroll
+    for (int p = 0; p < D / 2; p++) {
+        const double2 q = __ldg(src + p);
+        x[2 * p] = q.x;
+        x[2 * p + 1] = q.y;
+    }
+    double prior = 0.0;
+    for (int k = 0; k < K; k++) {
+        const double* __restrict__ mu = sg + k * gstride;
+        const double* __restrict__ Si = mu + D;
+        double xu[D];
+#pragma unroll
+        for (int c = 0; c < D; c++) xu[c] = __dsub_rn(x[c], mu[c]);
+        // temp = -0.5*x_u*sigma_i (gemm, alpha = -0.5) then * x_u.t() (GEMM_2_T: 4 interleaved partial sums)
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < D; r++) acc = __dadd_rn(acc, __dmul_rn(xu[r], Si[r * D + c]));
+            const double tc = __dmul_rn(acc, -0.5);
+            if (c < (D / 4) * 4)
+                s4[c & 3] = __dadd_rn(s4[c & 3], __dmul_rn(tc, xu[c]));
+            else
+                s4[0] = __dadd_rn(s4[0], __dmul_rn(tc, xu[c]));
+        }
+        const double q = __dadd_rn(__dadd_rn(__dadd_rn(s4[0], s4[1]), s4[2]), s4[3]);
+        // quirk B12: expf(float(q)).  Evaluated as the correctly rounded float of the double exp, which is
+        // what glibc's expf returns except for ~0.4% of arguments where it is off by one float ulp.
+        const double e = (double)(float)exp((double)(float)q);
+        prior = __dadd_rn(prior, __dmul_rn(__dmul_rn(mu[D + D * D + 1], mu[D + D * D]), e));
+    }
+    // eyemvnpdf(x_u, 15): alpha = -0.5*1.0/15; 1/pow(2 pi 15, 1) * exp(alpha*(dx^2 + dy^2))
+    const double alpha = __ddiv_rn(__dmul_rn(-0.5, 1.0), 15.0);
+    const double nrm = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(2.0, 3.14159265358979323846), 15.0)); // 1/pow(2 pi 15, 1)
+    const double* __restrict__ mz = meas + t * 4;
+    double lik = 1.0;
+    {
+        const double dx = __dsub_rn(x[6], mz[0]), dy = __dsub_rn(x[7], mz[1]);
+        const double q = __dadd_rn(__dmul_rn(__dmul_rn(dx, alpha), dx), __dmul_rn(__dmul_rn(dy, alpha), dy));
+        lik = __dmul_rn(nrm, exp(q));
+    }
+    {
+        const double dx = __dsub_rn(x[0], mz[2]), dy = __dsub_rn(x[1], mz[3]);
+        const double q = __dadd_rn(__dmul_rn(__dmul_rn(dx, alpha), dx), __dmul_rn(__dmul_rn(dy, alpha), dy));
+        lik = __dmul_rn(lik, __dmul_rn(nrm, exp(q)));
+    }
+    w_raw[s] = __dmul_rn(prior, lik);
+}
+
+__global__ void k_pf2d_resample_predict(const double* __restrict__ old_p, double* __restrict__ new_p,
+                                        const int32_t* __restrict__ parent, const uint32_t* __restrict__ status,
+                                        const double* __restrict__ noise, long long T, int N, int d)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * N * d) return;
+    const long long s = i / d;
+    const int c = (int)(i - s * d);
+    const long long t = s / N;
+    // degenerate weights: the reference re-randomises the particles with cv::randu (global RNG);
+    // not reproducible -> particles are kept and the status bit reports it
+    const long long sp = (status[t] & MKF_ST_POST_DEGENERATE) ? s : t * N + parent[s];
+    double v = __dadd_rn(0.0, old_p[sp * d + c]); // particles.row(i) = zeros + old_particles.row(idx)
+    if (noise && c < 8) v = __dadd_rn(v, __dmul_rn(noise[i], 5.0));
+    new_p[i] = v;
+}
+
+extern "C" void mkf_pf2d_destroy(mkf_pf2d* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    void* ptrs[] = {p->part[0], p->part[1], p->w_raw, p->wsum, p->parent, p->status, p->need_fb, p->gmm};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    p->in_meas.release();
+    p->in_u.release();
+    p->in_noise.release();
+    p->in_part.release();
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+// host: sigma_i = inv(s) (DECOMP_CHOLESKY), det_s = 1/(pow(2 pi, d/2) sqrt(det s))  (src/pf2D.cpp:28-37)
+static bool pf2d_gaussian(int d, const double* s, double* inv, double* det_s)
+{
+    std::vector<double> Lm(s, s + (size_t)d * d);
+    for (int i = 0; i < d; i++) {
+        for (int j = 0; j < i; j++) {
+            double t = Lm[i * d + j];
+            for (int k = 0; k < j; k++) t -= Lm[i * d + k] * Lm[j * d + k];
+            Lm[i * d + j] = t * Lm[j * d + j];
+        }
+        double t = Lm[i * d + i];
+        for (int k = 0; k < i; k++) t -= Lm[i * d + k] * Lm[i * d + k];
+        if (!(t >= 2.220446049250313e-16)) return false;
+        Lm[i * d + i] = 1.0 / std::sqrt(t);
+    }
+    double det = 1.0;
+    for (int c = 0; c < d; c++) {
+        std::vector<double> y(d);
+        for (int i = 0; i < d; i++) {
+            double t = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < i; k++) t -= Lm[i * d + k] * y[k];
+            y[i] = t * Lm[i * d + i];
+        }
+        for (int i = d - 1; i >= 0; i--) {
+            double t = y[i];
+            for (int k = d - 1; k > i; k--) t -= Lm[k * d + i] * inv[k * d + c];
+            inv[i * d + c] = t * Lm[i * d + i];
+        }
+    }
+    for (int i = 0; i < d; i++) det *= (1.0 / Lm[i * d + i]) * (1.0 / Lm[i * d + i]);
+    *det_s = 1.0 / (std::pow(2.0 * 3.14159265358979323846, d / 2.0) * std::sqrt(det));
+    return true;
+}
+
+extern "C" int mkf_pf2d_create(mkf_pf2d** out, int64_t T, int N, int d, int K, const double* means, const double* covs,
+                               const double* weights, int device, void* stream)
+{
+    if (!out || !means || !covs || !weights || T <= 0 || N <= 0 || K <= 0) {
+        mkf_set_error("mkf_pf2d_create: invalid argument");
+        return MKF_E_INVALID;
+    }
+    *out = nullptr;
+    if (!(d == 8 || d == 10 || d == 12)) {
+        mkf_set_error("mkf_pf2d_create: d=%d not built (d in {8,10,12}; the reference needs d >= 8)", d);
+        return MKF_E_UNSUPPORTED;
+    }
+    int ndev = mkf_device_count();
+    if (ndev <= 0) {
+        mkf_set_error("no CUDA device available: libmkf_b200 has no CPU fallback");
+        return MKF_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        mkf_set_error("mkf_pf2d_create: bad device");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    mkf_pf2d* p = new (std::nothrow) mkf_pf2d;
+    if (!p) return MKF_E_NOMEM;
+    p->T = T;
+    p->N = N;
+    p->d = d;
+    p->K = K;
+    p->device = device;
+    p->gstride = d + d * d + 2;
+    std::vector<double> g((size_t)K * p->gstride);
+    for (int k = 0; k < K; k++) {
+        double* gk = &g[(size_t)k * p->gstride];
+        memcpy(gk, means + (size_t)k * d, sizeof(double) * d);
+        if (!pf2d_gaussian(d, covs + (size_t)k * d * d, gk + d, gk + d + d * d)) {
+            mkf_set_error("mkf_pf2d_create: covariance %d is not positive definite", k);
+            delete p;
+            return MKF_E_INVALID;
+        }
+        gk[d + d * d + 1] = weights[k];
+    }
+    if (stream) {
+        p->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            mkf_set_error("cudaStreamCreate failed");
+            delete p;
+            return MKF_E_CUDA;
+        }
+        p->own_stream = true;
+    }
+    const size_t tot = (size_t)T * N;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&p->part[0], tot * d * 8)) || (e = cudaMalloc((void**)&p->part[1], tot * d * 8)) ||
+        (e = cudaMalloc((void**)&p->w_raw, tot * 8)) || (e = cudaMalloc((void**)&p->wsum, (size_t)T * 8)) ||
+        (e = cudaMalloc((void**)&p->parent, tot * 4)) || (e = cudaMalloc((void**)&p->status, (size_t)T * 4)) ||
+        (e = cudaMalloc((void**)&p->need_fb, (size_t)T * 4)) || (e = cudaMalloc((void**)&p->gmm, g.size() * 8))) {
+        cudaGetLastError();
+        mkf_set_error("mkf_pf2d_create: cudaMalloc failed (%s)", cudaGetErrorString(e));
+        mkf_pf2d_destroy(p);
+        return MKF_E_NOMEM;
+    }
+    cudaMemset(p->part[0], 0, tot * d * 8);
+    cudaMemset(p->w_raw, 0, tot * 8);
+    cudaMemset(p->wsum, 0, (size_t)T * 8);
+    cudaMemset(p->parent, 0, tot * 4);
+    cudaMemset(p->status, 0, (size_t)T * 4);
+    cudaMemset(p->need_fb, 0, (size_t)T * 4);
+    cudaMemcpy(p->gmm, g.data(), g.size() * 8, cudaMemcpyHostToDevice);
+    *out = p;
+    return MKF_OK;
+}
+
+template <class Tp>
+static int pf_in_ptr(mkf_pf2d* p, const Tp* ptr, size_t count, int mem, DevBuf& stage, const Tp** out)
+{
+    if (!ptr) {
+        *out = nullptr;
+        return MKF_OK;
+    }
+    if (is_device_ptr(ptr, mem)) {
+        *out = ptr;
+        return MKF_OK;
+    }
+    int rc = stage.ensure(count * sizeof(Tp));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(stage.p, ptr, count * sizeof(Tp), cudaMemcpyHostToDevice, p->stream));
+    *out = (const Tp*)stage.p;
+    return MKF_OK;
+}
+
+extern "C" int mkf_pf2d_set_particles(mkf_pf2d* p, const double* particles, int mem)
+{
+    if (!p || !particles) {
+        mkf_set_error("mkf_pf2d_set_particles: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    const size_t bytes = (size_t)p->T * p->N * p->d * 8;
+    CK(cudaMemcpyAsync(p->part[p->cur], particles, bytes,
+                       is_device_ptr(particles, mem) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return MKF_OK;
+}
+
+extern "C" int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u, const double* noise, int mem)
+{
+    if (!p || !meas || !u) {
+        mkf_set_error("mkf_pf2d_update: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    const double *d_meas, *d_u, *d_noise;
+    int rc;
+    const long long tot = p->T * p->N;
+    if ((rc = pf_in_ptr(p, meas, (size_t)p->T * 4, mem, p->in_meas, &d_meas))) return rc;
+    if ((rc = pf_in_ptr(p, u, (size_t)p->T, mem, p->in_u, &d_u))) return rc;
+    if ((rc = pf_in_ptr(p, noise, (size_t)tot * p->d, mem, p->in_noise, &d_noise))) return rc;
+    CK(cudaMemsetAsync(p->status, 0, (size_t)p->T * 4, p->stream));
+    const size_t smem = (size_t)p->K * p->gstride * sizeof(double);
+    if (smem > 200 * 1024) {
+        mkf_set_error("mkf_pf2d_update: GMM too large for shared memory");
+        return MKF_E_UNSUPPORTED;
+    }
+#define LAUNCH_W(DD)                                                                                         \
+    do {                                                                                                     \
+        if (smem > 48 * 1024)                                                                                \
+            CK(cudaFuncSetAttribute(k_pf2d_weight<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_pf2d_weight<DD><<<grid_for(tot, 128), 128, smem, p->stream>>>(p->part[p->cur], d_meas, p->gmm, p->K,  \
+                                                                       p->gstride, p->T, p->N, p->w_raw);    \
+    } while (0)
+    if (p->d == 8)
+        LAUNCH_W(8);
+    else if (p->d == 10)
+        LAUNCH_W(10);
+    else
+        LAUNCH_W(12);
+#undef LAUNCH_W
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if ((rc = run_resample(p->stream, p->T, p->need_fb, p->w_raw, p->N, p->N, d_u, 1, 1, p->wsum, p->parent, p->status,
+                           nullptr, 1, 0, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE)))
+        return rc;
+    k_pf2d_resample_predict<<<grid_for(tot * p->d, 256), 256, 0, p->stream>>>(p->part[p->cur], p->part[p->cur ^ 1],
+                                                                              p->parent, p->status, d_noise, p->T,
+                                                                              p->N, p->d);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    p->cur ^= 1;
+    return MKF_OK;
+}
+
+extern "C" int mkf_pf2d_get(mkf_pf2d* p, double* particles, double* w_norm, int32_t* parents, int mem)
+{
+    if (!p) {
+        mkf_set_error("null pf2d");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    const size_t tot = (size_t)p->T * p->N;
+    auto kind = [&](void* dst) { return is_device_ptr(dst, mem) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; };
+    if (particles) CK(cudaMemcpyAsync(particles, p->part[p->cur], tot * p->d * 8, kind(particles), p->stream));
+    if (parents) CK(cudaMemcpyAsync(parents, p->parent, tot * 4, kind(parents), p->stream));
+    DevBuf tmp;
+    if (w_norm) {
+        double* dst = w_norm;
+        const bool host = !is_device_ptr(w_norm, mem);
+        if (host) {
+            int rc = tmp.ensure(tot * 8);
+            if (rc) return rc;
+            dst = (double*)tmp.p;
+        }
+        k_aux_outputs<<<grid_for((long long)tot, 256), 256, 0, p->stream>>>(p->w_raw, p->wsum, nullptr, (long long)tot,
+                                                                           p->N, 0, dst, nullptr);
+        MKF_LAUNCHED();
+        if (host) cudaMemcpyAsync(w_norm, dst, tot * 8, cudaMemcpyDeviceToHost, p->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(p->stream);
+    tmp.release();
+    if (e != cudaSuccess) {
+        mkf_set_error("mkf_pf2d_get: %s", cudaGetErrorString(e));
+        return MKF_E_CUDA;
+    }
+    return MKF_OK;
+}
+
+extern "C" int mkf_pf2d_sync(mkf_pf2d* p)
+{
+    if (!p) {
+        mkf_set_error("null pf2d");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return MKF_OK;
+}
+
+#endif

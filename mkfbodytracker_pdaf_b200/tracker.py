@@ -152,6 +152,12 @@ class TrackBatch:
                                          L.MEM_HOST))
         return st
 
+    def summary_into(self, wsum, status):
+        """per-track wsum (float64) and status (32-bit) of the last update into caller buffers"""
+        mem = _same_mem(wsum, status)
+        L.check(L.lib.mkf_batch_download(self._h, None, None, None, None, None, None, _addr(wsum)[0],
+                                         _addr(status)[0], mem))
+
     def upload(self, x, P):
         x = _h(x, np.float64).reshape(self.T, self.N, self.model.d)
         P = _h(P, np.float64).reshape(self.T, self.N, self.model.d, self.model.d)
@@ -163,6 +169,14 @@ class TrackBatch:
 
     def sync(self):
         L.check(L.lib.mkf_batch_sync(self._h))
+
+    def profile(self, max_updates):
+        L.check(L.lib.mkf_batch_profile(self._h, int(max_updates)))
+
+    def profile_read(self):
+        a, b_, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        L.check(L.lib.mkf_batch_profile_read(self._h, C.byref(a), C.byref(b_), C.byref(c), C.byref(n)))
+        return dict(ms_bounds=a.value, ms_slot_update=b_.value, ms_resample=c.value, n=n.value)
 
     def close(self):
         if self._h:
