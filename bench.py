@@ -49,9 +49,11 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if os.environ.get("MKF_BENCH_SMI_MS") == "0":
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", os.environ.get("MKF_BENCH_SMI_MS", "20"), "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -60,7 +62,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self, which):
+        setattr(self, which, time.perf_counter())
 
     def stop(self):
         if not self.proc:
@@ -74,7 +79,10 @@ class ClockSampler:
         sm, mx, pw = [], [], []
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        inside = [r for (ts, r) in self.rows if t0 is not None and t1 is not None and t0 <= ts <= t1 + 0.03]
+        window = "timed region" if inside else "warm-up + timed region (region shorter than the sampling period)"
+        for r in (inside or [r for (_, r) in self.rows]):
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -89,7 +97,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def load_peak():
@@ -167,7 +176,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tracks", type=int, default=4096, help="tracks per GPU")
@@ -197,7 +206,10 @@ def main():
     T, N, K, W = args.tracks, args.slots, args.steps, args.warmup
     F = K + W
     model = mk.Model.load(mk.LEFT_ARM_MODEL, mk.RIGHT_ARM_MODEL)
-    stream = torch.cuda.current_stream()
+    # everything (our kernels, torch's packing ops, NCCL, the timing events) runs on ONE explicit
+    # stream: torch's default stream has handle 0, which the C ABI reads as "make a private stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     batch = mk.TrackBatch(model, T, N, device=local, stream=stream.cuda_stream)
     track0, _ = shard_tracks(world * T, world, rank)  # weak scaling: T tracks on every rank
 
@@ -223,17 +235,21 @@ def main():
         batch.estimate_into(None, pose)
 
     # ---------------- device-resident run ----------------
-    batch.reset(u0)
-    for f in range(W):
-        step(f)
-    barrier()
-    batch.profile(K)
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
+    batch.reset(u0)
+    for f in range(W):
+        step(f)
+    # warm the summary/gather path too (torch loads its kernels lazily on first use)
+    batch.summary_into(wsum_d, status_d)
+    gather_summaries(pack_summary(pose, wsum_d, status_d), world)
+    barrier()
+    batch.profile(K)
     launches0 = mk.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clk.mark("t0")
     e0.record()
     for f in range(W, F):
         step(f)
@@ -242,6 +258,7 @@ def main():
     gathered = gather_summaries(pack_summary(pose, wsum_d, status_d), world)
     e1.record()
     barrier()
+    clk.mark("t1")
     launches = mk.launch_count() - launches0
     clocks = clk.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
