@@ -159,6 +159,17 @@ int mkf_batch_download(mkf_batch* b, double* x, double* P, double* w_raw, double
                        int32_t* parents, double* wsum, uint32_t* status, int mem);
 int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, int mem);
 
+/* KF_model::predict (stage 1, src/KF_model.cpp:11-15) and/or innovation likelihood + KF_model::update
+ * (stage 2, src/pf2DRao.cpp:138 and src/KF_model.cpp:17-25; stage 3 = both) applied to n explicit
+ * Gaussians with explicit component indices comp[n].  x n x d and P n x d x d in/out, z n x 6 (stage 2),
+ * w_out n likelihoods or NULL.  Host pointers; synchronous.  Backs the KF_model shim. */
+int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int stage, double* x, double* P, const double* z,
+                 double* w_out, int device);
+
+/* ParticleFilter::getSampleProb (src/pf2DRao.cpp:105-122) for one track of a batch: density of C
+ * positions cand_xy (2 x C, row 0 = x) under N(posterior hand estimate, 0.8*scale*I).  Host pointers. */
+int mkf_batch_sample_prob(mkf_batch* b, int64_t track, const double* cand_xy, int C, double scale, double* out);
+
 /* ParticleFilter::resample for one weight vector (src/pf2DRao.cpp:175-210) on the device:
  * w[L] (host), N outputs, u < 0 draws from cv::RNG(seed) as the reference does. */
 int mkf_resample(const double* w, int L, int N, double u, uint64_t seed, int32_t* out, int device);

@@ -87,6 +87,7 @@ struct mkf_batch {
         as_ui, as_up;
     int as_C = 0;
     // optional per-kernel timing (mkf_batch_profile): 4 events per update
+    int stage = 3; // see SlotArgs::stage (mkf_kf_apply runs single stages)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
     int prof_n = 0;
@@ -362,6 +363,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     a.K = m->K;
     a.meas_layout = meas_layout;
     a.chol_mode = m->prm.chol_mode;
+    a.stage = b->stage;
     for (int r = 0; r < MKF_M; r++) a.bh[r] = m->BH[r];
     a.r = m->prm.meas_noise_var;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
@@ -681,4 +683,5 @@ extern "C" int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint6
 }
 
 #include "mkf_assoc.cuh"
+#include "mkf_extra.cuh"
 #include "mkf_pf2d.cuh"

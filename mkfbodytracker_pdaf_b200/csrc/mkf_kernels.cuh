@@ -51,6 +51,7 @@ struct SlotArgs {
     uint32_t* __restrict__ status;
     long long total; // T*N
     int N, K, meas_layout, chol_mode;
+    int stage; // bit 0: KF_model::predict, bit 1: likelihood + KF_model::update (3 = the fused frame step)
     double bh[MKF_M];
     double r; // measurement noise variance (R = r * I)
 };
@@ -66,18 +67,23 @@ struct SlotArgs {
 // -----------------------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ bool slot_math(double (&v)[SlotLay<D>::NE], const double* __restrict__ c,
-                                          const double (&zc)[MKF_M], const double r, const int chol_mode, double& w_out)
+                                          const double (&zc)[MKF_M], const double r, const int chol_mode,
+                                          const int stage, double& w_out)
 {
     using L = SlotLay<D>;
     constexpr int M = MKF_M;
 #define A_(i, j) v[L::OA + tri((i), (j))]
 #define B_(i, a) v[L::OB + (i) * M + (a)]
 #define C_(i, j) v[L::OC + tri((i), (j))]
-    const double g = c[0], g2 = c[1];
+    if (stage & 1) {
+        const double g = c[0], g2 = c[1];
 #pragma unroll
-    for (int e = 0; e < D; e++) v[e] = fma(g, v[e], c[2 + e]);
+        for (int e = 0; e < D; e++) v[e] = fma(g, v[e], c[2 + e]);
 #pragma unroll
-    for (int e = D; e < L::NE; e++) v[e] = fma(g2, v[e], c[2 + e]);
+        for (int e = D; e < L::NE; e++) v[e] = fma(g2, v[e], c[2 + e]);
+    }
+    w_out = 0.0;
+    if (!(stage & 2)) return true;
 
     double y[M];
 #pragma unroll
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
     if (!active) return;
 
     double w;
-    const bool ok = slot_math<D>(v, cst + k * L::CS, zc, a.r, a.chol_mode, w);
+    const bool ok = slot_math<D>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
     if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
 
     double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
