@@ -120,54 +120,77 @@ def load_traffic():
         return None
 
 
-def oracle_model():
+def cpu_arm():
+    """the reference's CPU implementation of the path: oracle/_ref (the reference's own KF_model.cpp, my_gmm.cpp,
+    pf2DRao.cpp compiled against oracle/cvshim) when it was built, else the oracle port.  Returns
+    (kind, run(T, N, frames, seed) -> (seconds, threads))."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import mkf_oracle as orc
     import mkfbodytracker_pdaf_b200 as mk
     m = mk.Model.load(mk.LEFT_ARM_MODEL, mk.RIGHT_ARM_MODEL)
     a = m.arrays()
-    return orc, orc.Model(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"])
+    arrays = {k: a[k] for k in ("means", "covs", "weights", "gamma", "pca_proj", "pca_mean")}
+    if os.environ.get("MKF_BENCH_CPU_KIND", "") != "port":
+        try:
+            import mkf_ref
+            if os.path.exists(mkf_ref.SO):
+                mkf_ref.lib()
+
+                def run(T, N, frames, seed):
+                    return mkf_ref.bench_tracks(arrays, T, N, frames, per_slot=False, seed=seed, jitter=1)
+                return "reference", run
+        except Exception:
+            pass
+    import mkf_oracle as orc
+    om = orc.Model(*[arrays[k] for k in ("means", "covs", "weights", "gamma", "pca_proj", "pca_mean")])
+
+    def run(T, N, frames, seed):
+        secs, used, _ = orc.bench_tracks(om, T, N, frames, per_slot=False, seed=seed, jitter=1)
+        return secs, used
+    return "port", run
+
+
+CPU_DESC = {"reference": "oracle/_ref: the reference's own src/{KF_model,my_gmm,pf2DRao}.cpp on the OpenCV-subset shim",
+            "port": "oracle/mkf_oracle.cpp (C++ restatement)"}
 
 
 def cpu_baseline(N, budget_s=12.0):
-    """the oracle port on all host cores over a bounded sample of the same workload"""
-    orc, om = oracle_model()
+    """the reference CPU path on all host cores over a bounded sample of the same workload"""
+    kind, run = cpu_arm()
     cores = os.cpu_count() or 1
     T_s = 8 * cores
-    secs, used, _ = orc.bench_tracks(om, T_s, N, 2, per_slot=False, seed=SEED, jitter=1)  # calibrate
+    secs, used = run(T_s, N, 2, SEED)  # calibrate
     rate = T_s * 2 / max(secs, 1e-9)
     frames = int(max(2, min(400, budget_s * rate / T_s)))
-    secs, used, _ = orc.bench_tracks(om, T_s, N, frames, per_slot=False, seed=SEED, jitter=1)
+    secs, used = run(T_s, N, frames, SEED)
     fu = T_s * frames / secs
-    return {"value": fu, "unit": UNIT, "cores": used, "kind": "port",
-            "slot_updates_per_s": fu * N,
-            "sample": f"{T_s} tracks x {N} slots x {frames} frames of the same synthetic workload "
-                      f"(oracle/mkf_oracle.cpp, one track per task, OpenMP over tracks, {secs:.2f} s)"}
+    return {"value": fu, "unit": UNIT, "cores": used, "kind": kind, "slot_updates_per_s": fu * N,
+            "sample": f"{T_s} tracks x {N} slots x {frames} frames of the same synthetic workload ({CPU_DESC[kind]}; "
+                      f"one track per task, single-threaded within a track, OpenMP over tracks; {secs:.2f} s)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    orc, om = oracle_model()
+    kind, run = cpu_arm()
     cores = os.cpu_count() or 1
     N = args.slots
     T_s = 8 * cores
     for _ in range(args.warmup):
-        orc.bench_tracks(om, T_s, N, 1, per_slot=False, seed=SEED, jitter=1)
-    t0 = time.perf_counter()
+        run(T_s, N, 1, SEED)
     used = cores
+    dt = 0.0
     for k in range(args.steps):
-        _, used, _ = orc.bench_tracks(om, T_s, N, 1, per_slot=False, seed=SEED + k, jitter=1)
-    dt = time.perf_counter() - t0
+        secs, used = run(T_s, N, 1, SEED + k)  # timed inside: the frame loop only (filter construction excluded)
+        dt += secs
     val = T_s * args.steps / dt
-    sample = (f"each step = 1 frame over {T_s} tracks x {N} slots (of the {args.tracks}-track workload), fresh filters "
-              "per step, reset included")
+    sample = (f"each step = 1 frame over {T_s} tracks x {N} slots (a bounded sample of the {args.tracks}-track workload), "
+              f"{CPU_DESC[kind]}, OpenMP over tracks")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name(args.tracks, N), "sample": sample},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "slot_updates_per_s": val * N, "gpu_launches": 0}
     print(json.dumps(out), flush=True)

@@ -1,0 +1,181 @@
+"""ctypes binding of oracle/_ref/libref.so: the reference's OWN src/KF_model.cpp, src/my_gmm.cpp and
+src/pf2DRao.cpp compiled in place against the OpenCV-subset shim oracle/cvshim (oracle/Makefile).
+
+TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py CPU legs).  The library is rebuilt only where
+/root/reference exists; elsewhere (the GPU box) the prebuilt file that travelled with the snapshot is used.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libref.so")
+_LIB = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def available() -> bool:
+    if os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
+        except Exception:
+            pass
+    return os.path.exists(SO)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not available():
+            raise FileNotFoundError(SO)
+        L = C.CDLL(SO)
+        L.ref_pf_create.restype = C.c_void_p
+        L.ref_pf_create.argtypes = [C.c_int]
+        L.ref_pf_destroy.argtypes = [C.c_void_p]
+        L.ref_pf_load_model.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.ref_pf_get_kf.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.ref_pf_reset.argtypes = [C.c_void_p, C.c_int64]
+        L.ref_pf_update.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64]
+        L.ref_pf_get_state.argtypes = [C.c_void_p, _dp, _dp]
+        L.ref_pf_estimate.argtypes = [C.c_void_p, _dp]
+        L.ref_pf_resample.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int64, _ip]
+        L.ref_pf_chol.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.ref_pf_mvnpdf.restype = C.c_double
+        L.ref_pf_mvnpdf.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        L.ref_kf_predict.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.ref_kf_update.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        L.ref_pf_sample_prob.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_double,
+                                         _dp, _dp]
+        L.ref_pf_get_samples_mean.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, _dp, _dp]
+        L.ref_bench_tracks.restype = C.c_double
+        L.ref_bench_tracks.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, C.c_int,
+                                       C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+class RefFilter:
+    """the reference's ParticleFilter (src/pf2DRao.h:13-31) with its gmm loaded as src/pfPose.cpp:61-65 does"""
+
+    def __init__(self, arrays, N):
+        self.a = {k: _f(v) for k, v in arrays.items()}
+        self.K, self.d = self.a["means"].shape
+        self.D = self.a["pca_proj"].shape[1]
+        self.N = N
+        self.h = lib().ref_pf_create(N)
+        a = self.a
+        lib().ref_pf_load_model(self.h, self.K, self.d, self.D, _p(a["means"]), _p(a["covs"]), _p(a["weights"]),
+                                _p(a["gamma"]), _p(a["pca_proj"]), _p(a["pca_mean"]))
+
+    def kf_members(self, k):
+        d = self.d
+        out = dict(Q=np.zeros((d, d)), B=np.zeros(d), H=np.zeros((6, d)), BH=np.zeros(6), R=np.zeros((6, 6)),
+                   F=np.zeros((d, d)))
+        lib().ref_pf_get_kf(self.h, k, *[_p(out[n]) for n in ("Q", "B", "H", "BH", "R", "F")])
+        return out
+
+    def reset(self, tick):
+        lib().ref_pf_reset(self.h, int(tick))
+
+    def update(self, meas, tick_ind, tick_post):
+        meas = _f(meas)
+        assert meas.shape == (6, self.N)
+        lib().ref_pf_update(self.h, _p(meas), int(tick_ind), int(tick_post))
+
+    def get_state(self):
+        x = np.zeros((self.N, self.d))
+        P = np.zeros((self.N, self.d, self.d))
+        lib().ref_pf_get_state(self.h, _p(x), _p(P))
+        return x, P
+
+    def estimate(self):
+        xb = np.zeros(self.d)
+        lib().ref_pf_estimate(self.h, _p(xb))
+        return xb
+
+    def resample(self, w, N, tick):
+        w = _f(w)
+        out = np.zeros(N, np.int32)
+        lib().ref_pf_resample(self.h, _p(w), len(w), N, int(tick), out.ctypes.data_as(_ip))
+        return out
+
+    def chol(self, S):
+        S = _f(S)
+        out = np.zeros_like(S)
+        lib().ref_pf_chol(self.h, S.shape[0], _p(S), _p(out))
+        return out
+
+    def mvnpdf(self, x, u, S):
+        x, u, S = _f(x), _f(u), _f(S)
+        return lib().ref_pf_mvnpdf(self.h, len(x), _p(x), _p(u), _p(S))
+
+    def kf_predict(self, k, x, P):
+        x, P = _f(x).copy(), _f(P).copy()
+        lib().ref_kf_predict(self.h, k, _p(x), _p(P))
+        return x, P
+
+    def kf_update(self, k, z, x, P):
+        z, x, P = _f(z), _f(x).copy(), _f(P).copy()
+        lib().ref_kf_update(self.h, k, _p(z), _p(x), _p(P))
+        return x, P
+
+    def sample_prob(self, in1, in2, scale):
+        in1, in2 = _f(in1), _f(in2)
+        w1, w2 = np.zeros(in1.shape[1]), np.zeros(in2.shape[1])
+        lib().ref_pf_sample_prob(self.h, self.d, self.D, _p(self.a["pca_proj"]), _p(self.a["pca_mean"]), _p(in1),
+                                 in1.shape[1], _p(in2), in2.shape[1], float(scale), _p(w1), _p(w2))
+        return w1, w2
+
+    def samples_mean_sd(self, N, scale):
+        m, s = np.zeros(2), np.zeros(2)
+        lib().ref_pf_get_samples_mean(self.h, self.d, self.D, _p(self.a["pca_proj"]), _p(self.a["pca_mean"]), N,
+                                      float(scale), _p(m), _p(s))
+        return m, s
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ref_pf_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def tick_to_u(tick, L):
+    """the uniform draw cv::RNG(tick) produces inside resample(): one discarded uniform(0,L), then uniform(0.0,1.0)"""
+    s = int(tick) & 0xFFFFFFFFFFFFFFFF
+    if s == 0:
+        s = 0xFFFFFFFF
+
+    def nxt():
+        nonlocal s
+        s = ((s & 0xFFFFFFFF) * 4164903690 + (s >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return s & 0xFFFFFFFF
+
+    nxt()
+    t = nxt()
+    return ((t << 32) | nxt()) * 5.4210108624275221700372640043497e-20
+
+
+def bench_tracks(arrays, T, N, frames, per_slot=False, seed=0x5EED0002, jitter=1, threads=0):
+    a = {k: _f(v) for k, v in arrays.items()}
+    K, d = a["means"].shape
+    D = a["pca_proj"].shape[1]
+    used = C.c_int(0)
+    secs = lib().ref_bench_tracks(K, d, D, _p(a["means"]), _p(a["covs"]), _p(a["weights"]), _p(a["gamma"]),
+                                  _p(a["pca_proj"]), _p(a["pca_mean"]), T, N, frames, int(per_slot), int(seed),
+                                  int(jitter), threads, C.byref(used))
+    return secs, used.value
