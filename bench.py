@@ -120,6 +120,15 @@ def load_traffic():
         return None
 
 
+def host_cores():
+    """threads the CPU legs use: every core this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    which must not throttle the reference arm, so the count is passed explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_arm():
     """the reference's CPU implementation of the path: oracle/_ref (the reference's own KF_model.cpp, my_gmm.cpp,
     pf2DRao.cpp compiled against oracle/cvshim) when it was built, else the oracle port.  Returns
@@ -136,7 +145,8 @@ def cpu_arm():
                 mkf_ref.lib()
 
                 def run(T, N, frames, seed):
-                    return mkf_ref.bench_tracks(arrays, T, N, frames, per_slot=False, seed=seed, jitter=1)
+                    return mkf_ref.bench_tracks(arrays, T, N, frames, per_slot=False, seed=seed, jitter=1,
+                                                threads=host_cores())
                 return "reference", run
         except Exception:
             pass
@@ -144,7 +154,7 @@ def cpu_arm():
     om = orc.Model(*[arrays[k] for k in ("means", "covs", "weights", "gamma", "pca_proj", "pca_mean")])
 
     def run(T, N, frames, seed):
-        secs, used, _ = orc.bench_tracks(om, T, N, frames, per_slot=False, seed=seed, jitter=1)
+        secs, used, _ = orc.bench_tracks(om, T, N, frames, per_slot=False, seed=seed, jitter=1, threads=host_cores())
         return secs, used
     return "port", run
 
@@ -156,7 +166,7 @@ CPU_DESC = {"reference": "oracle/_ref: the reference's own src/{KF_model,my_gmm,
 def cpu_baseline(N, budget_s=12.0):
     """the reference CPU path on all host cores over a bounded sample of the same workload"""
     kind, run = cpu_arm()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     T_s = 8 * cores
     secs, used = run(T_s, N, 2, SEED)  # calibrate
     rate = T_s * 2 / max(secs, 1e-9)
@@ -173,7 +183,7 @@ def run_reference(args):
     if rank != 0:
         return
     kind, run = cpu_arm()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     N = args.slots
     T_s = 8 * cores
     for _ in range(args.warmup):
