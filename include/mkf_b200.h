@@ -51,7 +51,9 @@ extern "C" {
 #define MKF_CHOL_CV3_LITERAL 1  /* ... on OpenCV >= 3.0 (diagonal convention of cv::Cholesky differs) */
 #define MKF_CHOL_EXACT 2        /* true upper Cholesky factor (MATLAB mvnpdf, the evident intent) */
 #define MKF_ALIAS_INDEPENDENT 0 /* each slot owns its Gaussian (north_star: one KF per particle) */
-#define MKF_ALIAS_CV_SHALLOW_LITERAL 1 /* quirk B3 (src/pf2DRao.cpp:155); not built: MKF_E_UNSUPPORTED */
+#define MKF_ALIAS_CV_SHALLOW_LITERAL 1 /* quirk B3 (src/pf2DRao.cpp:153-156): slots that drew the same parent
+                                          share its buffer and are filtered sequentially in place, as the
+                                          reference binary really does */
 
 /* memory space of caller pointers */
 #define MKF_MEM_AUTO 0 /* ask the driver (cudaPointerGetAttributes) */

@@ -77,6 +77,8 @@ struct mkf_batch {
     double* wsum = nullptr;
     uint32_t* status = nullptr;
     uint32_t* need_fb = nullptr;
+    uint32_t* unsorted = nullptr;  // per track: last posterior resample left unsorted parents
+    int32_t* chain_last = nullptr; // T x N scratch of the literal alias mode
     // model constants on this device
     double *d_comp = nullptr, *d_init = nullptr, *d_cw_hi = nullptr, *d_cw_lo = nullptr, *d_wprior = nullptr,
            *d_recon = nullptr, *d_pmean = nullptr, *d_tm = nullptr, *d_tinv = nullptr;
@@ -168,7 +170,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->bounds, b->w_raw, b->wsum,   b->status, b->need_fb, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->bounds, b->w_raw, b->wsum,   b->status, b->need_fb, b->unsorted, b->chain_last, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -243,11 +245,16 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     if ((rc = dmalloc((void**)&b->wsum, (size_t)T * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->status, (size_t)T * sizeof(uint32_t)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->need_fb, (size_t)2 * T * sizeof(uint32_t)))) return fail(rc);
+    if ((rc = dmalloc((void**)&b->unsorted, (size_t)T * sizeof(uint32_t)))) return fail(rc);
+    if (m->prm.alias_mode == MKF_ALIAS_CV_SHALLOW_LITERAL &&
+        (rc = dmalloc((void**)&b->chain_last, (size_t)b->total * sizeof(int32_t))))
+        return fail(rc);
     // the tail lanes of the last tile are read by nobody but keep them defined
     if (cudaMemset(b->st[0], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
         cudaMemset(b->st[1], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
         cudaMemset(b->status, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemset(b->need_fb, 0, (size_t)2 * T * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemset(b->unsorted, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemset(b->w_raw, 0, (size_t)b->total * sizeof(double)) != cudaSuccess ||
         cudaMemset(b->wsum, 0, (size_t)T * sizeof(double)) != cudaSuccess ||
         cudaMemset(b->parent, 0, (size_t)b->total * sizeof(int32_t)) != cudaSuccess ||
@@ -299,6 +306,7 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     int rc = in_ptr(b, u_init, (size_t)b->T, mem, b->in_u0, &d_u);
     if (rc) return rc;
     CK(cudaMemsetAsync(b->status, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
+    CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if ((rc = launch_bounds_kernel(b, d_u))) return rc;
     b->cur = 0;
     if (b->m->d == 12)
@@ -316,7 +324,7 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
 static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, const double* d_w, int L, int N,
                         const double* d_u, int u_stride, int normalise, double* d_wsum, int32_t* d_out,
                         uint32_t* d_status, const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb,
-                        uint32_t bit_deg)
+                        uint32_t bit_deg, uint32_t* d_unsorted = nullptr)
 {
     if (L <= 64 && N <= 64) {
         k_resample_small<<<grid_for(nt, 128), 128, 0, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
@@ -328,7 +336,7 @@ static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, co
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     k_resample_fallback<<<grid_for(nt, 128), 128, 0, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
-                                                                d_seeds, seed_stride, seed_off, need_fb);
+                                                                d_seeds, seed_stride, seed_off, need_fb, d_unsorted);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     return MKF_OK;
@@ -364,6 +372,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     a.meas_layout = meas_layout;
     a.chol_mode = m->prm.chol_mode;
     a.stage = b->stage;
+    a.alias_chain = (m->prm.alias_mode == MKF_ALIAS_CV_SHALLOW_LITERAL) ? 1 : 0;
+    a.unsorted = b->unsorted;
     for (int r = 0; r < MKF_M; r++) a.bh[r] = m->BH[r];
     a.r = m->prm.meas_noise_var;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
@@ -384,10 +394,18 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    if (a.alias_chain) { // tracks whose parents are unsorted (after the random-index fallback): sequential walk
+        if (m->d == 12)
+            k_slot_update_unsorted<12><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
+        else
+            k_slot_update_unsorted<10><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
+        MKF_LAUNCHED();
+        CK(cudaGetLastError());
+    }
     if (prof) cudaEventRecord(pe[2], b->stream);
     b->cur ^= 1;
     rc = run_resample(b->stream, b->T, b->need_fb, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status,
-                      d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE);
+                      d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE, b->unsorted);
     if (prof) {
         cudaEventRecord(pe[3], b->stream);
         b->prof_n++;
@@ -582,6 +600,7 @@ extern "C" int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, 
     if ((rc = in_ptr(b, x, (size_t)b->total * d, mem, b->in_x, &dx))) return rc;
     if ((rc = in_ptr(b, P, (size_t)b->total * d * d, mem, b->in_p, &dP))) return rc;
     b->cur = 0;
+    CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if (d == 12)
         k_upload<12><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[0], b->parent, dx, dP, b->d_tm, b->total, b->N);
     else
@@ -647,7 +666,7 @@ extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t se
             k_resample_block<128, 4><<<1, 128>>>(d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, 1, d_fb,
                                                  MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE);
         MKF_LAUNCHED();
-        k_resample_fallback<<<1, 32>>>(d_w, 1, L, N, d_u, 1, 0, d_ws, d_out, d_seed, 1, 0, d_fb);
+        k_resample_fallback<<<1, 32>>>(d_w, 1, L, N, d_u, 1, 0, d_ws, d_out, d_seed, 1, 0, d_fb, nullptr);
         MKF_LAUNCHED();
         e = cudaMemcpy(out, d_out, (size_t)N * 4, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {

@@ -73,6 +73,8 @@ extern "C" int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int 
     a.meas_layout = MKF_MEAS_SHARED;
     a.chol_mode = m->prm.chol_mode;
     a.stage = stage;
+    a.alias_chain = 0;
+    a.unsorted = nullptr;
     for (int r = 0; r < MKF_M; r++) a.bh[r] = m->BH[r];
     a.r = m->prm.meas_noise_var;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);

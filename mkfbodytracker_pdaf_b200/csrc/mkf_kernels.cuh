@@ -52,6 +52,8 @@ struct SlotArgs {
     long long total; // T*N
     int N, K, meas_layout, chol_mode;
     int stage; // bit 0: KF_model::predict, bit 1: likelihood + KF_model::update (3 = the fused frame step)
+    int alias_chain;                      // 1 = MKF_ALIAS_CV_SHALLOW_LITERAL
+    const uint32_t* __restrict__ unsorted; // per track: parents are not sorted (random-index fallback ran)
     double bh[MKF_M];
     double r; // measurement noise variance (R = r * I)
 };
@@ -225,6 +227,25 @@ __device__ __forceinline__ int mkf_component_of(const int32_t* __restrict__ bt, 
     return k;
 }
 
+// measurement column of local slot j of track t, minus BH
+__device__ __forceinline__ void mkf_load_meas(const SlotArgs& a, long long t, int j, double (&zc)[MKF_M])
+{
+    if (a.meas_layout == MKF_MEAS_SHARED) {
+#pragma unroll
+        for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + t * MKF_M + r) - a.bh[r];
+    } else {
+#pragma unroll
+        for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + (t * MKF_M + r) * a.N + j) - a.bh[r];
+    }
+}
+
+// One thread per slot.  alias_chain == 0 (MKF_ALIAS_INDEPENDENT): every slot starts from its parent's
+// Gaussian.  alias_chain == 1 (MKF_ALIAS_CV_SHALLOW_LITERAL, quirk B3 of src/pf2DRao.cpp:153-156): the
+// slots that drew the same parent share one cv::Mat buffer in the reference and are predicted/updated
+// sequentially in place, so slot j starts from the snapshot slot j-1 left behind.  Parents are sorted
+// after systematic resampling, so such slots form a run of consecutive slots: the thread of the run's
+// first slot walks the whole run with the Gaussian held in registers and stores a snapshot per slot;
+// the other threads of the run retire at once.
 template <int D>
 __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
 {
@@ -242,47 +263,103 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
     }
 
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = s < a.total;
+    bool active = s < a.total;
     double v[L::NE];
     double zc[MKF_M];
-    int k = 0;
+    int k = 0, j = 0, len = 1;
     long long t = 0;
+    const int32_t* __restrict__ bt = nullptr;
     if (active) {
         t = s / a.N;
-        const int j = (int)(s - t * a.N);
-        const long long sp = t * a.N + __ldg(a.parent + s);
-        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
-#pragma unroll
-        for (int p = 0; p < L::NP; p++) {
-            const double2 q = __ldg(src + p * 32);
-            v[2 * p] = q.x;
-            if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+        j = (int)(s - t * a.N);
+        const int par = __ldg(a.parent + s);
+        if (a.alias_chain) {
+            if (a.unsorted[t]) {
+                active = false; // random-index fallback left unsorted parents: k_slot_update_unsorted handles the track
+            } else if (j > 0 && __ldg(a.parent + s - 1) == par) {
+                active = false; // not the first slot of its run
+            } else {
+                while (j + len < a.N && __ldg(a.parent + s + len) == par) len++;
+            }
         }
-        if (a.meas_layout == MKF_MEAS_SHARED) {
+        if (active) {
+            const long long sp = t * a.N + par;
+            const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
 #pragma unroll
-            for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + t * MKF_M + r) - a.bh[r];
-        } else {
-#pragma unroll
-            for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + (t * MKF_M + r) * a.N + j) - a.bh[r];
+            for (int p = 0; p < L::NP; p++) {
+                const double2 q = __ldg(src + p * 32);
+                v[2 * p] = q.x;
+                if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+            }
+            mkf_load_meas(a, t, j, zc);
+            bt = a.bounds + t * (a.K + 2);
+            k = mkf_component_of(bt, a.K, j);
         }
-        k = mkf_component_of(a.bounds + t * (a.K + 2), a.K, j);
     }
     mkf_mbar_wait(&mbar, 0);
     if (!active) return;
 
-    double w;
-    const bool ok = slot_math<D>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
-    if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
-
-    double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+    for (int i = 0;;) {
+        double w;
+        const bool ok = slot_math<D>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+        if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+        const long long so = s + i;
+        double2* __restrict__ dst = a.st_out + (so >> 5) * (long long)(L::NP * 32) + (so & 31);
 #pragma unroll
-    for (int p = 0; p < L::NP; p++) {
-        double2 q;
-        q.x = v[2 * p];
-        q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-        __stcs(dst + p * 32, q);
+        for (int p = 0; p < L::NP; p++) {
+            double2 q;
+            q.x = v[2 * p];
+            q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+            __stcs(dst + p * 32, q);
+        }
+        a.w_raw[so] = w;
+        if (++i >= len) break;
+        mkf_load_meas(a, t, j + i, zc);
+        k = mkf_component_of(bt, a.K, j + i);
     }
-    a.w_raw[s] = w;
+}
+
+// alias_chain with UNSORTED parents (only after the degenerate random-index fallback of
+// src/pf2DRao.cpp:184-192): slots sharing a parent are not adjacent, so one thread per flagged track
+// walks the slots in order, starting each from the latest snapshot taken for its parent.
+// last: T x N scratch (latest snapshot slot per parent, -1 = none yet).
+template <int D>
+__global__ void __launch_bounds__(128, 2) k_slot_update_unsorted(const SlotArgs a, int32_t* __restrict__ last)
+{
+    using L = SlotLay<D>;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.total / a.N || !a.unsorted[t]) return;
+    int32_t* __restrict__ lt = last + t * a.N;
+    for (int j = 0; j < a.N; j++) lt[j] = -1;
+    const int32_t* __restrict__ bt = a.bounds + t * (a.K + 2);
+    for (int j = 0; j < a.N; j++) {
+        const long long s = t * a.N + j;
+        const int par = a.parent[s];
+        const int snap = lt[par];
+        const double2* __restrict__ base = snap >= 0 ? (const double2*)a.st_out : a.st_in;
+        const long long sp = t * a.N + (snap >= 0 ? snap : par);
+        const double2* __restrict__ src = base + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+        double v[L::NE];
+        for (int p = 0; p < L::NP; p++) {
+            const double2 q = src[p * 32]; // plain load: the source may be a snapshot this thread stored earlier
+            v[2 * p] = q.x;
+            if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+        }
+        double zc[MKF_M], w;
+        mkf_load_meas(a, t, j, zc);
+        const int k = mkf_component_of(bt, a.K, j);
+        const bool ok = slot_math<D>(v, a.comp_const + (long long)k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+        if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+        double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+        for (int p = 0; p < L::NP; p++) {
+            double2 q;
+            q.x = v[2 * p];
+            q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+            dst[p * 32] = q;
+        }
+        a.w_raw[s] = w;
+        lt[par] = j;
+    }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -514,10 +591,12 @@ __global__ void k_resample_fallback(const double* __restrict__ w_all, long long 
                                     const double* __restrict__ u, int u_stride, int normalise,
                                     const double* __restrict__ wsum_in, int32_t* __restrict__ out_all,
                                     const uint64_t* __restrict__ seeds, int seed_stride, int seed_off,
-                                    uint32_t* __restrict__ need_fb)
+                                    uint32_t* __restrict__ need_fb, uint32_t* __restrict__ unsorted)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T || !need_fb[t]) return;
+    if (t >= T) return;
+    if (unsorted) unsorted[t] = 0u;
+    if (!need_fb[t]) return;
     need_fb[t] = 0u;
     const double* __restrict__ w = w_all + t * L;
     int32_t* out = out_all + t * N;
@@ -531,6 +610,7 @@ __global__ void k_resample_fallback(const double* __restrict__ w_all, long long 
         mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
         (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
         for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
+        if (unsorted) unsorted[t] = 1u; // random indices are not sorted (matters for the literal alias mode)
         return;
     }
     auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };

@@ -184,9 +184,9 @@ int mkf_model_finalize(mkf_model* m)
         mkf_set_error("unsupported model shape K=%d D=%d (need 1<=K<=64, 14<=D<=32)", K, D);
         return MKF_E_INVALID;
     }
-    if (m->prm.alias_mode != MKF_ALIAS_INDEPENDENT) {
-        mkf_set_error("alias_mode CV_SHALLOW_LITERAL (quirk B3) is not built on the device; see DESIGN.md");
-        return MKF_E_UNSUPPORTED;
+    if (m->prm.alias_mode != MKF_ALIAS_INDEPENDENT && m->prm.alias_mode != MKF_ALIAS_CV_SHALLOW_LITERAL) {
+        mkf_set_error("invalid alias_mode %d", m->prm.alias_mode);
+        return MKF_E_INVALID;
     }
     if (m->prm.chol_mode < 0 || m->prm.chol_mode > 2 || !(m->prm.meas_noise_var > 0)) {
         mkf_set_error("invalid mkf_params");

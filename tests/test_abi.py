@@ -82,10 +82,12 @@ def test_model_argument_validation(left_arm):
         mk.Model.from_arrays(np.zeros((3, 11)), np.tile(np.eye(11), (3, 1)), np.ones(3) / 3, np.ones(3) * 0.9,
                              np.zeros((11, 22)), np.zeros(22))
     p = mk.default_params()
-    p.alias_mode = L.ALIAS_CV_SHALLOW_LITERAL
+    p.alias_mode = 7
     with pytest.raises(mk.MkfError) as e:
         mk.Model.from_arrays(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"], p)
-    assert e.value.code == L.E_UNSUPPORTED
+    assert e.value.code == L.E_INVALID
+    p.alias_mode = L.ALIAS_CV_SHALLOW_LITERAL  # quirk B3 is a supported mode
+    mk.Model.from_arrays(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"], p)
 
 
 def test_no_cpu_fallback(left_arm):

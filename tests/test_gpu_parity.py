@@ -286,3 +286,93 @@ def test_full_size_properties_config2(left_arm):
         assert np.array_equal(par[t], r["parents"])
         xo, _ = f.get_state()
         assert rel_err(d["x"][t], xo) <= RTOL
+
+
+def literal_model(arm):
+    a = arm.arrays
+    p = mk.default_params()
+    p.alias_mode = L.ALIAS_CV_SHALLOW_LITERAL
+    return mk.Model.from_arrays(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"], p)
+
+
+@pytest.mark.parametrize("N", [500, 37])
+def test_literal_alias_mode_matches_oracle_and_reference_sources(left_arm, N):
+    """alias_mode = CV_SHALLOW_LITERAL (quirk B3): the GPU must equal the oracle in literal mode and -- through
+    oracle/_ref -- the reference's own pf2DRao.cpp, free-running, indices bit-exact"""
+    import mkf_ref
+    have_ref = mkf_ref.available()
+    T, frames, seed = 3, 10, 0x5EED0001
+    rng = np.random.default_rng(17)
+    tick0 = [int(x) for x in rng.integers(1, 2**62, T)]
+    u0 = np.array([mkf_ref.tick_to_u(t, 15) for t in tick0])
+    fs = [orc.Filter(left_arm.orc, N, alias_mode=orc.ALIAS_CV_SHALLOW_LITERAL) for _ in range(T)]
+    fi = orc.Filter(left_arm.orc, N, alias_mode=orc.ALIAS_INDEPENDENT)
+    for f, u in zip(fs + [fi], list(u0) + [u0[0]]):
+        f.reset(u=u)
+    rf = None
+    if have_ref:
+        a = left_arm.arrays
+        rf = mkf_ref.RefFilter({k: a[k] for k in ("means", "covs", "weights", "gamma", "pca_proj", "pca_mean")}, N)
+        rf.reset(tick0[0])
+    b = mk.TrackBatch(literal_model(left_arm), T, N)
+    b.reset(u0)
+    differs_from_independent = False
+    for fr in range(frames):
+        meas, _, _ = synth_frame(seed, range(T), fr, N, jitter=0)
+        ticks = rng.integers(1, 2**62, (T, 2))
+        ui = np.array([mkf_ref.tick_to_u(t, 15) for t in ticks[:, 0]])
+        up = np.array([mkf_ref.tick_to_u(t, N) for t in ticks[:, 1]])
+        res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+        fi.update(meas[0], ui[0], up[0])
+        b.update(meas, ui, up)
+        stats, d = compare_frame(b, fs, res, check_state=True)
+        assert_parity(stats)
+        assert stats["x"] < 1e-9 and stats["P"] < 1e-9 and stats["w"] < 1e-9
+        if rf is not None:
+            rf.update(meas[0], int(ticks[0, 0]), int(ticks[0, 1]))
+            xr, Pr = rf.get_state()
+            assert rel_err(d["x"][0], xr) <= RTOL and rel_err(d["P"][0], Pr) <= RTOL
+            xb, _ = b.estimate()
+            assert rel_err(xb[0], rf.estimate()) <= RTOL
+        xi, _ = fi.get_state()
+        if fr >= 1 and rel_err(d["x"][0], xi) > 1e-3:
+            differs_from_independent = True
+    assert differs_from_independent, "literal aliasing must change the result from frame 2 on"
+
+
+@pytest.mark.parametrize("alias", [0, 1])
+def test_degenerate_frame_then_recovery(left_arm, alias):
+    """all weights underflow (measurement far away) -> cv::RNG random-index fallback (unsorted parents, seeded);
+    the following frames must still match the oracle in both alias modes"""
+    T, N = 4, 120
+    a = left_arm.arrays
+    p = mk.default_params()
+    p.alias_mode = alias
+    m = mk.Model.from_arrays(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"], p)
+    u0 = np.array([0.11, 0.37, 0.62, 0.93])
+    fs = [orc.Filter(left_arm.orc, N, alias_mode=alias) for _ in range(T)]
+    for f, u in zip(fs, u0):
+        f.reset(u=u)
+    b = mk.TrackBatch(m, T, N)
+    b.reset(u0)
+    rng = np.random.default_rng(23)
+    for fr in range(5):
+        meas, ui, up = synth_frame(0x5EED0002, range(T), fr, N)
+        if fr == 1:
+            meas[1:3, 2:4, :] = 1e5  # tracks 1 and 2 lose the hand completely on this frame
+        seeds = rng.integers(1, 2**62, (T, 2)).astype(np.uint64)
+        res = [fs[t].update(meas[t], ui[t], up[t], seed_ind=int(seeds[t, 0]), seed_post=int(seeds[t, 1]))
+               for t in range(T)]
+        b.update(meas, ui, up, seeds=seeds)
+        d = b.download()
+        for t in range(T):
+            assert np.array_equal(d["parents"][t], res[t]["parents"]), (fr, t)
+            deg = bool(res[t]["status"] & 2)
+            assert deg == bool(d["status"][t] & L.ST_POST_DEGENERATE)
+            assert deg == (fr == 1 and t in (1, 2))
+            if deg:
+                assert res[t]["wsum"] == 0 and d["wsum"][t] == 0 and np.isnan(d["w_norm"][t]).all()
+            else:
+                assert rel_err_weights(d["w_norm"][t], res[t]["w_norm"]) <= RTOL
+            xo, Po = fs[t].get_state()
+            assert rel_err(d["x"][t], xo) <= RTOL and rel_err(d["P"][t], Po) <= RTOL
