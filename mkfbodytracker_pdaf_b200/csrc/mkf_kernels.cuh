@@ -59,6 +59,95 @@ struct SlotArgs {
 };
 
 // -----------------------------------------------------------------------------------------
+// cv::Cholesky failure branch (a pivot < DBL_EPSILON, src/pf2DRao.cpp:37,52), literal:
+//   * chol() hands back the PARTIALLY factored clone (rows above the failing one factored with 1/L_ii on
+//     their diagonal, the failing row's off-diagonals replaced, everything else untouched) and mvnpdf uses
+//     it as R: v = y^T R^-1 through cv::invert(DECOMP_LU), log of its diagonal (possibly NaN);
+//   * KF_model::update inverts S by LU regardless (src/KF_model.cpp:21).
+// Rare, so it lives out of line on local-memory arrays.  W = S^-1 (lower packed) feeds the common update.
+// -----------------------------------------------------------------------------------------
+__device__ __noinline__ bool mkf_lu_invert6(double* A /* 36, destroyed */, double* b /* 36: out */)
+{
+    const int m = 6;
+    for (int i = 0; i < 36; i++) b[i] = ((i / 6) == (i % 6)) ? 1.0 : 0.0;
+    for (int i = 0; i < m; i++) {
+        int k = i;
+        for (int j = i + 1; j < m; j++)
+            if (fabs(A[j * m + i]) > fabs(A[k * m + i])) k = j;
+        if (fabs(A[k * m + i]) < DBL_EPSILON) {
+            for (int q = 0; q < 36; q++) b[q] = 0.0; // cv::invert: dst = Scalar(0)
+            return false;
+        }
+        if (k != i) {
+            for (int j = i; j < m; j++) {
+                double tmp = A[i * m + j];
+                A[i * m + j] = A[k * m + j];
+                A[k * m + j] = tmp;
+            }
+            for (int j = 0; j < m; j++) {
+                double tmp = b[i * m + j];
+                b[i * m + j] = b[k * m + j];
+                b[k * m + j] = tmp;
+            }
+        }
+        const double d = -1.0 / A[i * m + i];
+        for (int j = i + 1; j < m; j++) {
+            const double alpha = A[j * m + i] * d;
+            for (k = i + 1; k < m; k++) A[j * m + k] = fma(alpha, A[i * m + k], A[j * m + k]);
+            for (k = 0; k < m; k++) b[j * m + k] = fma(alpha, b[i * m + k], b[j * m + k]);
+        }
+        A[i * m + i] = -d;
+    }
+    for (int i = m - 1; i >= 0; i--)
+        for (int j = 0; j < m; j++) {
+            double sacc = b[i * m + j];
+            for (int k = i + 1; k < m; k++) sacc = fma(-A[i * m + k], b[k * m + j], sacc);
+            b[i * m + j] = sacc * A[i * m + i];
+        }
+    return true;
+}
+
+__device__ __noinline__ void mkf_chol_fail_path(const double* Sfull /* 36 */, const double* y /* 6 */, int chol_mode,
+                                                double* w_out, double* Wpacked /* 21 */)
+{
+    const int m = 6;
+    double R[36], Ri[36], T[36];
+    for (int i = 0; i < 36; i++) R[i] = Sfull[i];
+    if (chol_mode != MKF_CHOL_EXACT) { // CholImpl in place until the failing pivot
+        for (int i = 0; i < m; i++) {
+            int j;
+            double sacc;
+            for (j = 0; j < i; j++) {
+                sacc = R[i * m + j];
+                for (int k = 0; k < j; k++) sacc -= R[i * m + k] * R[j * m + k];
+                R[i * m + j] = sacc * R[j * m + j];
+            }
+            sacc = R[i * m + i];
+            for (int k = 0; k < j; k++) sacc -= R[i * m + k] * R[i * m + k];
+            if (sacc < DBL_EPSILON) break;
+            R[i * m + i] = 1.0 / sqrt(sacc);
+        }
+    }
+    for (int i = 0; i < 36; i++) T[i] = R[i];
+    mkf_lu_invert6(T, Ri);
+    double q0 = 0.0, q1 = 0.0, lsd = 0.0;
+    for (int j = 0; j < m; j++) {
+        double v = 0.0;
+        for (int k = 0; k < m; k++) v = fma(y[k], Ri[k * m + j], v);
+        if (j & 1)
+            q1 = fma(v, v, q1);
+        else
+            q0 = fma(v, v, q0);
+        lsd += log(R[j * m + j]);
+    }
+    *w_out = exp(-0.5 * (q0 + q1) - lsd - 5.5136311992280356);
+    for (int i = 0; i < 36; i++) T[i] = Sfull[i];
+    mkf_lu_invert6(T, Ri); // S.inv() of KF_model::update
+    for (int a = 0; a < m; a++)
+        for (int b = 0; b <= a; b++) Wpacked[a * (a + 1) / 2 + b] = 0.5 * (Ri[a * m + b] + Ri[b * m + a]);
+}
+
+// -----------------------------------------------------------------------------------------
 // the per-slot arithmetic in the measurement-aligned basis (H' = [I 0]):
 //   predict      x <- g x + b',  P <- g^2 P + Q'
 //   innovation   y = (z - BH) - x1,  S = A + r I   (A = P11)
@@ -164,6 +253,14 @@ __device__ __forceinline__ bool slot_math(double (&v)[SlotLay<D>::NE], const dou
             for (int k = a; k < M; k++) s = fma(Li[tri(k, a)], Li[tri(k, b)], s);
             W[tri(a, b)] = s;
         }
+    if (!ok) { // literal cv::Cholesky-failure semantics (rare): likelihood from the unfactored matrix, LU inverse
+        double Sf[36];
+#pragma unroll
+        for (int a = 0; a < M; a++)
+#pragma unroll
+            for (int b = 0; b < M; b++) Sf[a * M + b] = ((a >= b) ? A_(a, b) : A_(b, a)) + ((a == b) ? r : 0.0);
+        mkf_chol_fail_path(Sf, y, chol_mode, &w_out, W);
+    }
 #define W_(a, b) W[((a) >= (b)) ? tri((a), (b)) : tri((b), (a))]
 
     // state mean

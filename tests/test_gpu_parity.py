@@ -369,10 +369,90 @@ def test_degenerate_frame_then_recovery(left_arm, alias):
             assert np.array_equal(d["parents"][t], res[t]["parents"]), (fr, t)
             deg = bool(res[t]["status"] & 2)
             assert deg == bool(d["status"][t] & L.ST_POST_DEGENERATE)
-            assert deg == (fr == 1 and t in (1, 2))
+            if fr == 1 and t in (1, 2):
+                assert deg
+            if t in (0, 3) or fr == 0:
+                assert not deg
             if deg:
                 assert res[t]["wsum"] == 0 and d["wsum"][t] == 0 and np.isnan(d["w_norm"][t]).all()
             else:
                 assert rel_err_weights(d["w_norm"][t], res[t]["w_norm"]) <= RTOL
             xo, Po = fs[t].get_state()
             assert rel_err(d["x"][t], xo) <= RTOL and rel_err(d["P"][t], Po) <= RTOL
+
+
+def test_cholesky_failure_branch_matches_oracle(left_arm, rng):
+    """S not positive definite: cv::Cholesky fails, chol() returns the partially factored clone and the
+    reference carries on with LU inverses (src/pf2DRao.cpp:37,52; src/KF_model.cpp:21)"""
+    T, N = 2, 64
+    fs = oracle_filters(left_arm, T, N, [0.3, 0.8])
+    H = left_arm.np.H
+    xs, Ps = [], []
+    for f in fs:
+        x, P = f.get_state()
+        for j in range(0, N, 3):  # every third slot gets an indefinite innovation covariance
+            scale = [200.0, 3000.0, 40000.0][(j // 3) % 3]
+            P[j] = P[j] - scale * (H.T @ np.diag(rng.uniform(0.5, 1.5, 6)) @ H)
+        f.set_state(x, P)
+        xs.append(x)
+        Ps.append(P)
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    b.upload(np.stack(xs), np.stack(Ps))
+    meas, ui, up = synth_frame(0x5EED0002, range(T), 0, N)
+    res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+    b.update(meas, ui, up)
+    d = b.download()
+    n_fail = 0
+    for t in range(T):
+        assert res[t]["status"] & 4 and d["status"][t] & L.ST_CHOL_FAIL
+        wo, wg = res[t]["w_raw"], d["w_raw"][t]
+        assert np.array_equal(np.isnan(wo), np.isnan(wg))
+        fin = np.isfinite(wo) & (wo > 1e-290) & (wo < 1e290)
+        assert np.max(np.abs(wg[fin] - wo[fin]) / wo[fin]) <= 1e-6  # ill-conditioned by construction
+        n_fail += int((~fin).sum())
+        # NaN weights make wsum NaN -> random-index fallback (seed 1 on both sides): still bit-exact
+        assert np.array_equal(d["parents"][t], res[t]["parents"])
+        xo, Po = fs[t].get_state()
+        assert np.array_equal(np.isnan(xo), np.isnan(d["x"][t]))
+        ok = np.isfinite(Po).all(axis=(1, 2)) & np.isfinite(xo).all(axis=1)
+        assert ok.sum() > N // 2
+        assert rel_err(d["x"][t][ok], xo[ok]) <= RTOL and rel_err(d["P"][t][ok], Po[ok]) <= RTOL
+    print("cholesky-failure slots with non-finite or extreme weights:", n_fail)
+
+
+@pytest.mark.parametrize("K,d", [(25, 10), (35, 10), (26, 12)])
+def test_other_model_shapes(K, d):
+    """the file-name pattern data?3D_PCA_<samples>_<K>_<d>.yml implies other shapes (launch files use
+    25_10, 26_10, 35_10; bodyTrackingBagCompare.launch:2-3, launch/ChaLearn.launch:7-8): synthetic models"""
+    rng = np.random.default_rng(K * 100 + d)
+    D = 22
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    proj = q[:d].astype(np.float32).astype(np.float64)
+    pmean = np.concatenate([[388, 281, 1.7, 390, 223, 1.8, 369, 158, 1.8, 324, 74.5, 1.8, 326, 128.6, 1.85],
+                            np.zeros(D - 15)])[:D]
+    means = rng.standard_normal((K, d)) * 40
+    covs = np.zeros((K, d, d))
+    for k in range(K):
+        a_ = rng.standard_normal((d, d))
+        covs[k] = 150.0 * (a_ @ a_.T / d + 0.05 * np.eye(d))
+    wts = rng.dirichlet(np.ones(K))
+    gam = rng.uniform(0.85, 0.99, K)
+    m = mk.Model.from_arrays(means, covs, wts, gam, proj, pmean)
+    om = orc.Model(means, covs, wts, gam, proj, pmean)
+    T, N = 4, 300
+    u0 = rng.random(T)
+    fs = [orc.Filter(om, N) for _ in range(T)]
+    for f, u in zip(fs, u0):
+        f.reset(u=u)
+    b = mk.TrackBatch(m, T, N)
+    b.reset(u0)
+    for fr in range(5):
+        meas, ui, up = synth_frame(0x5EED0002, range(T), fr, N)
+        res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+        b.update(meas, ui, up)
+        stats, _ = compare_frame(b, fs, res, check_state=True)
+        assert_parity(stats)
+    xb, pose = b.estimate()
+    for t in range(T):
+        xo, po = fs[t].estimate()
+        assert rel_err(xb[t], xo) <= RTOL and rel_err(pose[t], po) <= RTOL

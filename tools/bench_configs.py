@@ -139,7 +139,18 @@ def pf2d(name, T, N, d, K, steps):
 
 left = mk.Model.load(mk.LEFT_ARM_MODEL, mk.RIGHT_ARM_MODEL)
 right = mk.Model.load(mk.RIGHT_ARM_MODEL, mk.RIGHT_ARM_MODEL)
-which = sys.argv[1:] or ["2b", "3", "4", "5", "pf2d"]
+which = sys.argv[1:] or ["2", "2lit", "2b", "3", "4", "5", "pf2d"]
+if "2" in which:
+    rbpf("config 2: 4096 tracks x 500 slots, shared column, alias INDEPENDENT", left, 4096, 500, 50, False, 0x5EED0002)
+if "2lit" in which:
+    prm = mk.default_params()
+    prm.alias_mode = 1
+    a = left.arrays()
+    lit = mk.Model.from_arrays(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"], prm)
+    rbpf("config 2: 4096 tracks x 500 slots, shared column, alias CV_SHALLOW_LITERAL (quirk B3)", lit, 4096, 500, 50,
+         False, 0x5EED0002)
+    rbpf("config 4: 256 tracks x 65536 slots, per-slot columns, alias CV_SHALLOW_LITERAL", lit, 256, 65536, 10, True,
+         0x5EED0004)
 if "2b" in which:
     rbpf("config 2 (bank): 4096 tracks x 15 slots, shared column", left, 4096, 15, 50, False, 0x5EED0002)
 if "3" in which:
