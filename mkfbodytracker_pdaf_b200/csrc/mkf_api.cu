@@ -377,31 +377,37 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     for (int r = 0; r < MKF_M; r++) a.bh[r] = m->BH[r];
     a.r = m->prm.meas_noise_var;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
-    if (m->d == 12) {
-        static bool attr12 = false;
-        if (!attr12 && smem > 48 * 1024) {
-            CK(cudaFuncSetAttribute(k_slot_update<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr12 = true;
+    {
+        static bool attr_done = false;
+        if (!attr_done && smem > 48 * 1024) {
+            CK(cudaFuncSetAttribute(k_slot_update<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done = true;
         }
-        k_slot_update<12><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
-    } else {
-        static bool attr10 = false;
-        if (!attr10 && smem > 48 * 1024) {
-            CK(cudaFuncSetAttribute(k_slot_update<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr10 = true;
+        const unsigned g = grid_for(b->total, 128);
+        if (m->d == 12) {
+            if (a.alias_chain)
+                k_slot_update<12, true><<<g, 128, smem, b->stream>>>(a);
+            else
+                k_slot_update<12, false><<<g, 128, smem, b->stream>>>(a);
+        } else {
+            if (a.alias_chain)
+                k_slot_update<10, true><<<g, 128, smem, b->stream>>>(a);
+            else
+                k_slot_update<10, false><<<g, 128, smem, b->stream>>>(a);
         }
-        k_slot_update<10><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
-    if (a.alias_chain) { // tracks whose parents are unsorted (after the random-index fallback): sequential walk
-        if (m->d == 12)
-            k_slot_update_unsorted<12><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
-        else
-            k_slot_update_unsorted<10><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
-        MKF_LAUNCHED();
-        CK(cudaGetLastError());
-    }
+    // rare tracks (cv::Cholesky failure flagged, or unsorted parents in the literal alias mode) are redone
+    if (m->d == 12)
+        k_slot_update_repair<12><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
+    else
+        k_slot_update_repair<10><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
     if (prof) cudaEventRecord(pe[2], b->stream);
     b->cur ^= 1;
     rc = run_resample(b->stream, b->T, b->need_fb, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status,

@@ -79,9 +79,14 @@ extern "C" int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int 
     a.r = m->prm.meas_noise_var;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
     if (m->d == 12)
-        k_slot_update<12><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
+        k_slot_update<12, false><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
     else
-        k_slot_update<10><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
+        k_slot_update<10, false><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
+    MKF_LAUNCHED();
+    if (m->d == 12)
+        k_slot_update_repair<12><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, nullptr);
+    else
+        k_slot_update_repair<10><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, nullptr);
     MKF_LAUNCHED();
     if (cudaGetLastError() != cudaSuccess) {
         mkf_set_error("mkf_kf_apply: kernel launch failed");

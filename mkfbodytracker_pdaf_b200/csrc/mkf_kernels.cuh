@@ -156,7 +156,7 @@ __device__ __noinline__ void mkf_chol_fail_path(const double* Sfull /* 36 */, co
 //                A <- r I - r^2 W;  B <- r (W B^T)^T;  C <- C - B W B^T
 // returns false when cv::Cholesky would have failed (pivot < DBL_EPSILON)
 // -----------------------------------------------------------------------------------------
-template <int D>
+template <int D, bool SLOW>
 __device__ __forceinline__ bool slot_math(double (&v)[SlotLay<D>::NE], const double* __restrict__ c,
                                           const double (&zc)[MKF_M], const double r, const int chol_mode,
                                           const int stage, double& w_out)
@@ -253,7 +253,7 @@ __device__ __forceinline__ bool slot_math(double (&v)[SlotLay<D>::NE], const dou
             for (int k = a; k < M; k++) s = fma(Li[tri(k, a)], Li[tri(k, b)], s);
             W[tri(a, b)] = s;
         }
-    if (!ok) { // literal cv::Cholesky-failure semantics (rare): likelihood from the unfactored matrix, LU inverse
+    if (SLOW && !ok) { // literal cv::Cholesky-failure semantics (rare): likelihood from the unfactored matrix, LU inverse
         double Sf[36];
 #pragma unroll
         for (int a = 0; a < M; a++)
@@ -336,14 +336,16 @@ __device__ __forceinline__ void mkf_load_meas(const SlotArgs& a, long long t, in
     }
 }
 
-// One thread per slot.  alias_chain == 0 (MKF_ALIAS_INDEPENDENT): every slot starts from its parent's
-// Gaussian.  alias_chain == 1 (MKF_ALIAS_CV_SHALLOW_LITERAL, quirk B3 of src/pf2DRao.cpp:153-156): the
+// One thread per slot.  CHAIN == false (MKF_ALIAS_INDEPENDENT): every slot starts from its parent's
+// Gaussian.  CHAIN == true (MKF_ALIAS_CV_SHALLOW_LITERAL, quirk B3 of src/pf2DRao.cpp:153-156): the
 // slots that drew the same parent share one cv::Mat buffer in the reference and are predicted/updated
 // sequentially in place, so slot j starts from the snapshot slot j-1 left behind.  Parents are sorted
 // after systematic resampling, so such slots form a run of consecutive slots: the thread of the run's
 // first slot walks the whole run with the Gaussian held in registers and stores a snapshot per slot;
 // the other threads of the run retire at once.
-template <int D>
+// A cv::Cholesky failure only raises MKF_ST_CHOL_FAIL here; k_slot_update_repair then redoes the track
+// with the literal failure semantics, which keeps that (never taken in practice) branch out of this kernel.
+template <int D, bool CHAIN>
 __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
 {
     using L = SlotLay<D>;
@@ -370,9 +372,9 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
         t = s / a.N;
         j = (int)(s - t * a.N);
         const int par = __ldg(a.parent + s);
-        if (a.alias_chain) {
+        if (CHAIN) {
             if (a.unsorted[t]) {
-                active = false; // random-index fallback left unsorted parents: k_slot_update_unsorted handles the track
+                active = false; // unsorted parents (random-index fallback): k_slot_update_repair walks the track
             } else if (j > 0 && __ldg(a.parent + s - 1) == par) {
                 active = false; // not the first slot of its run
             } else {
@@ -396,12 +398,11 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
     mkf_mbar_wait(&mbar, 0);
     if (!active) return;
 
-    for (int i = 0;;) {
+    if (!CHAIN) {
         double w;
-        const bool ok = slot_math<D>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+        const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
         if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
-        const long long so = s + i;
-        double2* __restrict__ dst = a.st_out + (so >> 5) * (long long)(L::NP * 32) + (so & 31);
+        double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
 #pragma unroll
         for (int p = 0; p < L::NP; p++) {
             double2 q;
@@ -409,53 +410,88 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
             q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
             __stcs(dst + p * 32, q);
         }
-        a.w_raw[so] = w;
-        if (++i >= len) break;
-        mkf_load_meas(a, t, j + i, zc);
-        k = mkf_component_of(bt, a.K, j + i);
+        a.w_raw[s] = w;
+    } else {
+        for (int i = 0;;) {
+            double w;
+            const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+            if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+            const long long so = s + i;
+            double2* __restrict__ dst = a.st_out + (so >> 5) * (long long)(L::NP * 32) + (so & 31);
+#pragma unroll
+            for (int p = 0; p < L::NP; p++) {
+                double2 q;
+                q.x = v[2 * p];
+                q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                __stcs(dst + p * 32, q);
+            }
+            a.w_raw[so] = w;
+            if (++i >= len) break;
+            mkf_load_meas(a, t, j + i, zc);
+            k = mkf_component_of(bt, a.K, j + i);
+        }
     }
 }
 
-// alias_chain with UNSORTED parents (only after the degenerate random-index fallback of
-// src/pf2DRao.cpp:184-192): slots sharing a parent are not adjacent, so one thread per flagged track
-// walks the slots in order, starting each from the latest snapshot taken for its parent.
-// last: T x N scratch (latest snapshot slot per parent, -1 = none yet).
+// Rare tracks redone after k_slot_update: (i) a cv::Cholesky failure was flagged (literal failure semantics
+// through slot_math<SLOW>), (ii) literal alias mode with UNSORTED parents (after the degenerate random-index
+// fallback of src/pf2DRao.cpp:184-192 the slots sharing a parent are not adjacent).  One CTA scans 128
+// tracks' flags.  Independent mode: the CTA's threads stride over the track's slots.  Literal alias mode:
+// one thread walks the slots in order, each starting from the latest snapshot taken for its parent
+// (last: T x N scratch, -1 = none yet).  st_in is intact (ping-pong), so everything is recomputed from it.
 template <int D>
-__global__ void __launch_bounds__(128, 2) k_slot_update_unsorted(const SlotArgs a, int32_t* __restrict__ last)
+__global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a, int32_t* __restrict__ last)
 {
     using L = SlotLay<D>;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.total / a.N || !a.unsorted[t]) return;
-    int32_t* __restrict__ lt = last + t * a.N;
-    for (int j = 0; j < a.N; j++) lt[j] = -1;
-    const int32_t* __restrict__ bt = a.bounds + t * (a.K + 2);
-    for (int j = 0; j < a.N; j++) {
-        const long long s = t * a.N + j;
-        const int par = a.parent[s];
-        const int snap = lt[par];
-        const double2* __restrict__ base = snap >= 0 ? (const double2*)a.st_out : a.st_in;
-        const long long sp = t * a.N + (snap >= 0 ? snap : par);
-        const double2* __restrict__ src = base + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
-        double v[L::NE];
-        for (int p = 0; p < L::NP; p++) {
-            const double2 q = src[p * 32]; // plain load: the source may be a snapshot this thread stored earlier
-            v[2 * p] = q.x;
-            if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+    __shared__ uint32_t flags[128];
+    const long long T = a.total / a.N;
+    const long long base = (long long)blockIdx.x * 128;
+    {
+        const long long t = base + threadIdx.x;
+        uint32_t f = 0;
+        if (t < T) f = (a.status[t] & MKF_ST_CHOL_FAIL) || (a.alias_chain && a.unsorted[t]);
+        flags[threadIdx.x] = f;
+        if (!__syncthreads_or((int)f)) return;
+    }
+    for (int q = 0; q < 128; q++) {
+        if (!flags[q]) continue;
+        const long long t = base + q;
+        const int32_t* __restrict__ bt = a.bounds + t * (a.K + 2);
+        int32_t* __restrict__ lt = last ? last + t * a.N : nullptr;
+        if (a.alias_chain && threadIdx.x == 0)
+            for (int j = 0; j < a.N; j++) lt[j] = -1;
+        const int j0 = a.alias_chain ? 0 : (int)threadIdx.x;
+        const int jstep = a.alias_chain ? 1 : 128;
+        if (!a.alias_chain || threadIdx.x == 0) {
+            for (int j = j0; j < a.N; j += jstep) {
+                const long long s = t * a.N + j;
+                const int par = a.parent[s];
+                const int snap = a.alias_chain ? lt[par] : -1;
+                const double2* base_p = snap >= 0 ? (const double2*)a.st_out : a.st_in;
+                const long long sp = t * a.N + (snap >= 0 ? snap : par);
+                const double2* src = base_p + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+                double v[L::NE];
+                for (int p = 0; p < L::NP; p++) {
+                    const double2 qq = src[p * 32]; // plain load: may be a snapshot this thread stored earlier
+                    v[2 * p] = qq.x;
+                    if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
+                }
+                double zc[MKF_M], w;
+                mkf_load_meas(a, t, j, zc);
+                const int k = mkf_component_of(bt, a.K, j);
+                slot_math<D, true>(v, a.comp_const + (long long)k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+                double2* dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+                for (int p = 0; p < L::NP; p++) {
+                    double2 qq;
+                    qq.x = v[2 * p];
+                    qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                    dst[p * 32] = qq;
+                }
+                a.w_raw[s] = w;
+                if (a.alias_chain) lt[par] = j;
+            }
         }
-        double zc[MKF_M], w;
-        mkf_load_meas(a, t, j, zc);
-        const int k = mkf_component_of(bt, a.K, j);
-        const bool ok = slot_math<D>(v, a.comp_const + (long long)k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
-        if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
-        double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
-        for (int p = 0; p < L::NP; p++) {
-            double2 q;
-            q.x = v[2 * p];
-            q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-            dst[p * 32] = q;
-        }
-        a.w_raw[s] = w;
-        lt[par] = j;
+        __syncthreads();
     }
 }
 

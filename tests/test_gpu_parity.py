@@ -456,3 +456,4 @@ def test_other_model_shapes(K, d):
     for t in range(T):
         xo, po = fs[t].estimate()
         assert rel_err(xb[t], xo) <= RTOL and rel_err(pose[t], po) <= RTOL
+
