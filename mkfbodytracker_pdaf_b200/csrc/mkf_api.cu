@@ -288,8 +288,15 @@ static inline unsigned grid_for(long long n, int bt) { return (unsigned)((n + bt
 static int launch_bounds_kernel(mkf_batch* b, const double* d_u)
 {
     const mkf_model* m = b->m;
-    k_indicator_bounds<<<grid_for(b->T, 128), 128, 0, b->stream>>>(d_u, b->T, b->N, m->K, b->d_cw_hi, b->d_cw_lo,
-                                                                    b->d_wprior, m->prior_wmax, b->bounds, b->status);
+#define LAUNCH_BOUNDS(G)                                                                                       \
+    k_indicator_bounds<G><<<grid_for(b->T * G, 128), 128, 0, b->stream>>>(d_u, b->T, b->N, m->K, b->d_cw_hi,       \
+                                                                           b->d_cw_lo, b->d_wprior, m->prior_wmax, \
+                                                                           b->bounds, b->status)
+    if (m->K <= 16)
+        LAUNCH_BOUNDS(16);
+    else
+        LAUNCH_BOUNDS(32); // K <= 64: two components per lane
+#undef LAUNCH_BOUNDS
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     return MKF_OK;

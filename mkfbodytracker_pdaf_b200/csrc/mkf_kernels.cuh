@@ -496,37 +496,58 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
 }
 
 // -----------------------------------------------------------------------------------------
-// K -> N indicator resample: per-track run boundaries e_k = #{j : indicator_j <= k}
-// one thread per track.  bounds[t] = { e_0..e_{K-1}, wrap_from, wrap_k }
+// K -> N indicator resample: per-track run boundaries e_k = #{j : indicator_j <= k}.
+// GROUP lanes (a power of two >= K, <= 32) cooperate on one track: lane k evaluates e_k in closed form
+// against the double-double prefix sum of the prior weights; if any lane is ambiguous (or the thresholds
+// run past the total prior mass) lane 0 replays the literal loop.  bounds[t] = { e_0..e_{K-1}, wrap_from, wrap_k }
 // -----------------------------------------------------------------------------------------
+template <int GROUP>
 __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, int N, int K,
                                    const double* __restrict__ cw_hi, const double* __restrict__ cw_lo,
                                    const double* __restrict__ wprior, double wmax, int32_t* __restrict__ bounds,
                                    uint32_t* __restrict__ status)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = gid / GROUP;
+    const int k = (int)(gid % GROUP);
+    const bool live = t < T;
     const double step = __ddiv_rn(1.0, (double)N);
-    const double uu = u[t];
-    const double beta0 = __dmul_rn(uu, step);
+    const double beta0 = live ? __dmul_rn(u[t], step) : 0.0;
     const double tol = mkf_resample_tol(N, K, wmax, step);
-    int32_t* bt = bounds + t * (K + 2);
     bool amb = false;
-    int e = 0;
-    for (int k = 0; k < K; k++) {
-        dd C;
-        C.hi = cw_hi[k];
-        C.lo = cw_lo[k];
-        e = mkf_count_le(C, beta0, step, N, tol, amb);
-        bt[k] = e;
+    int e[2] = {0, 0}; // K <= 2 * GROUP: components k and k + GROUP
+    if (live) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int kk = k + h * GROUP;
+            if (kk >= K) break;
+            dd C;
+            C.hi = cw_hi[kk];
+            C.lo = cw_lo[kk];
+            e[h] = mkf_count_le(C, beta0, step, N, tol, amb);
+            if (kk == K - 1 && e[h] < N) amb = true; // thresholds beyond the total prior mass: the loop wraps around
+        }
     }
-    bt[K] = N;
-    bt[K + 1] = 0;
-    if (e < N) amb = true; // thresholds beyond the total prior mass: the literal loop wraps around
-    if (!amb) return;
+    // combine the ambiguity flags of the GROUP lanes that share a track
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(unsigned)(GROUP - 1)));
+    const unsigned votes = __ballot_sync(0xffffffffu, amb);
+    const bool any_amb = (votes & gmask) != 0u;
+    if (!live) return;
+    int32_t* bt = bounds + t * (K + 2);
+    if (!any_amb) {
+        if (k < K) bt[k] = e[0];
+        if (k + GROUP < K) bt[k + GROUP] = e[1];
+        if (k == 0) {
+            bt[K] = N;
+            bt[K + 1] = 0;
+        }
+        return;
+    }
+    if (k != 0) return;
     // literal loop (src/pf2DRao.cpp:195-207) -> counts per component
     uint32_t st = MKF_ST_IND_FALLBACK;
-    for (int k = 0; k < K; k++) bt[k] = 0;
+    for (int q = 0; q < K; q++) bt[q] = 0;
     int idx = 0, wraps = 0, wrap_from = N, wrap_k = 0;
     double beta = beta0;
     double wi = wprior[0];
@@ -542,21 +563,20 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
         }
         beta = __dadd_rn(beta, step);
         if (wraps == 0) {
-            bt[idx] = i + 1; // last output index + 1 holding component <= idx (filled below)
+            bt[idx] = i + 1; // last output index + 1 holding component idx (made cumulative below)
         } else if (wrap_from == N) {
             wrap_from = i;
             wrap_k = idx;
             st |= MKF_ST_IND_WRAP;
         }
     }
-    // bt[k] currently: (last i with component k) + 1, or 0 if unused -> make cumulative
     int run = 0;
-    for (int k = 0; k < K; k++) {
-        if (bt[k] > run) run = bt[k];
-        bt[k] = run;
+    for (int q = 0; q < K; q++) {
+        if (bt[q] > run) run = bt[q];
+        bt[q] = run;
     }
-    for (int k = 0; k < K; k++)
-        if (bt[k] > wrap_from) bt[k] = wrap_from;
+    for (int q = 0; q < K; q++)
+        if (bt[q] > wrap_from) bt[q] = wrap_from;
     bt[K - 1] = (wrap_from < N) ? wrap_from : N;
     bt[K] = wrap_from;
     bt[K + 1] = wrap_k;

@@ -457,3 +457,22 @@ def test_other_model_shapes(K, d):
         xo, po = fs[t].estimate()
         assert rel_err(xb[t], xo) <= RTOL and rel_err(pose[t], po) <= RTOL
 
+
+
+def test_indicator_bounds_all_shapes_and_edge_draws(left_arm):
+    """K -> N indicator resample through reset(): every K group size, u at the edges, bit-exact vs the loop"""
+    rng = np.random.default_rng(5)
+    a = left_arm.arrays
+    for K in (1, 2, 15, 16, 17, 33, 64):
+        means = rng.standard_normal((K, 12)) * 30
+        covs = np.tile(np.eye(12) * 50.0, (K, 1, 1))
+        wts = rng.dirichlet(np.ones(K) * 0.3)
+        m = mk.Model.from_arrays(means, covs, wts, np.full(K, 0.9), a["pca_proj"], a["pca_mean"])
+        for N in (7, 500, 4099):
+            u = np.concatenate([[0.0, 1.0 - 2.0**-53, 0.5], rng.random(13)])
+            b = mk.TrackBatch(m, len(u), N)
+            b.reset(u)
+            ind = b.download(state=False, cov=False)["indicators"]
+            for t in range(len(u)):
+                want, _ = orc.resample(wts, N, u[t])
+                assert np.array_equal(ind[t], want), (K, N, t)
