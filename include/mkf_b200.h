@@ -172,6 +172,31 @@ int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int stage, doub
  * positions cand_xy (2 x C, row 0 = x) under N(posterior hand estimate, 0.8*scale*I).  Host pointers. */
 int mkf_batch_sample_prob(mkf_batch* b, int64_t track, const double* cand_xy, int C, double scale, double* out);
 
+/* ---- candidate generation front-end (the step before the path) ----
+ * The proposal part of PFTracker::getMeasurementProposal (src/pfPose.cpp:216-236) with
+ * ParticleFilter::getSamples (src/pf2DRao.cpp:85-103) and the likelihood-image lookup (:254) for T persons:
+ * tracking[t] != 0 (NULL = all): C candidates per hand ~ N(posterior hand estimate, (0.8*roi_w)^2 I) (quirk B10);
+ * tracking[t] == 0: uniform on the first-frame box around the face ROI.  Draws come from the counter generator
+ * of mkf_synth.h keyed (seed, track0 + t, frame, hand, c) -- reproducible, unlike cv::randn/randu.
+ * like: n_img (1 or T) likelihood images of img_rows x img_cols uint8 (already blurred by the caller,
+ * src/pfPose.cpp:213), may be NULL with cand_L NULL.  Outputs in the layout mkf_batch_associate consumes:
+ * cand_xy T x 2 x 2 x C, cand_L T x 2 x C. */
+int mkf_batch_propose(mkf_batch* arm0, mkf_batch* arm1, int C, const double* roi, const uint8_t* tracking,
+                      const uint8_t* like, int n_img, uint64_t seed, uint64_t frame, int64_t track0, double* cand_xy,
+                      uint8_t* cand_L, int mem);
+
+/* ---- output back-end (the step after the path) ----
+ * PFTracker::get3Dpose (src/pfPose.cpp:93-127) of every track's current estimate: pos3d T x 3 x 5 (columns:
+ * hand, elbow, shoulder, head, neck).  Kcam: 3 x 3 camera matrix (host, row-major) or NULL for the Kinect
+ * literal the reference hard-codes (src/pfPose.cpp:101); mkf_load_camera_matrix reads a cal.yml. */
+int mkf_batch_pose3d(mkf_batch* b, const double* Kcam, double* pos3d, int mem);
+/* PFTracker::publishTFtree + publish2Dpos (src/pfPose.cpp:129-208) for T persons from both arms' estimates
+ * (arm0 = e1, arm1 = e2): tf T x 10 x 3 = the nine broadcast translations in source order followed by the
+ * camera Euler triple; joints2d T x 8 x 2.  Either output may be NULL. */
+int mkf_batch_skeleton(mkf_batch* arm0, mkf_batch* arm1, const double* Kcam, double* tf, double* joints2d, int mem);
+/* camera_matrix (3 x 3) of a ROS camera_calibration YAML such as the reference's cal.yml:4-7 */
+int mkf_load_camera_matrix(const char* path, double* K9);
+
 /* ParticleFilter::resample for one weight vector (src/pf2DRao.cpp:175-210) on the device:
  * w[L] (host), N outputs, u < 0 draws from cv::RNG(seed) as the reference does. */
 int mkf_resample(const double* w, int L, int N, double u, uint64_t seed, int32_t* out, int device);

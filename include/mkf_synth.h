@@ -168,4 +168,43 @@ MKF_HD void mkf_synth_candidate(uint64_t seed, uint64_t track, uint64_t frame, i
     }
 }
 
+/* Candidate proposal front-end (src/pfPose.cpp:216-236, src/pf2DRao.cpp:85-103) driven by the counter
+ * generator instead of cv::randn / cv::randu (whose streams are not reproducible):
+ *  tracking != 0: x = hx + (spread*scale) * n1, y = hy + (spread*scale) * n2 -- cv::randn is handed
+ *                 C = 0.8*scale*I as a STANDARD-DEVIATION matrix (quirk B10), scale = roi width;
+ *  tracking == 0: first frame after (re)acquiring the face: uniform on the box
+ *                 [max(x-4w,0), min(x+5w,cols)) x [min(y+h,rows), min(y+7h,rows))  (integer-truncated). */
+#define MKF_SYNTH_LANE_PROP 0x50000000u /* + (hand*C + c)*2 + {0:x,1:y} */
+MKF_HD void mkf_synth_proposal(uint64_t seed, uint64_t track, uint64_t frame, int hand, int C, int c, int tracking,
+                               double hx, double hy, const double roi[4], int rows, int cols, double spread,
+                               double* px, double* py)
+{
+    const uint64_t lane = (uint64_t)MKF_SYNTH_LANE_PROP + 2ull * ((uint64_t)hand * (uint64_t)C + (uint64_t)c);
+    const uint64_t h0 = mkf_hash4(seed, track, frame, lane), h1 = mkf_hash4(seed, track, frame, lane + 1);
+    if (tracking) {
+        const double sd = MKF_SMUL(MKF_SMUL(spread, roi[2]), 1.0);
+        *px = MKF_SADD(hx, MKF_SMUL(sd, mkf_gauss(h0)));
+        *py = MKF_SADD(hy, MKF_SMUL(sd, mkf_gauss(h1)));
+    } else {
+        int xmin = (int)roi[0] - (int)(4 * roi[2]);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)roi[0] + (int)(5 * roi[2]);
+        if (xmax > cols) xmax = cols;
+        int ymin = (int)roi[1] + (int)(roi[3]);
+        if (ymin > rows) ymin = rows;
+        int ymax = (int)roi[1] + (int)(7 * roi[3]);
+        if (ymax > rows) ymax = rows;
+        *px = MKF_SADD((double)xmin, MKF_SMUL(mkf_u01(h0), (double)(xmax - xmin)));
+        *py = MKF_SADD((double)ymin, MKF_SMUL(mkf_u01(h1), (double)(ymax - ymin)));
+    }
+}
+
+/* likelihood.at<uchar>(y, x) with the implicit double -> int truncation of src/pfPose.cpp:254, guarded by the
+ * inside-image test of :251 (outside candidates never reach the lookup; they get L = 0 here) */
+MKF_HD uint8_t mkf_likelihood_lookup(const uint8_t* img, int rows, int cols, double x, double y)
+{
+    if (!((y > 0) && (y < (double)rows) && (x > 0) && (x < (double)cols))) return 0;
+    return img[(long long)(int)y * cols + (int)x];
+}
+
 #endif /* MKF_SYNTH_H */

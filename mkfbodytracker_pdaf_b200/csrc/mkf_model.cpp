@@ -450,3 +450,38 @@ extern "C" int mkf_model_get(const mkf_model* m, double* means, double* covs, do
     cp(m->BH, BH);
     return MKF_OK;
 }
+
+// camera_matrix of a ROS camera_calibration YAML (cal.yml:4-7); used only by the get3Dpose back-end
+extern "C" int mkf_load_camera_matrix(const char* path, double* K9)
+{
+    if (!path || !K9) {
+        mkf_set_error("mkf_load_camera_matrix: null argument");
+        return MKF_E_INVALID;
+    }
+    std::ifstream f(path);
+    if (!f) {
+        mkf_set_error("cannot open '%s'", path);
+        return MKF_E_IO;
+    }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string txt = ss.str();
+    size_t p = txt.find("camera_matrix:");
+    if (p == std::string::npos || (p = txt.find("data:", p)) == std::string::npos ||
+        (p = txt.find('[', p)) == std::string::npos) {
+        mkf_set_error("'%s': no camera_matrix data", path);
+        return MKF_E_PARSE;
+    }
+    const char* c = txt.c_str() + p + 1;
+    for (int i = 0; i < 9; i++) {
+        while (*c == ' ' || *c == ',' || *c == '\n' || *c == '\r' || *c == '\t') c++;
+        char* e = nullptr;
+        K9[i] = strtod(c, &e);
+        if (e == c) {
+            mkf_set_error("'%s': camera_matrix needs 9 numbers", path);
+            return MKF_E_PARSE;
+        }
+        c = e;
+    }
+    return MKF_OK;
+}

@@ -167,6 +167,13 @@ class TrackBatch:
         L.check(L.lib.mkf_synth_fill(self._h, int(seed), int(track0), int(frame), int(jitter), layout,
                                      _addr(meas_dev)[0], _addr(u_ind_dev)[0], _addr(u_post_dev)[0]))
 
+    def pose3d(self, Kcam=None):
+        """PFTracker::get3Dpose (src/pfPose.cpp:93-127) of every track: (T, 3, 5)"""
+        out = np.zeros((self.T, 3, 5))
+        k = _h(Kcam, np.float64).reshape(9) if Kcam is not None else None
+        L.check(L.lib.mkf_batch_pose3d(self._h, _addr(k)[0], out.ctypes.data, L.MEM_HOST))
+        return out
+
     def sync(self):
         L.check(L.lib.mkf_batch_sync(self._h))
 
@@ -207,6 +214,35 @@ def assoc_results(arm0: TrackBatch, C_: int):
     bins = np.zeros((T, 2, N), np.int32)
     L.check(L.lib.mkf_batch_assoc_results(arm0._h, gate.ctypes.data, w.ctypes.data, bins.ctypes.data, L.MEM_HOST))
     return dict(gate=gate, weights=w, bins=bins)
+
+
+def propose(arm0: TrackBatch, arm1: TrackBatch, C_: int, roi, tracking=None, like=None, seed=0, frame=0, track0=0,
+            cand_xy=None, cand_L=None):
+    """candidate generation front-end (src/pfPose.cpp:216-236, src/pf2DRao.cpp:85-103): returns (cand_xy, cand_L)"""
+    T = arm0.T
+    if cand_xy is None:
+        cand_xy = np.zeros((T, 2, 2, C_))
+        cand_L = np.zeros((T, 2, C_), np.uint8) if like is not None else None
+    n_img = 1 if like is None or len(like.shape) == 2 else like.shape[0]
+    mem = _same_mem(roi, tracking, like, cand_xy, cand_L)
+    L.check(L.lib.mkf_batch_propose(arm0._h, arm1._h, C_, _addr(roi)[0], _addr(tracking)[0], _addr(like)[0], n_img,
+                                    int(seed), int(frame), int(track0), _addr(cand_xy)[0], _addr(cand_L)[0], mem))
+    return cand_xy, cand_L
+
+
+def skeleton(arm0: TrackBatch, arm1: TrackBatch, Kcam=None):
+    """publishTFtree translations (+ camera Euler triple) and publish2Dpos joints (src/pfPose.cpp:129-208)"""
+    tf = np.zeros((arm0.T, 10, 3))
+    j2 = np.zeros((arm0.T, 8, 2))
+    k = _h(Kcam, np.float64).reshape(9) if Kcam is not None else None
+    L.check(L.lib.mkf_batch_skeleton(arm0._h, arm1._h, _addr(k)[0], tf.ctypes.data, j2.ctypes.data, L.MEM_HOST))
+    return tf, j2
+
+
+def load_camera_matrix(path):
+    K = np.zeros(9)
+    L.check(L.lib.mkf_load_camera_matrix(os.fsencode(path), K.ctypes.data))
+    return K.reshape(3, 3)
 
 
 def resample(w, N, u=-1.0, seed=1, device=0):

@@ -616,6 +616,129 @@ extern "C" void orc_filter_estimate(const orc_filter* f, double* xbar, double* p
 }
 
 // ---------------------------------------------------------------------------------------------
+// output back-end: PFTracker::rpy / get3Dpose / publishTFtree / publish2Dpos  (src/pfPose.cpp:84-208)
+// ---------------------------------------------------------------------------------------------
+namespace {
+// cv::invert(DECOMP_LU) 3x3 closed form (determinant + adjugate), OpenCV 2.4 modules/core/src/lapack.cpp
+bool invert3(const double* S, double* Dst)
+{
+#define SD(r, c) S[(r)*3 + (c)]
+    double d = SD(0, 0) * (SD(1, 1) * SD(2, 2) - SD(1, 2) * SD(2, 1)) - SD(0, 1) * (SD(1, 0) * SD(2, 2) - SD(1, 2) * SD(2, 0)) +
+               SD(0, 2) * (SD(1, 0) * SD(2, 1) - SD(1, 1) * SD(2, 0));
+    if (d == 0.) {
+        for (int i = 0; i < 9; i++) Dst[i] = 0;
+        return false;
+    }
+    d = 1. / d;
+    double t[9];
+    t[0] = (SD(1, 1) * SD(2, 2) - SD(1, 2) * SD(2, 1)) * d;
+    t[1] = (SD(0, 2) * SD(2, 1) - SD(0, 1) * SD(2, 2)) * d;
+    t[2] = (SD(0, 1) * SD(1, 2) - SD(0, 2) * SD(1, 1)) * d;
+    t[3] = (SD(1, 2) * SD(2, 0) - SD(1, 0) * SD(2, 2)) * d;
+    t[4] = (SD(0, 0) * SD(2, 2) - SD(0, 2) * SD(2, 0)) * d;
+    t[5] = (SD(0, 2) * SD(1, 0) - SD(0, 0) * SD(1, 2)) * d;
+    t[6] = (SD(1, 0) * SD(2, 1) - SD(1, 1) * SD(2, 0)) * d;
+    t[7] = (SD(0, 1) * SD(2, 0) - SD(0, 0) * SD(2, 1)) * d;
+    t[8] = (SD(0, 0) * SD(1, 1) - SD(0, 1) * SD(1, 0)) * d;
+#undef SD
+    for (int i = 0; i < 9; i++) Dst[i] = t[i];
+    return true;
+}
+
+// rpy(roll, pitch, yaw) = R3*R2*R1  (src/pfPose.cpp:84-91)
+void rpy(double roll, double pitch, double yaw, double* R)
+{
+    const double R1[9] = {1, 0, 0, 0, std::cos(roll), -std::sin(roll), 0, std::sin(roll), std::cos(roll)};
+    const double R2[9] = {std::cos(pitch), 0, std::sin(pitch), 0, 1, 0, -std::sin(pitch), 0, std::cos(pitch)};
+    const double R3[9] = {std::cos(yaw), -std::sin(yaw), 0, std::sin(yaw), std::cos(yaw), 0, 0, 0, 1};
+    double R32[9];
+    gemm_nn(R3, 3, 3, R2, 3, 1.0, nullptr, 0.0, R32); // (R3*R2) evaluated first, then *R1
+    gemm_nn(R32, 3, 3, R1, 3, 1.0, nullptr, 0.0, R);
+}
+
+// get3Dpose (src/pfPose.cpp:93-127): estimate is the D-vector e; Kc the 3x3 camera matrix; out pos3D 3 x 5
+void get3dpose(const double* estimate, const double* Kc, double* pos3D)
+{
+    double est[32];
+    for (int i = 0; i < 22; i++) est[i] = estimate[i];
+    double R[9], T[12], P[12];
+    rpy(est[16], est[17], est[15], R);
+    for (int r = 0; r < 3; r++) { // hconcat(R, t, T)
+        for (int c = 0; c < 3; c++) T[r * 4 + c] = R[r * 3 + c];
+        T[r * 4 + 3] = est[18 + r];
+    }
+    gemm_nn(Kc, 3, 3, T, 4, 1.0, nullptr, 0.0, P); // P = K*T
+    double im[15];
+    for (int k = 0; k < 5; k++) {
+        est[3 * k] = est[3 * k] * est[3 * k + 2];
+        est[3 * k + 1] = est[3 * k + 1] * est[3 * k + 2];
+        for (int c = 0; c < 3; c++) im[k * 3 + c] = est[3 * k + c];
+    }
+    double P3[9], PI[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) P3[r * 3 + c] = P[r * 4 + c];
+    invert3(P3, PI);
+    // pos3D = P_I*(im_points - repeat(P.col(3).t(),5,1)).t()  -> AddEx evaluated, transposed, gemm(P_I, .., GEMM_2_T)
+    double diff[15];
+    for (int k = 0; k < 5; k++)
+        for (int c = 0; c < 3; c++) diff[k * 3 + c] = im[k * 3 + c] - P[c * 4 + 3];
+    gemm_nt(PI, 3, 3, diff, 5, 1.0, nullptr, 0.0, pos3D);
+}
+} // namespace
+
+extern "C" void orc_get3dpose(const double* estimate, const double* Kc, double* pos3D) { get3dpose(estimate, Kc, pos3D); }
+
+// publishTFtree (src/pfPose.cpp:129-171) translations, in broadcast order: for k = 0,1 {arm1 joint k+1 -> k,
+// arm2 joint k+1 -> k}, Neck->arm1 shoulder, Neck->arm2 shoulder, Head->Neck, world->Head, world->cam; plus the
+// camera Euler angles (setEuler(-e1[16], -e1[17], -e1[15])).  tf: 10 x 3 (9 translations + 1 euler triple last).
+// publish2Dpos (src/pfPose.cpp:173-208): 8 joints x (x, y).
+extern "C" void orc_skeleton(const double* e1, const double* e2, const double* Kc, double* tf, double* joints2d)
+{
+    double p1[15], p2[15];
+    get3dpose(e1, Kc, p1);
+    get3dpose(e2, Kc, p2);
+#define P1(r, c) p1[(r)*5 + (c)]
+#define P2(r, c) p2[(r)*5 + (c)]
+    int o = 0;
+    for (int k = 0; k < 2; k++) {
+        tf[o++] = P1(0, k) - P1(0, k + 1);
+        tf[o++] = P1(2, k) - P1(2, k + 1);
+        tf[o++] = -P1(1, k) + P1(1, k + 1);
+        tf[o++] = P2(0, k) - P2(0, k + 1);
+        tf[o++] = P2(2, k) - P2(2, k + 1);
+        tf[o++] = -P2(1, k) + P2(1, k + 1);
+    }
+    const double neck_x = (P1(0, 4) + P2(0, 4)) / 2.0, neck_y = (P1(1, 4) + P2(1, 4)) / 2.0, neck_z = (P1(2, 4) + P2(2, 4)) / 2.0;
+    const double head_x = (P1(0, 3) + P2(0, 3)) / 2.0, head_y = (P1(1, 3) + P2(1, 3)) / 2.0, head_z = (P1(2, 3) + P2(2, 3)) / 2.0;
+    tf[o++] = P1(0, 2) - neck_x;
+    tf[o++] = P1(2, 2) - neck_z;
+    tf[o++] = -P1(1, 2) + neck_y;
+    tf[o++] = P2(0, 2) - neck_x;
+    tf[o++] = P2(2, 2) - neck_z;
+    tf[o++] = -P2(1, 2) + neck_y;
+    tf[o++] = neck_x - head_x;
+    tf[o++] = neck_z - head_z;
+    tf[o++] = -neck_y + head_y;
+    tf[o++] = head_x;
+    tf[o++] = head_z;
+    tf[o++] = -head_y;
+    tf[o++] = -e1[18];
+    tf[o++] = -e1[20];
+    tf[o++] = e1[19];
+    tf[o++] = -e1[16];
+    tf[o++] = -e1[17];
+    tf[o++] = -e1[15];
+#undef P1
+#undef P2
+    if (joints2d) {
+        const double j[16] = {e1[0], e1[1], e2[0], e2[1], 0.5 * (e1[9] + e2[9]), 0.5 * (e1[10] + e2[10]),
+                              0.5 * (e1[12] + e2[12]), 0.5 * (e1[13] + e2[13]), e1[3], e1[4], e2[3], e2[4],
+                              e1[6], e1[7], e2[6], e2[7]};
+        for (int i = 0; i < 16; i++) joints2d[i] = j[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // association: PFTracker::getMeasurementProposal  (src/pfPose.cpp:238-323) with
 // getSampleProb (src/pf2DRao.cpp:105-122)
 // ---------------------------------------------------------------------------------------------
@@ -881,6 +1004,27 @@ extern "C" double orc_bench_tracks(const orc_model* m, int64_t T, int N, int fra
     auto t1 = std::chrono::steady_clock::now();
     for (int64_t t = 0; t < T; t++) orc_filter_destroy(filt[t]);
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// candidate generation front-end for one person (src/pfPose.cpp:216-236 with getSamples, src/pf2DRao.cpp:85-103),
+// driven by the shared counter generator.  like: rows x cols uint8 or NULL.
+extern "C" void orc_propose(const orc_filter* armL, const orc_filter* armR, int C, const double* roi, int tracking,
+                            const uint8_t* like, int rows, int cols, uint64_t seed, uint64_t track, uint64_t frame,
+                            double* cand_xy, uint8_t* cand_L)
+{
+    const orc_filter* arm[2] = {armL, armR};
+    for (int h = 0; h < 2; h++) {
+        double xb[12], pose[64];
+        estimator(arm[h], xb);       // getSamples: full_state = getEstimator(); state = H*full_state + M
+        reconstruct(arm[h]->m, xb, pose);
+        for (int c = 0; c < C; c++) {
+            double x, y;
+            mkf_synth_proposal(seed, track, frame, h, C, c, tracking, pose[0], pose[1], roi, rows, cols, 0.8, &x, &y);
+            cand_xy[((size_t)h * 2 + 0) * C + c] = x;
+            cand_xy[((size_t)h * 2 + 1) * C + c] = y;
+            if (cand_L) cand_L[(size_t)h * C + c] = mkf_likelihood_lookup(like, rows, cols, x, y);
+        }
+    }
 }
 
 // expose the shared synthetic generator so numpy-free tests can pin it

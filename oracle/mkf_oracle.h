@@ -91,6 +91,18 @@ int orc_associate(const orc_filter* armL, const orc_filter* armR, int C, const d
                   const uint8_t* cand_L, const double* roi, int img_rows, int img_cols, const double* u_cand,
                   const uint64_t* seed_cand, uint8_t* gate, double* weights, int32_t* bins, double* meas);
 
+/* candidate generation front-end for one person (src/pfPose.cpp:216-236, src/pf2DRao.cpp:85-103) on the shared
+ * counter generator: cand_xy 2 x 2 x C, cand_L 2 x C (NULL with like NULL) */
+void orc_propose(const orc_filter* armL, const orc_filter* armR, int C, const double* roi, int tracking,
+                 const uint8_t* like, int rows, int cols, uint64_t seed, uint64_t track, uint64_t frame, double* cand_xy,
+                 uint8_t* cand_L);
+
+/* output back-end (src/pfPose.cpp:84-208): get3Dpose of one D-vector estimate with camera matrix Kc (3 x 3) ->
+ * pos3D 3 x 5; skeleton = publishTFtree translations (9 x 3, broadcast order) + camera Euler triple (tf 10 x 3)
+ * and publish2Dpos joints (8 x 2) from the two arms' estimates */
+void orc_get3dpose(const double* estimate, const double* Kc, double* pos3D);
+void orc_skeleton(const double* e1, const double* e2, const double* Kc, double* tf, double* joints2d);
+
 /* legacy plain particle filter (src/pf2D.cpp, uncompiled in the reference) */
 typedef struct orc_pf2d orc_pf2d;
 /* gmm: K components over d dims: means K x d, covs K x d x d, weights K (my_gmm::loadGaussian, src/pf2D.cpp:28-37) */

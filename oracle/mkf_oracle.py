@@ -78,6 +78,10 @@ def lib():
     L.orc_cvrng.argtypes = [C.c_uint64, C.c_int, C.c_int, _ip, C.c_int, _dp]
     L.orc_associate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, _bp, _dp, C.c_int, C.c_int, _dp, _u64p, _bp,
                                 _dp, _ip, _dp]
+    L.orc_propose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_int, _bp, C.c_int, C.c_int, C.c_uint64,
+                              C.c_uint64, C.c_uint64, _dp, _bp]
+    L.orc_get3dpose.argtypes = [_dp, _dp, _dp]
+    L.orc_skeleton.argtypes = [_dp, _dp, _dp, _dp, _dp]
     L.orc_pf2d_create.restype = C.c_void_p
     L.orc_pf2d_create.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     L.orc_pf2d_destroy.argtypes = [C.c_void_p]
@@ -336,3 +340,33 @@ def synth_candidate(seed, track, frame, hand, Cn, c, jitter=1):
     lib().orc_synth_candidate(int(seed), int(track), int(frame), hand, Cn, c, jitter, C.byref(cx), C.byref(cy),
                               C.byref(Lv))
     return cx.value, cy.value, Lv.value
+
+
+KINECT_K = np.array([[525.0, 0.0, 319.5], [0.0, 525.0, 239.5], [0.0, 0.0, 1.0]])  # src/pfPose.cpp:101
+
+
+def get3dpose(estimate, K=KINECT_K):
+    e = _f64(estimate)
+    K = _f64(K)
+    out = np.zeros((3, 5))
+    lib().orc_get3dpose(_ptr(e, _dp), _ptr(K, _dp), _ptr(out, _dp))
+    return out
+
+
+def skeleton(e1, e2, K=KINECT_K):
+    e1, e2, K = _f64(e1), _f64(e2), _f64(K)
+    tf = np.zeros((10, 3))
+    j2 = np.zeros((8, 2))
+    lib().orc_skeleton(_ptr(e1, _dp), _ptr(e2, _dp), _ptr(K, _dp), _ptr(tf, _dp), _ptr(j2, _dp))
+    return tf, j2
+
+
+def propose(armL: Filter, armR: Filter, Cn, roi, tracking, like, seed, track, frame):
+    roi = _f64(roi)
+    xy = np.zeros((2, 2, Cn))
+    Lv = np.zeros((2, Cn), np.uint8) if like is not None else None
+    rows, cols = (like.shape if like is not None else (480, 640))
+    like_c = np.ascontiguousarray(like, np.uint8) if like is not None else None
+    lib().orc_propose(armL.h, armR.h, Cn, _ptr(roi, _dp), int(tracking), _ptr(like_c, _bp), rows, cols, int(seed),
+                      int(track), int(frame), _ptr(xy, _dp), _ptr(Lv, _bp))
+    return xy, Lv
