@@ -59,6 +59,9 @@ extern "C" {
 #define MKF_MEM_AUTO 0 /* ask the driver (cudaPointerGetAttributes) */
 #define MKF_MEM_HOST 1
 #define MKF_MEM_DEVICE 2
+#define MKF_MEM_HOST_ASYNC 3 /* PINNED host memory, no synchronisation: the copies are ordered on the batch's
+                                stream and the caller waits (mkf_batch_sync) before touching the buffers;
+                                honoured by mkf_batch_update and mkf_batch_estimate */
 
 /* measurement layouts accepted by mkf_batch_update */
 #define MKF_MEAS_SHARED 0   /* T x 6       : one column per track, replicated to its N slots */

@@ -15,7 +15,7 @@ OK = 0
 E_INVALID, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 CHOL_CV24_LITERAL, CHOL_CV3_LITERAL, CHOL_EXACT = 0, 1, 2
 ALIAS_INDEPENDENT, ALIAS_CV_SHALLOW_LITERAL = 0, 1
-MEM_AUTO, MEM_HOST, MEM_DEVICE = 0, 1, 2
+MEM_AUTO, MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2, 3
 MEAS_SHARED, MEAS_PER_SLOT = 0, 1
 ST_IND_FALLBACK, ST_POST_FALLBACK, ST_POST_DEGENERATE, ST_CHOL_FAIL = 0x1, 0x2, 0x4, 0x8
 ST_CAND_FALLBACK, ST_CAND_DEGENERATE, ST_IND_WRAP = 0x10, 0x20, 0x40

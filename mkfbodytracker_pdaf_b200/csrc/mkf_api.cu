@@ -98,7 +98,7 @@ struct mkf_batch {
 static bool is_device_ptr(const void* p, int mem)
 {
     if (mem == MKF_MEM_DEVICE) return true;
-    if (mem == MKF_MEM_HOST) return false;
+    if (mem == MKF_MEM_HOST || mem == MKF_MEM_HOST_ASYNC) return false;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
@@ -527,7 +527,7 @@ extern "C" int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int 
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if ((rc = ox.finish(b)) || (rc = op.finish(b))) return rc;
-    if (ox.host || op.host) CK(cudaStreamSynchronize(b->stream));
+    if ((ox.host || op.host) && mem != MKF_MEM_HOST_ASYNC) CK(cudaStreamSynchronize(b->stream));
     return MKF_OK;
 }
 

@@ -115,11 +115,11 @@ class TrackBatch:
         p, mem = _addr(u_init)
         L.check(L.lib.mkf_batch_reset(self._h, p, mem))
 
-    def update(self, meas, u_ind, u_post, seeds=None, layout=None):
+    def update(self, meas, u_ind, u_post, seeds=None, layout=None, mem=None):
         """ParticleFilter::update for all tracks.  meas: (T,6) shared or (T,6,N) per-slot."""
         if layout is None:
             layout = L.MEAS_SHARED if len(meas.shape) == 2 else L.MEAS_PER_SLOT
-        mem = _same_mem(meas, u_ind, u_post, seeds)
+        mem = _same_mem(meas, u_ind, u_post, seeds) if mem is None else mem
         L.check(L.lib.mkf_batch_update(self._h, _addr(meas)[0], layout, _addr(u_ind)[0], _addr(u_post)[0],
                                        _addr(seeds)[0], mem))
 
