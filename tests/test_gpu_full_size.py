@@ -1,0 +1,132 @@
+"""BASELINE.json configs 3, 4, 5 at their full sizes: the oracle cannot run them in seconds, so parity is checked
+through size-independent properties plus oracle spot-checks of a few tracks (config 2 full size lives in
+test_gpu_parity.py::test_full_size_properties_config2)."""
+import numpy as np
+import pytest
+
+import mkf_oracle as orc
+import mkfbodytracker_pdaf_b200 as mk
+from helpers import RTOL, rel_err, rel_err_weights, synth_frame, synth_u_init
+
+pytestmark = pytest.mark.gpu
+
+
+def check_resample_properties(par, wn, N, rows):
+    assert par.min() >= 0 and par.max() < N
+    assert np.all(np.diff(par, axis=1) >= 0)
+    for t in rows:
+        cnt = np.bincount(par[t], minlength=N)
+        assert cnt.sum() == N and np.all(np.abs(cnt - N * wn[t]) < 1 + 1e-9)
+
+
+def test_config5_full_size_one_million_tracks(right_arm):
+    torch = pytest.importorskip("torch")
+    seed, T, N = 0x5EED0005, 1 << 20, 15
+    dev = torch.device("cuda:0")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        b = mk.TrackBatch(right_arm.mk, T, N, stream=s.cuda_stream)
+        meas = torch.empty((T, 6), dtype=torch.float64, device=dev)
+        ui = torch.empty(T, dtype=torch.float64, device=dev)
+        up = torch.empty(T, dtype=torch.float64, device=dev)
+        u0 = torch.empty(T, dtype=torch.float64, device=dev)
+        b.synth_fill(seed, 0, 0xFFFFFF, 1, mk.MEAS_SHARED, meas, u0, None)
+        b.reset(u0)
+        frames = 3
+        for fr in range(frames):
+            b.synth_fill(seed, 0, fr, 1, mk.MEAS_SHARED, meas, ui, up)
+            b.update(meas, ui, up)
+        d = b.download(state=False, cov=False)
+        xb, pose = b.estimate()
+    assert not d["status"].any()
+    assert np.allclose(d["w_norm"].sum(1), 1.0, rtol=0, atol=1e-12)
+    check_resample_properties(d["parents"], d["w_norm"], N, range(0, T, 65537))
+    assert np.all(np.diff(d["indicators"], axis=1) >= 0) and np.isfinite(pose).all()
+    u0h = u0.cpu().numpy()
+    for t in (0, 524287, T - 1):  # oracle spot-check, free-running
+        f = orc.Filter(right_arm.orc, N)
+        f.reset(u=u0h[t])
+        for fr in range(frames):
+            mz, a_, c_ = synth_frame(seed, [t], fr)
+            r = f.update(mz[0], a_[0], c_[0])
+        assert np.array_equal(d["parents"][t], r["parents"])
+        assert rel_err_weights(d["w_norm"][t], r["w_norm"]) <= RTOL
+        xo, po = f.estimate()
+        assert rel_err(xb[t], xo) <= RTOL and rel_err(pose[t], po) <= RTOL
+
+
+def test_config4_full_size(left_arm):
+    torch = pytest.importorskip("torch")
+    seed, T, N = 0x5EED0004, 256, 65536
+    dev = torch.device("cuda:0")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        b = mk.TrackBatch(left_arm.mk, T, N, stream=s.cuda_stream)
+        meas = torch.empty((T, 6, N), dtype=torch.float64, device=dev)
+        ui = torch.empty(T, dtype=torch.float64, device=dev)
+        up = torch.empty(T, dtype=torch.float64, device=dev)
+        u0 = torch.tensor(synth_u_init(seed, range(T)), device=dev)
+        b.reset(u0)
+        frames = 2
+        for fr in range(frames):
+            b.synth_fill(seed, 0, fr, 0, mk.MEAS_PER_SLOT, meas, ui, up)
+            b.update(meas, ui, up)
+        par = torch.empty((T, N), dtype=torch.int32, device=dev)
+        wsum = torch.empty(T, dtype=torch.float64, device=dev)
+        status = torch.empty(T, dtype=torch.int32, device=dev)
+        mk._lib.check(mk._lib.lib.mkf_batch_download(b._h, None, None, None, None, None, par.data_ptr(),
+                                                     wsum.data_ptr(), status.data_ptr(), mk.MEM_DEVICE))
+        xb, pose = b.estimate()
+    par = par.cpu().numpy()
+    assert not (status.cpu().numpy() & 0x4C).any() and (wsum.cpu().numpy() > 0).all()
+    assert par.min() >= 0 and par.max() < N and np.all(np.diff(par, axis=1) >= 0)
+    # oracle spot-check of one full 65 536-slot track, free-running over both frames
+    t = 131
+    f = orc.Filter(left_arm.orc, N)
+    f.reset(u=float(u0[t].cpu()))
+    for fr in range(frames):
+        mz, a_, c_ = synth_frame(seed, [t], fr, N, jitter=0)
+        r = f.update(mz[0], a_[0], c_[0])
+    assert np.array_equal(par[t], r["parents"])
+    xo, po = f.estimate()
+    assert rel_err(xb[t], xo) <= RTOL and rel_err(pose[t], po) <= RTOL
+
+
+def test_config3_full_size_gate_and_bins(left_arm, right_arm):
+    torch = pytest.importorskip("torch")
+    seed, T, N, Cn = 0x5EED0003, 16384, 15, 17
+    s = torch.cuda.Stream()
+    b0 = mk.TrackBatch(left_arm.mk, T, N, stream=s.cuda_stream)
+    b1 = mk.TrackBatch(right_arm.mk, T, N, stream=s.cuda_stream)
+    rng = np.random.default_rng(3)
+    u0 = rng.random(T)
+    b0.reset(u0)
+    b1.reset(u0)
+    cand = np.zeros((T, 2, 2, Cn))
+    cand[:, :, 0] = rng.uniform(-32, 672, (T, 2, Cn))
+    cand[:, :, 1] = rng.uniform(-24, 504, (T, 2, Cn))
+    cand[:, 0, :, 0] = [388.0, 250.0]
+    cand[:, 1, :, 0] = [248.0, 250.0]
+    cand[::50, :, 0, 1] = 0.0     # exactly on the image border: the gate is strict (src/pfPose.cpp:251)
+    cand[::75, :, 1, 2] = 480.0
+    Lv = np.where(rng.random((T, 2, Cn)) < 0.5, 0, rng.integers(1, 129, (T, 2, Cn))).astype(np.uint8)
+    Lv[:, :, 0] = 220
+    roi = np.tile(np.array([300.0, 51.0, 47.0, 47.0]), (T, 1))
+    u_c, u_i, u_p = rng.random((T, 2)), rng.random((T, 2)), rng.random((T, 2))
+    mk.associate(b0, b1, cand, Lv, roi, u_c, u_i, u_p)
+    res = mk.assoc_results(b0, Cn)
+    x, y = cand[:, :, 0], cand[:, :, 1]
+    gate = (y > 0) & (y < 480) & (x > 0) & (x < 640) & (Lv != 0)
+    assert np.array_equal(res["gate"].astype(bool), gate), "gate decisions must be bit-exact at full size"
+    w = res["weights"]
+    assert np.all(w[~gate] == 0) and np.allclose(w.sum(2), 1.0, rtol=0, atol=1e-12)
+    bins = res["bins"]
+    assert np.all(np.diff(bins, axis=2) >= 0) and bins.min() >= 0 and bins.max() < Cn
+    assert np.all(np.take_along_axis(gate, bins.astype(np.int64), axis=2)), "only gated candidates are drawn"
+    fL, fR = orc.Filter(left_arm.orc, N), orc.Filter(right_arm.orc, N)
+    for t in (0, 50, 8191, T - 1):  # oracle spot-checks
+        fL.reset(u=u0[t])
+        fR.reset(u=u0[t])
+        want = orc.associate(fL, fR, cand[t], Lv[t], roi[t], u_c[t])
+        assert np.array_equal(res["gate"][t], want["gate"]) and np.array_equal(bins[t], want["bins"])
+        assert rel_err_weights(w[t], want["weights"]) <= RTOL
