@@ -130,17 +130,26 @@ static int estimate_pose_device(mkf_batch* b, double* d_pose)
 #define LAUNCH_EST(DD, BT)                                                                                   \
     k_estimate<DD, BT><<<(unsigned)b->T, BT, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean, \
                                                               b->d_tinv, nullptr, d_pose)
+#define LAUNCH_EST_SMALL(DD, G)                                                                              \
+    k_estimate_small<DD, G><<<grid_for(b->T, 128 / G), 128, 0, b->stream>>>(st, b->parent, b->T, b->N, m->D,  \
+                                                                             b->d_recon, b->d_pmean, b->d_tinv, \
+                                                                             nullptr, d_pose)
     if (m->d == 12) {
-        if (b->N <= 64)
-            LAUNCH_EST(12, 32);
+        if (b->N <= 16)
+            LAUNCH_EST_SMALL(12, 16);
+        else if (b->N <= 96)
+            LAUNCH_EST_SMALL(12, 32);
         else
             LAUNCH_EST(12, 128);
     } else {
-        if (b->N <= 64)
-            LAUNCH_EST(10, 32);
+        if (b->N <= 16)
+            LAUNCH_EST_SMALL(10, 16);
+        else if (b->N <= 96)
+            LAUNCH_EST_SMALL(10, 32);
         else
             LAUNCH_EST(10, 128);
     }
+#undef LAUNCH_EST_SMALL
 #undef LAUNCH_EST
     MKF_LAUNCHED();
     CK(cudaGetLastError());

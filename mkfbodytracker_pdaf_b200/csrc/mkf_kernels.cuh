@@ -825,6 +825,60 @@ __global__ void __launch_bounds__(BT) k_estimate(const double2* __restrict__ st,
     }
 }
 
+// getEstimator + reconstruction for small N: GROUP (16 or 32) lanes per track, several tracks per CTA
+template <int D, int GROUP>
+__global__ void __launch_bounds__(128) k_estimate_small(const double2* __restrict__ st, const int32_t* __restrict__ parent,
+                                                         long long T, int N, int Dpose, const double* __restrict__ recon,
+                                                         const double* __restrict__ pmean, const double* __restrict__ tinv,
+                                                         double* __restrict__ xbar_out, double* __restrict__ pose_out)
+{
+    using L = SlotLay<D>;
+    constexpr int TPB = 128 / GROUP; // tracks per CTA
+    __shared__ double xb[TPB][D];
+    const int g = threadIdx.x / GROUP, l = threadIdx.x % GROUP;
+    const long long t = (long long)blockIdx.x * TPB + g;
+    double acc[D];
+#pragma unroll
+    for (int e = 0; e < D; e++) acc[e] = 0.0;
+    if (t < T) {
+        for (int j = l; j < N; j += GROUP) {
+            const long long sp = t * N + __ldg(parent + t * N + j);
+            const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+#pragma unroll
+            for (int p = 0; p < D / 2; p++) {
+                const double2 q = __ldg(src + p * 32);
+                acc[2 * p] += q.x;
+                acc[2 * p + 1] += q.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < D; e++) {
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    if (l == 0) {
+#pragma unroll
+        for (int e = 0; e < D; e++) xb[g][e] = acc[e] * (1.0 / (double)N);
+    }
+    __syncthreads();
+    if (t >= T) return;
+    for (int r = l; r < Dpose + D; r += GROUP) {
+        if (r < Dpose) {
+            if (!pose_out) continue;
+            double sacc = 0.0;
+            for (int c = 0; c < D; c++) sacc = fma(recon[r * D + c], xb[g][c], sacc);
+            pose_out[t * Dpose + r] = sacc + pmean[r];
+        } else {
+            if (!xbar_out) continue;
+            const int q = r - Dpose;
+            double sacc = 0.0;
+            for (int c = 0; c < D; c++) sacc = fma(tinv[q * D + c], xb[g][c], sacc);
+            xbar_out[t * D + q] = sacc;
+        }
+    }
+}
+
 // -----------------------------------------------------------------------------------------
 // state I/O
 // -----------------------------------------------------------------------------------------

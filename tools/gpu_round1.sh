@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; python -c "import json,sys; d=json.loads(open('gpurun_out/bench_r01.json').read()); print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e'],'clocks',d['clocks'],'roofline',d['roofline']['frac'], d['cpu_baseline'])"
-tail -3 gpurun_out/bench_r01.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/bench_configs.py 2b 5 3
