@@ -676,11 +676,15 @@ extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t se
         rc = MKF_E_NOMEM;
     }
     if (!rc) {
-        cudaMemcpy(d_w, w, (size_t)L * 8, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_u, &uu, 8, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_seed, &seed, 8, cudaMemcpyHostToDevice);
-        cudaMemset(d_st, 0, 4);
-        cudaMemset(d_fb, 0, 4);
+        if ((e = cudaMemcpy(d_w, w, (size_t)L * 8, cudaMemcpyHostToDevice)) ||
+            (e = cudaMemcpy(d_u, &uu, 8, cudaMemcpyHostToDevice)) ||
+            (e = cudaMemcpy(d_seed, &seed, 8, cudaMemcpyHostToDevice)) || (e = cudaMemset(d_st, 0, 4)) ||
+            (e = cudaMemset(d_fb, 0, 4))) {
+            mkf_set_error("mkf_resample: %s", cudaGetErrorString(e));
+            rc = MKF_E_CUDA;
+        }
+    }
+    if (!rc) {
         // the reference applies resample() to already-normalised weights: no division here
         if (L <= 64 && N <= 64)
             k_resample_small<<<1, 32>>>(d_w, 1, L, N, d_u, 1, 0, d_ws, d_out, d_st, 1, d_fb, MKF_ST_POST_DEGENERATE);
@@ -696,9 +700,12 @@ extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t se
             rc = MKF_E_CUDA;
         }
         uint32_t st = 0;
-        cudaMemcpy(&st, d_st, 4, cudaMemcpyDeviceToHost);
+        if (!rc && (e = cudaMemcpy(&st, d_st, 4, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            mkf_set_error("mkf_resample: %s", cudaGetErrorString(e));
+            rc = MKF_E_CUDA;
+        }
         if (!rc) rc = (st & MKF_ST_POST_DEGENERATE) ? 1 : 0; // like orc_resample: 1 = degenerate fallback taken
-    } else {
+    } else if (rc == MKF_E_NOMEM) {
         mkf_set_error("mkf_resample: cudaMalloc failed");
     }
     void* ptrs[] = {d_w, d_u, d_ws, d_out, d_st, d_fb, d_seed};

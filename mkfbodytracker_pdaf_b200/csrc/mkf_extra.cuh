@@ -49,11 +49,14 @@ extern "C" int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int 
     };
     if ((rc = dcomp.ensure((size_t)n * 4)) || (rc = dz.ensure((size_t)n * 6 * 8)) || (rc = du.ensure((size_t)n * 8)))
         return done2(rc);
-    cudaMemcpyAsync(dcomp.p, comp, (size_t)n * 4, cudaMemcpyHostToDevice, b->stream);
-    if (z)
-        cudaMemcpyAsync(dz.p, z, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, b->stream);
-    else
-        cudaMemsetAsync(dz.p, 0, (size_t)n * 6 * 8, b->stream);
+    cudaError_t ce = cudaMemcpyAsync(dcomp.p, comp, (size_t)n * 4, cudaMemcpyHostToDevice, b->stream);
+    if (ce == cudaSuccess)
+        ce = z ? cudaMemcpyAsync(dz.p, z, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, b->stream)
+               : cudaMemsetAsync(dz.p, 0, (size_t)n * 6 * 8, b->stream);
+    if (ce != cudaSuccess) {
+        mkf_set_error("mkf_kf_apply: %s", cudaGetErrorString(ce));
+        return done2(MKF_E_CUDA);
+    }
     k_set_bounds_from_comp<<<grid_for(n, 128), 128, 0, b->stream>>>((const int32_t*)dcomp.p, n, m->K, b->bounds,
                                                                      b->parent);
     MKF_LAUNCHED();
