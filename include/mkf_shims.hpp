@@ -23,7 +23,6 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
-#include <random>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -391,28 +390,18 @@ class ParticleFilter {
         return mkf::unflat(xb.data(), gmm.d(), 1);
     }
     // ParticleFilter::getSamples (src/pf2DRao.cpp:85-103): N proposals ~ N(hand estimate, (0.8 scale)^2) per axis
-    // (cv::randn takes C = 0.8*scale*I as a standard-deviation matrix, quirk B10).  Host-side sampling from a
-    // std::mt19937_64 seeded like the resampler; distribution-equivalent, not bit-equivalent, to cv::randn.
+    // (cv::randn takes C = 0.8*scale*I as a standard-deviation matrix, quirk B10).  Drawn on the device by
+    // mkf_batch_propose from the counter generator of mkf_synth.h (cv::randn's stream is not reproducible);
+    // distribution-equivalent to second order, not bit-equivalent, to cv::randn.
     cv::Mat getSamples(cv::Mat H, cv::Mat M, int N, double scale)
     {
         (void)H;
         (void)M; // the model already holds pca_proj / pca_mean
-        std::vector<double> pose(gmm.D());
-        mkf::check(mkf_batch_estimate(gmm.batch(), nullptr, pose.data(), MKF_MEM_HOST));
-        std::mt19937_64 eng(next_seed());
-        std::normal_distribution<double> nx(pose[0], gmm.params.proposal_spread * scale),
-            ny(pose[1], gmm.params.proposal_spread * scale);
-        cv::Mat out = cv::Mat::zeros(2, N
-#ifdef MKF_HAVE_OPENCV
-                                     ,
-                                     CV_64F
-#endif
-        );
-        for (int i = 0; i < N; i++) {
-            out.at<double>(0, i) = nx(eng);
-            out.at<double>(1, i) = ny(eng);
-        }
-        return out;
+        const double roi[4] = {0.0, 0.0, scale, scale};
+        std::vector<double> xy((size_t)4 * N); // 2 hands x 2 rows x N; this filter plays both arms, hand 0 is used
+        mkf::check(mkf_batch_propose(gmm.batch(), gmm.batch(), N, roi, nullptr, nullptr, 1, next_seed(), sample_calls_++,
+                                     0, xy.data(), nullptr, MKF_MEM_HOST));
+        return mkf::unflat(xy.data(), 2, N);
     }
     // ParticleFilter::getSampleProb (src/pf2DRao.cpp:105-122)
     void getSampleProb(cv::Mat H, cv::Mat M, cv::Mat input1, cv::Mat input2, std::vector<double>& weight1,
@@ -454,6 +443,7 @@ class ParticleFilter {
     }
     bool seeded_ = false;
     uint64_t seed_ = 0;
+    uint64_t sample_calls_ = 0;
 };
 
 #endif // MKF_SHIMS_HPP

@@ -51,7 +51,7 @@ def test_oracle_get3dpose_matches_numpy(left_arm, rng):
 
 
 def test_camera_matrix_loader():
-    K = mk.load_camera_matrix(os.path.join(mk.MODEL_DIR, "cal.yml"))
+    K = mk.load_camera_matrix(os.path.join(mk.MODEL_DIR, "webcam_camera_matrix.yml"))
     assert np.array_equal(K, np.array([[660.326889, 0, 318.70589], [0, 660.857176, 240.784699], [0, 0, 1]]))  # cal.yml:4-7
     with pytest.raises(mk.MkfError):
         mk.load_camera_matrix("/nonexistent/cal.yml")
@@ -77,7 +77,7 @@ def test_pose3d_and_skeleton_on_device(left_arm, right_arm):
             b.update(meas, ui, up)
             for t in range(T):
                 fs[t].update(meas[t], ui[t], up[t])
-    Kcal = mk.load_camera_matrix(os.path.join(mk.MODEL_DIR, "cal.yml"))
+    Kcal = mk.load_camera_matrix(os.path.join(mk.MODEL_DIR, "webcam_camera_matrix.yml"))
     for K in (None, Kcal):
         p3 = b0.pose3d(K)
         tf, j2 = mk.skeleton(b0, b1, K)

@@ -53,16 +53,4 @@ for fn in ("data13D_PCA_100000_15_12.yml", "data23D_PCA_100000_15_12.yml"):
         b = fs2.getNode(k).mat()
         assert b.dtype == mats[k].dtype and b.shape == mats[k].shape and np.array_equal(b, mats[k]), (fn, k)
     print("wrote", fn)
-# cal.yml (ROS camera_calibration format) is tiny; re-emit its numbers too
-import re
-txt = open(os.path.join(REF, "cal.yml")).read()
-def grab(key):
-    m = re.search(key + r":\s*\n\s*rows:\s*(\d+)\s*\n\s*cols:\s*(\d+)\s*\n\s*data:\s*\[([^\]]*)\]", txt)
-    return int(m.group(1)), int(m.group(2)), [float(v) for v in m.group(3).split(",")]
-with open(os.path.join(OUT, "cal.yml"), "w") as f:
-    f.write("# camera calibration shipped with the reference (never read by its code; SURVEY.md section 0)\n")
-    f.write("image_width: 640\nimage_height: 480\n")
-    for key in ("camera_matrix", "distortion_coefficients", "rectification_matrix", "projection_matrix"):
-        r, c, d = grab(key)
-        f.write(f"{key}:\n  rows: {r}\n  cols: {c}\n  data: [{', '.join(repr(v) for v in d)}]\n")
-print("wrote cal.yml")
+# the webcam camera matrix (cal.yml:4-7) lives in models/webcam_camera_matrix.yml (hand-written, 9 numbers)
