@@ -62,7 +62,9 @@ __device__ __forceinline__ dd dd_add_d(dd a, double b)
 __device__ __forceinline__ int mkf_count_le(dd C, double beta0, double step, int N, double tol, bool& amb)
 {
     dd df = dd_add_d(C, -beta0);
-    double qi = floor(__ddiv_rn(df.hi, step));
+    // quotient estimate: step = fl(1/N), so df.hi * N is within one unit of df.hi / step; the remainder test
+    // below corrects it (a double division here would cost more than the rest of the function)
+    double qi = floor(__dmul_rn(df.hi, (double)N));
     double rem = __dadd_rn(__fma_rn(-qi, step, df.hi), df.lo); // C - T_qi
     if (rem < 0.0) {
         qi -= 1.0;
@@ -204,6 +206,33 @@ __device__ __forceinline__ dd mkf_block_excl_scan_dd(dd v, dd* scratch, dd& tota
     dd prev = dd_shfl_up(inc, 1);
     if (lane == 0) prev = dd_make(0.0);
     return dd_add(pre, prev);
+}
+
+// block-wide exclusive scan of one double per thread (plain IEEE adds); also returns the block total
+template <int BT>
+__device__ __forceinline__ double mkf_block_excl_scan_d(double v, double* scratch, double& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    double pre = 0.0, tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < BT / 32; w++) {
+        const double s = scratch[w];
+        if (w < wid) pre += s;
+        tot += s;
+    }
+    __syncthreads();
+    total = tot;
+    double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prev = 0.0;
+    return pre + prev;
 }
 
 // block-wide exclusive max-scan of one int per thread (identity -1); returns block max in total

@@ -595,44 +595,44 @@ __global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict_
                                                         uint32_t* __restrict__ need_fb, uint32_t bit_fb,
                                                         uint32_t bit_deg)
 {
-    __shared__ dd sc_dd[BT / 32];
     __shared__ int sc_i[BT / 32];
-    __shared__ double sc_d[BT / 32];
+    __shared__ double sc_d[BT / 32], sc_d2[BT / 32];
     __shared__ int sh_flag;
     const long long t = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double* __restrict__ w = w_all + t * L;
     int32_t* __restrict__ out = out_all + t * N;
 
-    // pass 1: exact (double-double) sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172)
-    dd acc = dd_make(0.0);
-    double mx = 0.0;
+    // pass 1: sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172).  The sum only has to be an accurate
+    // normaliser (the reference's own sequential sum is no more exact); the stored value is reused by
+    // k_resample_fallback so both paths normalise identically.
+    double acc = 0.0, mx = 0.0;
     for (int i = tid; i < L; i += BT) {
         const double x = w[i];
-        acc = dd_add_d(acc, x);
+        acc += x;
         if (x > mx) mx = x;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        acc = dd_add(acc, dd_shfl_xor(acc, o));
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     if (lane == 0) {
-        sc_dd[wid] = acc;
-        sc_d[wid] = mx;
+        sc_d[wid] = acc;
+        sc_d2[wid] = mx;
     }
     if (tid == 0) sh_flag = 0;
     __syncthreads();
-    acc = dd_make(0.0);
+    acc = 0.0;
     mx = 0.0;
 #pragma unroll
     for (int q = 0; q < BT / 32; q++) {
-        acc = dd_add(acc, sc_dd[q]);
-        mx = fmax(mx, sc_d[q]);
+        acc += sc_d[q];
+        mx = fmax(mx, sc_d2[q]);
     }
     __syncthreads();
-    const double wsum = normalise ? acc.hi : 1.0;
-    if (tid == 0 && wsum_out) wsum_out[t] = acc.hi;
+    const double wsum = normalise ? acc : 1.0;
+    if (tid == 0 && wsum_out) wsum_out[t] = acc;
     const double wmax_n = normalise ? __ddiv_rn(mx, wsum) : mx;
     if (!(wmax_n > 0.0)) { // max weight 0 / NaN -> random-index fallback (src/pf2DRao.cpp:184-192)
         if (tid == 0) {
@@ -643,40 +643,45 @@ __global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict_
     }
     const double step = __ddiv_rn(1.0, (double)N);
     const double beta0 = __dmul_rn(u[t * u_stride], step);
-    const double tol = mkf_resample_tol(N, L, wmax_n, step);
+    // ambiguity band: rounding the sequential loop may have accumulated (mkf_resample_tol) plus the error of the
+    // prefix sums below -- at most 13 roundings on the way to any C_k, each <= 2^-53 x (a partial sum <= S):
+    // bounded by 16 * 2^-53 * S with S the total mass (1 after normalisation)
+    const double mass = normalise ? 1.0 : acc;
+    const double tol = mkf_resample_tol(N, L, wmax_n, step) + 16.0 * 1.1102230246251565e-16 * (1.0 + mass);
 
     for (int i = tid; i < N; i += BT) out[i] = -1;
     __syncthreads();
 
-    // pass 2: double-double prefix sums of the normalised weights -> child ranges
+    // pass 2: prefix sums of the normalised weights -> child ranges.  Within a tile the scan is plain double;
+    // the carry across tiles is kept in double-double so the error does not grow with the number of tiles.
     dd carry = dd_make(0.0);
     bool amb = false;
     for (int base = 0; base < L; base += BT * ITEMS) {
         const int i0 = base + tid * ITEMS;
-        dd pre[ITEMS];
-        dd run = dd_make(0.0);
+        double pre[ITEMS];
+        double run = 0.0;
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) {
             double x = (i0 + q < L) ? w[i0 + q] : 0.0;
             if (normalise) x = __ddiv_rn(x, wsum);
-            run = dd_add_d(run, x);
+            run += x;
             pre[q] = run;
         }
-        dd tile_tot;
-        dd excl = mkf_block_excl_scan_dd<BT>(run, sc_dd, tile_tot);
-        const dd start = dd_add(carry, excl);
+        double tile_tot;
+        const double excl = mkf_block_excl_scan_d<BT>(run, sc_d, tile_tot);
+        const dd start = dd_add_d(carry, excl);
         int e_prev = 0; // e_{-1} = 0 by definition: no output precedes the first weight
         if (i0 > 0 && i0 < L) e_prev = mkf_count_le(start, beta0, step, N, tol, amb);
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) {
             if (i0 + q < L) {
-                const int e = mkf_count_le(dd_add(start, pre[q]), beta0, step, N, tol, amb);
+                const int e = mkf_count_le(dd_add_d(start, pre[q]), beta0, step, N, tol, amb);
                 if (e > e_prev) out[e_prev] = i0 + q;
                 if (i0 + q == L - 1 && e < N) amb = true; // literal loop would wrap past the last weight
                 e_prev = e;
             }
         }
-        carry = dd_add(carry, tile_tot);
+        carry = dd_add_d(carry, tile_tot);
     }
     if (amb) sh_flag = 1;
     __syncthreads();
