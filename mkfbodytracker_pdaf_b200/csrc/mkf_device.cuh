@@ -35,12 +35,6 @@ __device__ __forceinline__ dd dd_fast_two_sum(double a, double b) // |a| >= |b|
     r.lo = __dsub_rn(b, __dsub_rn(r.hi, a));
     return r;
 }
-__device__ __forceinline__ dd dd_add(dd a, dd b)
-{
-    dd s = dd_two_sum(a.hi, b.hi);
-    s.lo = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
-    return dd_fast_two_sum(s.hi, s.lo);
-}
 __device__ __forceinline__ dd dd_add_d(dd a, double b)
 {
     dd s = dd_two_sum(a.hi, b);
@@ -165,49 +159,6 @@ __device__ __forceinline__ void mkf_mbar_wait(uint64_t* bar, uint32_t phase)
 // ---------------------------------------------------------------------------------------------
 // warp / block collectives
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ dd dd_shfl_up(dd v, int delta)
-{
-    dd r;
-    r.hi = __shfl_up_sync(0xffffffffu, v.hi, delta);
-    r.lo = __shfl_up_sync(0xffffffffu, v.lo, delta);
-    return r;
-}
-__device__ __forceinline__ dd dd_shfl_xor(dd v, int m)
-{
-    dd r;
-    r.hi = __shfl_xor_sync(0xffffffffu, v.hi, m);
-    r.lo = __shfl_xor_sync(0xffffffffu, v.lo, m);
-    return r;
-}
-
-// block-wide exclusive scan of one dd per thread; also returns the block total.
-// scratch: BT/32 dd entries of shared memory.  All BT threads must call.
-template <int BT>
-__device__ __forceinline__ dd mkf_block_excl_scan_dd(dd v, dd* scratch, dd& total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    dd inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        dd n = dd_shfl_up(inc, o);
-        if (lane >= o) inc = dd_add(n, inc);
-    }
-    if (lane == 31) scratch[wid] = inc;
-    __syncthreads();
-    dd pre = dd_make(0.0), tot = dd_make(0.0);
-#pragma unroll
-    for (int w = 0; w < BT / 32; w++) {
-        dd s = scratch[w];
-        if (w < wid) pre = dd_add(pre, s);
-        tot = dd_add(tot, s);
-    }
-    __syncthreads();
-    total = tot;
-    dd prev = dd_shfl_up(inc, 1);
-    if (lane == 0) prev = dd_make(0.0);
-    return dd_add(pre, prev);
-}
-
 // block-wide exclusive scan of one double per thread (plain IEEE adds); also returns the block total
 template <int BT>
 __device__ __forceinline__ double mkf_block_excl_scan_d(double v, double* scratch, double& total)

@@ -8,8 +8,6 @@
 #ifndef MKF_PF2D_CUH
 #define MKF_PF2D_CUH
 
-#define MKF_PF2D_MAXD 12
-
 struct mkf_pf2d {
     long long T = 0;
     int N = 0, d = 0, K = 0, device = 0;
