@@ -235,6 +235,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the single JSON line: the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("MKF_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     T, N, K, W = args.tracks, args.slots, args.steps, args.warmup
     F = K + W
