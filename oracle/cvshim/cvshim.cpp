@@ -1,6 +1,8 @@
 // oracle/cvshim/cvshim.cpp -- TEST INFRASTRUCTURE: implementation of the OpenCV-2.4 subset declared
 // in opencv2/core/core.hpp (see the header for scope and caveats).
 #include <deque>
+#include <fstream>
+#include <sstream>
 
 #include "opencv2/core/core.hpp"
 
@@ -181,8 +183,25 @@ double invert(const Mat& src, Mat& dst, int method)
                 result = true;
                 dst.el(0, 0) = 1. / d;
             }
-        } else {
-            cvshim_assert(false, "3x3 closed-form inverse is not part of the subset");
+        } else { // n == 3: determinant + adjugate
+            double d = s.el(0, 0) * (s.el(1, 1) * s.el(2, 2) - s.el(1, 2) * s.el(2, 1)) -
+                       s.el(0, 1) * (s.el(1, 0) * s.el(2, 2) - s.el(1, 2) * s.el(2, 0)) +
+                       s.el(0, 2) * (s.el(1, 0) * s.el(2, 1) - s.el(1, 1) * s.el(2, 0));
+            if (d != 0.) {
+                result = true;
+                d = 1. / d;
+                double t[9];
+                t[0] = (s.el(1, 1) * s.el(2, 2) - s.el(1, 2) * s.el(2, 1)) * d;
+                t[1] = (s.el(0, 2) * s.el(2, 1) - s.el(0, 1) * s.el(2, 2)) * d;
+                t[2] = (s.el(0, 1) * s.el(1, 2) - s.el(0, 2) * s.el(1, 1)) * d;
+                t[3] = (s.el(1, 2) * s.el(2, 0) - s.el(1, 0) * s.el(2, 2)) * d;
+                t[4] = (s.el(0, 0) * s.el(2, 2) - s.el(0, 2) * s.el(2, 0)) * d;
+                t[5] = (s.el(0, 2) * s.el(1, 0) - s.el(0, 0) * s.el(1, 2)) * d;
+                t[6] = (s.el(1, 0) * s.el(2, 1) - s.el(1, 1) * s.el(2, 0)) * d;
+                t[7] = (s.el(0, 1) * s.el(2, 0) - s.el(0, 0) * s.el(2, 1)) * d;
+                t[8] = (s.el(0, 0) * s.el(1, 1) - s.el(0, 1) * s.el(1, 0)) * d;
+                for (int i = 0; i < 9; i++) dst.el(i / 3, i % 3) = t[i];
+            }
         }
     } else {
         setIdentity(dst);
@@ -357,6 +376,153 @@ void randn(Mat& dst, const Mat& mean, const Mat& stddev)
                 dst.ptr<double>(r)[c * cn + k] = v;
             }
         }
+    std::vector<double> rec;
+    for (int r = 0; r < dst.rows; r++)
+        for (int c = 0; c < dst.cols * cn; c++) rec.push_back(dst.ptr<double>(r)[c]);
+    cvshim_random_log().push_back(rec);
+}
+std::vector<std::vector<double> >& cvshim_random_log()
+{
+    static thread_local std::vector<std::vector<double> > log;
+    return log;
+}
+// cv::randu(dst, low, high) for CV_64F: low + (high - low) * U[0,1) from the global RNG (not OpenCV's stream)
+void randu(const Mat& dstc, double low, double high)
+{
+    Mat dst = dstc;
+    std::vector<double> rec;
+    for (int r = 0; r < dst.rows; r++)
+        for (int c = 0; c < dst.cols; c++) {
+            const double v = low + (high - low) * g_the_rng.uniform(0.0, 1.0);
+            dst.el(r, c) = v;
+            rec.push_back(v);
+        }
+    cvshim_random_log().push_back(rec);
+}
+void hconcat(const Mat& a, const Mat& b, Mat& dst)
+{
+    cvshim_assert(a.rows == b.rows, "hconcat height");
+    Mat aa = a.clone(), bb = b.clone();
+    dst.create(a.rows, a.cols + b.cols, CV_64F);
+    for (int r = 0; r < aa.rows; r++) {
+        for (int c = 0; c < aa.cols; c++) dst.el(r, c) = aa.el(r, c);
+        for (int c = 0; c < bb.cols; c++) dst.el(r, aa.cols + c) = bb.el(r, c);
+    }
+}
+
+// GaussianBlur for CV_8UC1 (the likelihood image, src/pfPose.cpp:213): separable, BORDER_REFLECT_101, the 8-bit
+// fixed-point path of OpenCV 2.4's filter engine (kernel scaled by 2^8 per pass, rounding shift by 16 at the end).
+// Restated from memory; the product does not blur (the caller hands over the blurred image).
+void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY, int)
+{
+    cvshim_assert(src.depth() == CV_8U && src.channels() == 1, "GaussianBlur: CV_8UC1 only");
+    if (sigmaY <= 0) sigmaY = sigmaX;
+    auto kernel = [](int n, double sigma) {
+        std::vector<double> k(n);
+        double sum = 0;
+        for (int i = 0; i < n; i++) {
+            const double x = i - (n - 1) * 0.5;
+            k[i] = std::exp(-0.5 * x * x / (sigma * sigma));
+            sum += k[i];
+        }
+        std::vector<int> ki(n);
+        for (int i = 0; i < n; i++) ki[i] = (int)std::lrint((double)(float)(k[i] / sum) * 256.0);
+        return ki;
+    };
+    const std::vector<int> kx = kernel(ksize.width, sigmaX), ky = kernel(ksize.height, sigmaY);
+    auto refl = [](int p, int n) {
+        if (n == 1) return 0;
+        while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+        return p;
+    };
+    Mat s = src.clone();
+    const int R = s.rows, C = s.cols, rx = ksize.width / 2, ry = ksize.height / 2;
+    std::vector<int> tmp((size_t)R * C);
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) {
+            int acc = 0;
+            for (int k = -rx; k <= rx; k++) acc += kx[k + rx] * (int)s.at<uchar>(r, refl(c + k, C));
+            tmp[(size_t)r * C + c] = acc;
+        }
+    dst.create(R, C, CV_8UC1);
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) {
+            int acc = 0;
+            for (int k = -ry; k <= ry; k++) acc += ky[k + ry] * tmp[(size_t)refl(r + k, R) * C + c];
+            const int v = (acc + (1 << 15)) >> 16;
+            dst.at<uchar>(r, c) = (uchar)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+}
+void cvtColor(const Mat& src, Mat& dst, int code)
+{
+    cvshim_assert(code == CV_GRAY2RGB && src.depth() == CV_8U && src.channels() == 1, "cvtColor: GRAY2RGB only");
+    Mat s = src;
+    dst.create(s.rows, s.cols, CV_8UC3);
+    for (int r = 0; r < s.rows; r++)
+        for (int c = 0; c < s.cols; c++) {
+            const uchar v = s.at<uchar>(r, c);
+            uchar* d = dst.data + (size_t)r * dst.step + (size_t)c * 3;
+            d[0] = d[1] = d[2] = v;
+        }
+}
+
+// cv::FileStorage (OpenCV-YAML-1.0), just enough for `fs["key"] >> mat` on !!opencv-matrix nodes
+FileStorage::FileStorage(const std::string& path, int)
+{
+    std::ifstream f(path.c_str());
+    if (f) {
+        std::stringstream ss;
+        ss << f.rdbuf();
+        txt_ = ss.str();
+    }
+}
+FileNode FileStorage::operator[](const char* key) const
+{
+    FileNode n;
+    const std::string pat = std::string(key) + ":";
+    size_t pos = 0;
+    for (;;) {
+        pos = txt_.find(pat, pos);
+        if (pos == std::string::npos) return n;
+        if (pos == 0 || txt_[pos - 1] == '\n') break;
+        pos += pat.size();
+    }
+    const size_t end = txt_.find(']', pos);
+    if (end != std::string::npos) n.text = txt_.substr(pos, end - pos + 1);
+    return n;
+}
+void operator>>(const FileNode& n, Mat& m)
+{
+    if (n.text.empty()) {
+        m = Mat();
+        return;
+    }
+    auto num = [&](const char* name) {
+        const size_t p = n.text.find(name);
+        cvshim_assert(p != std::string::npos, "FileNode: missing field");
+        return std::atoi(n.text.c_str() + p + std::strlen(name));
+    };
+    const int rows = num("rows:"), cols = num("cols:");
+    size_t p = n.text.find("dt:");
+    cvshim_assert(p != std::string::npos, "FileNode: missing dt");
+    p += 3;
+    while (n.text[p] == ' ' || n.text[p] == '"') p++;
+    const char dt = n.text[p];
+    cvshim_assert(dt == 'd' || dt == 'f', "FileNode: dt must be d or f");
+    m.create(rows, cols, dt == 'd' ? CV_64F : CV_32F);
+    p = n.text.find('[', n.text.find("data:"));
+    const char* c = n.text.c_str() + p + 1;
+    for (int i = 0; i < rows * cols; i++) {
+        while (*c == ' ' || *c == ',' || *c == '\n' || *c == '\r' || *c == '\t') c++;
+        char* e = 0;
+        const double v = std::strtod(c, &e);
+        cvshim_assert(e != c, "FileNode: malformed number");
+        if (dt == 'd')
+            m.at<double>(i / cols, i % cols) = v;
+        else
+            m.at<float>(i / cols, i % cols) = (float)v;
+        c = e;
+    }
 }
 Mat& operator*=(Mat& a, double s) // a.convertTo(a, a.type(), s): in place, through views
 {
@@ -447,7 +613,7 @@ void MatExpr::assign(Mat& m) const
         if (flags == 'I')
             setIdentity(m, Scalar(alpha));
         else
-            for (int r = 0; r < m.rows; r++) std::memset(m.ptr<double>(r), 0, sizeof(double) * m.cols * m.channels());
+            for (int r = 0; r < m.rows; r++) std::memset(m.data + (size_t)r * m.step, 0, m.elemSize() * (size_t)m.cols);
         break;
     }
 }

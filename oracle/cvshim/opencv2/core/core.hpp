@@ -21,17 +21,26 @@
 #include <limits>
 #include <memory>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif
 
+#define CV_8U 0
+#define CV_32F 5
 #define CV_64F 6
+#define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_32FC1 5
 #define CV_64FC1 6
 #define CV_64FC2 14
-#define CV_8UC3 16
+#define CV_MAT_DEPTH(t) ((t)&7)
+#define CV_MAT_CN(t) ((((t) >> 3) & 63) + 1)
+#define CV_MAKETYPE(depth, cn) (((depth)&7) + (((cn)-1) << 3))
 #define CV_REDUCE_SUM 0
+#define CV_GRAY2RGB 8
 #define CV_GEMM_A_T 1
 #define CV_GEMM_B_T 2
 #define CV_GEMM_C_T 4
@@ -86,15 +95,36 @@ struct Scalar {
 
 class MatExpr;
 
-// CV_64F matrix with 1 or 2 channels, row-major with a byte step; headers share the buffer
+struct Size {
+    int width, height;
+    Size() : width(0), height(0) {}
+    Size(int w, int h) : width(w), height(h) {}
+};
+struct Point {
+    int x, y;
+    Point() : x(0), y(0) {}
+    Point(int x_, int y_) : x(x_), y(y_) {}
+};
+struct Vec3b {
+    uchar val[3];
+    uchar& operator[](int i) { return val[i]; }
+    const uchar& operator[](int i) const { return val[i]; }
+};
+
+// matrix of depth CV_8U / CV_32F / CV_64F with 1..3 channels, row-major with a byte step; headers share the
+// buffer.  The arithmetic (gemm, invert, MatExpr ...) is CV_64F only; the other depths exist for images and for
+// the f32 model matrices, i.e. create / at / copy / convertTo / blur / cvtColor.
 class Mat {
   public:
     int rows, cols;
     size_t step; // bytes between rows
     uchar* data;
-    Mat() : rows(0), cols(0), step(0), data(0), cn_(1) {}
-    Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(0), cn_(1) { create(r, c, type); }
-    Mat(const Mat& m) : rows(m.rows), cols(m.cols), step(m.step), data(m.data), cn_(m.cn_), buf_(m.buf_) {}
+    Mat() : rows(0), cols(0), step(0), data(0), cn_(1), depth_(CV_64F) {}
+    Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(0), cn_(1), depth_(CV_64F) { create(r, c, type); }
+    Mat(const Mat& m)
+        : rows(m.rows), cols(m.cols), step(m.step), data(m.data), cn_(m.cn_), depth_(m.depth_), buf_(m.buf_)
+    {
+    }
     Mat& operator=(const Mat& m)
     {
         rows = m.rows;
@@ -102,29 +132,36 @@ class Mat {
         step = m.step;
         data = m.data;
         cn_ = m.cn_;
+        depth_ = m.depth_;
         buf_ = m.buf_;
         return *this;
     }
+    static size_t depthBytes(int depth) { return depth == CV_8U ? 1 : (depth == CV_32F ? 4 : 8); }
+    size_t elemSize() const { return depthBytes(depth_) * cn_; }
+    int depth() const { return depth_; }
     Mat& operator=(const MatExpr& e);
 
     // Mat::create: keeps the current buffer when shape and type already match (this is what makes
     // `state = F*state + B` write through to every header sharing the buffer)
     void create(int r, int c, int type)
     {
-        const int cn = (type == CV_64FC2) ? 2 : 1;
-        cvshim_assert(type == CV_64F || type == CV_64FC2, "only CV_64F / CV_64FC2");
-        if (data && rows == r && cols == c && cn_ == cn) return;
+        const int cn = CV_MAT_CN(type), dp = CV_MAT_DEPTH(type);
+        cvshim_assert((dp == CV_8U || dp == CV_32F || dp == CV_64F) && cn >= 1 && cn <= 3, "unsupported Mat type");
+        if (data && rows == r && cols == c && cn_ == cn && depth_ == dp) return;
         rows = r;
         cols = c;
         cn_ = cn;
-        step = sizeof(double) * (size_t)c * cn;
-        buf_.reset(new double[(size_t)std::max(r * c * cn, 1)], std::default_delete<double[]>());
+        depth_ = dp;
+        step = elemSize() * (size_t)c;
+        const size_t bytes = std::max<size_t>(step * (size_t)r, 8);
+        buf_.reset(new double[(bytes + 7) / 8], std::default_delete<double[]>());
         data = (uchar*)buf_.get();
     }
-    int type() const { return cn_ == 2 ? CV_64FC2 : CV_64F; }
+    int type() const { return CV_MAKETYPE(depth_, cn_); }
     int channels() const { return cn_; }
     bool empty() const { return data == 0 || rows * cols == 0; }
-    bool isContinuous() const { return step == sizeof(double) * (size_t)cols * cn_ || rows <= 1; }
+    bool isContinuous() const { return step == elemSize() * (size_t)cols || rows <= 1; }
+    Size size() const { return Size(cols, rows); }
 
     static MatExpr zeros(int r, int c, int type);
     static MatExpr eye(int r, int c, int type);
@@ -181,7 +218,7 @@ class Mat {
     }
     void copyTo(const Mat& dst) const
     {
-        cvshim_assert(dst.rows == rows && dst.cols == cols && dst.cn_ == cn_, "copyTo fixed-size destination");
+        cvshim_assert(dst.rows == rows && dst.cols == cols && dst.cn_ == cn_ && dst.depth_ == depth_, "copyTo fixed-size destination");
         copy_elements(const_cast<Mat&>(dst));
     }
     void copyTo(std::vector<double>& v) const
@@ -190,14 +227,30 @@ class Mat {
         for (int r = 0; r < rows; r++)
             for (int c = 0; c < cols; c++) v[(size_t)r * cols + c] = el(r, c);
     }
-    void convertTo(Mat& dst, int /*rtype*/, double alpha = 1, double beta = 0) const
+    double getAs(int r, int i) const // i-th scalar of row r, any depth
+    {
+        const uchar* p = data + (size_t)r * step;
+        return depth_ == CV_8U ? (double)p[i] : (depth_ == CV_32F ? (double)((const float*)p)[i] : ((const double*)p)[i]);
+    }
+    // convertTo(dst, rtype, alpha, beta): dst = saturate_cast<rtype>(src*alpha + beta); rtype < 0 keeps the depth
+    void convertTo(Mat& dst, int rtype, double alpha = 1, double beta = 0) const
     {
         Mat src = *this; // keep the source header alive if dst aliases it
-        dst.create(rows, cols, type());
+        const int dd = rtype < 0 ? depth_ : CV_MAT_DEPTH(rtype);
+        dst.create(rows, cols, CV_MAKETYPE(dd, cn_));
         for (int r = 0; r < rows; r++) {
-            const double* s = src.ptr<double>(r);
-            double* d = dst.ptr<double>(r);
-            for (int c = 0; c < cols * cn_; c++) d[c] = s[c] * alpha + beta;
+            uchar* d = dst.data + (size_t)r * dst.step;
+            for (int c = 0; c < cols * cn_; c++) {
+                const double v = src.getAs(r, c) * alpha + beta;
+                if (dd == CV_64F)
+                    ((double*)d)[c] = v;
+                else if (dd == CV_32F)
+                    ((float*)d)[c] = (float)v;
+                else {
+                    const long iv = std::lrint(v); // cvRound
+                    d[c] = (uchar)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+                }
+            }
         }
     }
 
@@ -231,7 +284,7 @@ class Mat {
             c0 = 0;
         }
         cvshim_assert(len > 0, "diag out of range");
-        return view(r0, c0, len, 1, step + sizeof(double) * cn_);
+        return view(r0, c0, len, 1, step + elemSize());
     }
 
   private:
@@ -242,19 +295,20 @@ class Mat {
         m.cols = nc;
         m.step = st;
         m.cn_ = cn_;
+        m.depth_ = depth_;
         m.buf_ = buf_;
-        m.data = data + (size_t)r0 * step + (size_t)c0 * sizeof(double) * cn_;
+        m.data = data + (size_t)r0 * step + (size_t)c0 * elemSize();
         return m;
     }
     void copy_elements(Mat& dst) const
     {
         for (int r = 0; r < rows; r++) {
-            const double* s = ptr<double>(r);
-            double* d = dst.ptr<double>(r);
-            if (s != d) std::memmove(d, s, sizeof(double) * (size_t)cols * cn_);
+            const uchar* s = data + (size_t)r * step;
+            uchar* d = dst.data + (size_t)r * dst.step;
+            if (s != d) std::memmove(d, s, elemSize() * (size_t)cols);
         }
     }
-    int cn_;
+    int cn_, depth_;
     std::shared_ptr<double> buf_;
 };
 
@@ -280,6 +334,69 @@ Mat repeat(const Mat& src, int ny, int nx);
 void split(const Mat& src, std::vector<Mat>& mv);
 void vconcat(const Mat& a, const Mat& b, Mat& dst);
 void randn(Mat& dst, const Mat& mean, const Mat& stddev);
+void randu(const Mat& dst, double low, double high); // fills a (view of a) CV_64F matrix
+void hconcat(const Mat& a, const Mat& b, Mat& dst);
+// every array produced by randn / randu, in call order (the harness replays the reference's internal draws)
+std::vector<std::vector<double> >& cvshim_random_log();
+
+// imgproc subset used by PFTracker::getMeasurementProposal / callback (src/pfPose.cpp:213-214, 253, 357-367)
+enum { BORDER_DEFAULT = 4 };
+void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT);
+void cvtColor(const Mat& src, Mat& dst, int code);
+inline void circle(Mat&, Point, int, const Scalar&, int = 1, int = 8, int = 0) {}
+inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) {}
+
+// Mat_<T> with the comma initialiser of `(Mat_<double>(3,3) << a, b, ...)`
+template <class T>
+class Mat_ : public Mat {
+  public:
+    Mat_(int r, int c) : Mat(r, c, sizeof(T) == 8 ? CV_64F : (sizeof(T) == 4 ? CV_32F : CV_8U)) {}
+};
+template <class T>
+class MatCommaInitializer_ {
+  public:
+    MatCommaInitializer_(const Mat_<T>& m) : m_(m), i_(0) {}
+    template <class V>
+    MatCommaInitializer_<T>& operator,(V v)
+    {
+        put((T)v);
+        return *this;
+    }
+    void put(T v)
+    {
+        m_.template at<T>(i_ / m_.cols, i_ % m_.cols) = v;
+        i_++;
+    }
+    operator Mat() const { return m_; }
+    Mat_<T> m_;
+    int i_;
+};
+template <class T, class V>
+MatCommaInitializer_<T> operator<<(const Mat_<T>& m, V v)
+{
+    MatCommaInitializer_<T> ci(m);
+    ci.put((T)v);
+    return ci;
+}
+
+// cv::FileStorage reader for OpenCV-YAML-1.0 "!!opencv-matrix" nodes (src/pfPose.cpp:34-55)
+class FileNode {
+  public:
+    std::string text; // the node's block
+};
+void operator>>(const FileNode& n, Mat& m);
+class FileStorage {
+  public:
+    enum { READ = 0 };
+    FileStorage(const std::string& path, int flags);
+    FileNode operator[](const char* key) const;
+    void release() {}
+    bool isOpened() const { return !txt_.empty(); }
+
+  private:
+    std::string txt_;
+};
+
 Mat& operator*=(Mat& a, double s);
 inline Mat& operator*=(Mat&& a, double s) { return operator*=(static_cast<Mat&>(a), s); }
 

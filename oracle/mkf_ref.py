@@ -179,3 +179,86 @@ def bench_tracks(arrays, T, N, frames, per_slot=False, seed=0x5EED0002, jitter=1
                                   _p(a["pca_proj"]), _p(a["pca_mean"]), T, N, frames, int(per_slot), int(seed),
                                   int(jitter), threads, C.byref(used))
     return secs, used.value
+
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_i64p = C.POINTER(C.c_int64)
+
+
+def _bind_tracker(L):
+    if getattr(L, "_tracker_bound", False):
+        return
+    L.ref_tracker_create.restype = C.c_void_p
+    L.ref_tracker_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64]
+    L.ref_tracker_destroy.argtypes = [C.c_void_p]
+    L.ref_tracker_num_particles.argtypes = [C.c_void_p]
+    L.ref_random_log_get.argtypes = [C.c_int, _dp, C.c_int]
+    L.ref_tracker_callback.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _u32p, _i64p, C.c_int]
+    L.ref_tracker_outputs.argtypes = [_dp, _dp, _u8p, C.c_int, C.c_int]
+    L.ref_tracker_get_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    L.ref_tracker_pose.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    L._tracker_bound = True
+
+
+class RefTracker:
+    """the reference's PFTracker (src/pfPose.{h,cpp}) driven without ROS: one synthetic frame per call()"""
+
+    def __init__(self, model_dir, left_file, right_file, tick1, tick2):
+        L = lib()
+        _bind_tracker(L)
+        self.h = L.ref_tracker_create(os.fsencode(model_dir), os.fsencode("/" + left_file),
+                                      os.fsencode("/" + right_file), int(tick1), int(tick2))
+        self.N = L.ref_tracker_num_particles(self.h)
+
+    def callback(self, like, roi_xywh, ticks):
+        """like: (rows, cols) uint8 raw likelihood image; roi (x, y, w, h) or None (no face); ticks: 6 ints.
+        returns dict(cands=[hand][2, C], blurred=(rows, cols) uint8, joints2d (8,2), tf (10,3), n_tf)"""
+        L = lib()
+        like = np.ascontiguousarray(like, np.uint8)
+        rows, cols = like.shape
+        L.ref_random_log_clear()
+        has = roi_xywh is not None
+        r = np.zeros(4, np.uint32)
+        if has:
+            x, y, w, h = roi_xywh
+            r[:] = [x, y, h, w]  # message order: x_offset, y_offset, height, width
+        t = np.ascontiguousarray(ticks, np.int64)
+        L.ref_tracker_callback(self.h, like.ctypes.data_as(_u8p), rows, cols, int(has), r.ctypes.data_as(_u32p),
+                               t.ctypes.data_as(_i64p), len(t))
+        j2 = np.zeros((8, 2))
+        tf = np.zeros((10, 3))
+        prob = np.zeros((rows, cols), np.uint8)
+        ntf = L.ref_tracker_outputs(_p(j2), _p(tf), prob.ctypes.data_as(_u8p), rows, cols)
+        logs = []
+        for i in range(L.ref_random_log_count()):
+            n = L.ref_random_log_get(i, None, 0)
+            buf = np.zeros(n)
+            L.ref_random_log_get(i, _p(buf), n)
+            logs.append(buf)
+        cands = None
+        if len(logs) == 4:    # first frame after (re)acquiring the face: randu x1, x2, y1, y2
+            cands = [np.stack([logs[0], logs[2]]), np.stack([logs[1], logs[3]])]
+        elif len(logs) == 2:  # getSamples: interleaved (x, y) per arm
+            cands = [np.stack([logs[0][0::2], logs[0][1::2]]), np.stack([logs[1][0::2], logs[1][1::2]])]
+        return dict(cands=cands, blurred=prob, joints2d=j2, tf=tf, n_tf=ntf)
+
+    def get_state(self, arm, d=12):
+        x = np.zeros((self.N, d))
+        P = np.zeros((self.N, d, d))
+        lib().ref_tracker_get_state(self.h, arm, _p(x), _p(P))
+        return x, P
+
+    def pose(self, arm, D=22):
+        e = np.zeros(D)
+        p3 = np.zeros((3, 5))
+        lib().ref_tracker_pose(self.h, arm, _p(e), _p(p3))
+        return e, p3
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ref_tracker_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
