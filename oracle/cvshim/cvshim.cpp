@@ -359,6 +359,7 @@ void vconcat(const Mat& a, const Mat& b, Mat& dst)
 // cv::randn with a cn x cn "stddev" matrix: dst = mean + stddev * N(0, I) per element.  The Gaussian
 // source (Box-Muller on a cv::RNG) is NOT OpenCV's Ziggurat: distribution-equivalent only.
 static thread_local RNG g_the_rng(0x12345678ULL);
+void cvshim_seed_the_rng(uint64 seed) { g_the_rng = RNG(seed); } // cv::theRNG().state = seed
 void randn(Mat& dst, const Mat& mean, const Mat& stddev)
 {
     const int cn = dst.channels();

@@ -65,6 +65,7 @@ inline void cvshim_assert(bool ok, const char* what)
 // the test harness controls what cv::getTickCount() returns (queue of values, then a counter)
 int64 getTickCount();
 void cvshim_push_tick(int64 t);
+void cvshim_seed_the_rng(uint64_t seed); // state of the global generator behind randn / randu
 
 struct Range {
     int start, end;

@@ -54,6 +54,7 @@ void* ref_tracker_create(const char* pkg_path, const char* left_file, const char
 void ref_tracker_destroy(void* tr) { delete (PFTracker*)tr; }
 int ref_tracker_num_particles(void* tr) { return ((PFTracker*)tr)->numParticles; }
 
+void ref_set_rng_seed(uint64_t seed) { cv::cvshim_seed_the_rng(seed); }
 void ref_random_log_clear() { cv::cvshim_random_log().clear(); }
 int ref_random_log_count() { return (int)cv::cvshim_random_log().size(); }
 int ref_random_log_get(int i, double* out, int cap)

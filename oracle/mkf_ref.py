@@ -192,6 +192,7 @@ def _bind_tracker(L):
     L.ref_tracker_create.restype = C.c_void_p
     L.ref_tracker_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64]
     L.ref_tracker_destroy.argtypes = [C.c_void_p]
+    L.ref_set_rng_seed.argtypes = [C.c_uint64]
     L.ref_tracker_num_particles.argtypes = [C.c_void_p]
     L.ref_random_log_get.argtypes = [C.c_int, _dp, C.c_int]
     L.ref_tracker_callback.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _u32p, _i64p, C.c_int]
@@ -204,9 +205,10 @@ def _bind_tracker(L):
 class RefTracker:
     """the reference's PFTracker (src/pfPose.{h,cpp}) driven without ROS: one synthetic frame per call()"""
 
-    def __init__(self, model_dir, left_file, right_file, tick1, tick2):
+    def __init__(self, model_dir, left_file, right_file, tick1, tick2, rng_seed=0x12345678):
         L = lib()
         _bind_tracker(L)
+        L.ref_set_rng_seed(int(rng_seed))  # the generator behind the node's cv::randn / cv::randu draws
         self.h = L.ref_tracker_create(os.fsencode(model_dir), os.fsencode("/" + left_file),
                                       os.fsencode("/" + right_file), int(tick1), int(tick2))
         self.N = L.ref_tracker_num_particles(self.h)

@@ -86,3 +86,24 @@ def test_reference_node_frames_match_oracle(left_arm, right_arm):
         assert np.array_equal(out["joints2d"], j2)
         # sanity: the tracked hands sit on the likelihood blobs
         assert abs(poses[0][0] - (388 + 60 * np.sin(2 * np.pi * fr / 75))) < 60
+
+
+def test_config0_golden_trajectory_of_the_reference_node():
+    """the committed 300-frame trajectory of the reference node is reproduced bit for bit (first 30 frames)"""
+    import os
+    import sys
+    gold_path = os.path.join(os.path.dirname(__file__), "golden", "config0_reference_node.npz")
+    if not os.path.exists(gold_path):
+        pytest.skip("golden/config0_reference_node.npz missing")
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_reference_node as mg
+    gold = np.load(gold_path)
+    got = mg.run(frames=30)
+    assert np.array_equal(got["pose"], gold["pose"][:30])
+    assert np.array_equal(got["tf"], gold["tf"][:30]) and np.array_equal(got["joints2d"], gold["joints2d"][:30])
+    # the node tracks the synthetic hands: left hand follows the moving blob, right hand its mirror
+    fr = np.arange(300)
+    hx = 388 + 60 * np.sin(2 * np.pi * fr / 75)
+    hy = 250 + 70 * np.sin(2 * np.pi * fr / 50 + np.pi / 3)
+    err = np.hypot(gold["pose"][20:, 0, 0] - hx[20:], gold["pose"][20:, 0, 1] - hy[20:])
+    assert np.median(err) < 25.0
