@@ -2,11 +2,14 @@
 // mgb45/mkfbodytracker_pdaf.  TEST INFRASTRUCTURE ONLY (see mkf_oracle.h): the product
 // library never links or calls this file.
 //
-// PARITY UNPINNED: the reference ships no golden vectors / tests and its
-// arithmetic is OpenCV `core` (unpinned, 2.4-era API, not installed here).  The OpenCV
-// primitives used by the reference are restated below from the published OpenCV 2.4.x
-// algorithms (GEMMSingleMul operation order, LUImpl, CholImpl, cv::RNG); that restatement
-// is from memory of the OpenCV sources and only influences results at O(1e-16) relative.
+// PINNING.  The reference ships no golden vectors / tests, so the anchor is the reference
+// ITSELF run here: oracle/_ref/libref.so is the reference's own src/{KF_model,my_gmm,pf2DRao,pfPose}.cpp compiled
+// in place (oracle/Makefile) against oracle/cvshim, and tests/test_ref_sources.py + tests/test_ref_tracker.py
+// require this file to agree with it BIT FOR BIT (filter states, weights, indices, poses) through whole frames of
+// the node.  What remains unpinned is the third-party arithmetic under both: OpenCV `core` (unpinned, 2.4-era API,
+// not installed here) is restated -- here and in cvshim -- from the published OpenCV 2.4.x algorithms
+// (GEMMSingleMul operation order, LUImpl, CholImpl, cv::RNG), from memory of the OpenCV sources; that restatement
+// only influences results at O(1e-16) relative and is cross-checked against OpenCV-python 4.13 where exported.
 //
 // Everything is IEEE double evaluated in the order the reference's cv::MatExpr tree evaluates
 // it; build with -ffp-contract=off so that no multiply-add is fused.

@@ -3,13 +3,14 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (libmkf_b200.so) never links or calls it.
  *
- * PARITY UNPINNED: mgb45/mkfbodytracker_pdaf ships no tests, golden vectors or recorded
- * outputs, and its arithmetic lives in OpenCV `core` (version not
- * pinned by the reference; 2.4-era API), which is not installed here.  The restatement is
- * cross-checked instead against (i) an independent numpy restatement, (ii) analytic
- * known-answer tests, (iii) OpenCV-python 4.13 primitives (gemm / invert(DECOMP_LU) /
- * FileStorage), (iv) the reference's own .cpp files compiled against oracle/cvshim
- * (oracle/_ref, see oracle/Makefile).
+ * PINNING: mgb45/mkfbodytracker_pdaf ships no tests, golden vectors or recorded outputs (SURVEY.md
+ * section 4).  The restatement is pinned against the reference itself run here -- oracle/_ref: the
+ * reference's own .cpp files compiled in place against oracle/cvshim (oracle/Makefile), bit-exact
+ * agreement required by tests/test_ref_sources.py and tests/test_ref_tracker.py -- and cross-checked
+ * against an independent numpy restatement, analytic known-answer tests and OpenCV-python 4.13
+ * primitives (gemm / invert(DECOMP_LU) / FileStorage).  Unpinned: the OpenCV `core` arithmetic
+ * underneath (version not pinned by the reference, not installed here), restated from the published
+ * 2.4.x algorithms.
  */
 #ifndef MKF_ORACLE_H
 #define MKF_ORACLE_H
