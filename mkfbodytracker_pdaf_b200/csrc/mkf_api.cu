@@ -337,8 +337,18 @@ static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, co
         k_resample_small<<<grid_for(nt, 128), 128, 0, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
                                                                  d_status, 1, need_fb, bit_deg);
     } else {
-        k_resample_block<128, 4><<<(unsigned)nt, 128, 0, stream>>>(d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out,
-                                                                    d_status, 1, need_fb, bit_fb, bit_deg);
+        // one CTA per track; wider CTAs for long weight / index vectors so a track's tiles are few
+        const int span = L > N ? L : N;
+#define MKF_RS_BLOCK(BT)                                                                                            \
+    k_resample_block<BT, 4><<<(unsigned)nt, BT, 0, stream>>>(d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out,    \
+                                                              d_status, 1, need_fb, bit_fb, bit_deg)
+        if (span <= 1024)
+            MKF_RS_BLOCK(128);
+        else if (span <= 8192)
+            MKF_RS_BLOCK(512);
+        else
+            MKF_RS_BLOCK(1024);
+#undef MKF_RS_BLOCK
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
@@ -496,6 +506,36 @@ extern "C" int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layou
     return update_device(b, d_meas, meas_layout, d_ui, d_up, 1, d_seeds, 2, 1);
 }
 
+// getEstimator + reconstruction of every track of the batch (device pointers; either output may be null)
+template <int DD>
+static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
+{
+    const mkf_model* m = b->m;
+    const double2* st = b->st[b->cur];
+    if (b->N <= 16)
+        k_estimate_small<DD, 16><<<grid_for(b->T, 128 / 16), 128, 0, b->stream>>>(
+            st, b->parent, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose);
+    else if (b->N <= 96)
+        k_estimate_small<DD, 32><<<grid_for(b->T, 128 / 32), 128, 0, b->stream>>>(
+            st, b->parent, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose);
+    else if (b->N <= 2048)
+        k_estimate<DD, 128><<<(unsigned)b->T, 128, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
+                                                                   b->d_tinv, d_xbar, d_pose);
+    else // long tracks: more loads in flight per track (BT = 512 is slower at N = 500: 64 vs 41 us at 4096 tracks)
+        k_estimate<DD, 512><<<(unsigned)b->T, 512, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
+                                                                   b->d_tinv, d_xbar, d_pose);
+}
+static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
+{
+    if (b->m->d == 12)
+        launch_estimate_d<12>(b, d_xbar, d_pose);
+    else
+        launch_estimate_d<10>(b, d_xbar, d_pose);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    return MKF_OK;
+}
+
 extern "C" int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int mem)
 {
     if (!b) {
@@ -508,33 +548,7 @@ extern "C" int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int 
     int rc;
     if ((rc = ox.init(b, xbar, (size_t)b->T * m->d, mem, b->out_a))) return rc;
     if ((rc = op.init(b, pose, (size_t)b->T * m->D, mem, b->out_b))) return rc;
-    const double2* st = b->st[b->cur];
-#define LAUNCH_EST(DD, BT)                                                                                   \
-    k_estimate<DD, BT><<<(unsigned)b->T, BT, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean, \
-                                                              b->d_tinv, ox.devp, op.devp)
-#define LAUNCH_EST_SMALL(DD, G)                                                                              \
-    k_estimate_small<DD, G><<<grid_for(b->T, 128 / G), 128, 0, b->stream>>>(st, b->parent, b->T, b->N, m->D,  \
-                                                                             b->d_recon, b->d_pmean, b->d_tinv, \
-                                                                             ox.devp, op.devp)
-    if (m->d == 12) {
-        if (b->N <= 16)
-            LAUNCH_EST_SMALL(12, 16);
-        else if (b->N <= 96)
-            LAUNCH_EST_SMALL(12, 32);
-        else
-            LAUNCH_EST(12, 128);
-    } else {
-        if (b->N <= 16)
-            LAUNCH_EST_SMALL(10, 16);
-        else if (b->N <= 96)
-            LAUNCH_EST_SMALL(10, 32);
-        else
-            LAUNCH_EST(10, 128);
-    }
-#undef LAUNCH_EST_SMALL
-#undef LAUNCH_EST
-    MKF_LAUNCHED();
-    CK(cudaGetLastError());
+    if ((rc = launch_estimate(b, ox.devp, op.devp))) return rc;
     if ((rc = ox.finish(b)) || (rc = op.finish(b))) return rc;
     if ((ox.host || op.host) && mem != MKF_MEM_HOST_ASYNC) CK(cudaStreamSynchronize(b->stream));
     return MKF_OK;
@@ -686,14 +700,10 @@ extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t se
     }
     if (!rc) {
         // the reference applies resample() to already-normalised weights: no division here
-        if (L <= 64 && N <= 64)
-            k_resample_small<<<1, 32>>>(d_w, 1, L, N, d_u, 1, 0, d_ws, d_out, d_st, 1, d_fb, MKF_ST_POST_DEGENERATE);
-        else
-            k_resample_block<128, 4><<<1, 128>>>(d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, 1, d_fb,
-                                                 MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE);
-        MKF_LAUNCHED();
-        k_resample_fallback<<<1, 32>>>(d_w, 1, L, N, d_u, 1, 0, d_ws, d_out, d_seed, 1, 0, d_fb, nullptr);
-        MKF_LAUNCHED();
+        rc = run_resample(0, 1, d_fb, d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, d_seed, 1, 0, MKF_ST_POST_FALLBACK,
+                          MKF_ST_POST_DEGENERATE);
+    }
+    if (!rc) {
         e = cudaMemcpy(out, d_out, (size_t)N * 4, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {
             mkf_set_error("mkf_resample: %s", cudaGetErrorString(e));

@@ -123,38 +123,7 @@ __global__ void k_assoc_meas(const double* __restrict__ cand_xy, const double* _
     }
 }
 
-static int estimate_pose_device(mkf_batch* b, double* d_pose)
-{
-    const mkf_model* m = b->m;
-    const double2* st = b->st[b->cur];
-#define LAUNCH_EST(DD, BT)                                                                                   \
-    k_estimate<DD, BT><<<(unsigned)b->T, BT, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean, \
-                                                              b->d_tinv, nullptr, d_pose)
-#define LAUNCH_EST_SMALL(DD, G)                                                                              \
-    k_estimate_small<DD, G><<<grid_for(b->T, 128 / G), 128, 0, b->stream>>>(st, b->parent, b->T, b->N, m->D,  \
-                                                                             b->d_recon, b->d_pmean, b->d_tinv, \
-                                                                             nullptr, d_pose)
-    if (m->d == 12) {
-        if (b->N <= 16)
-            LAUNCH_EST_SMALL(12, 16);
-        else if (b->N <= 96)
-            LAUNCH_EST_SMALL(12, 32);
-        else
-            LAUNCH_EST(12, 128);
-    } else {
-        if (b->N <= 16)
-            LAUNCH_EST_SMALL(10, 16);
-        else if (b->N <= 96)
-            LAUNCH_EST_SMALL(10, 32);
-        else
-            LAUNCH_EST(10, 128);
-    }
-#undef LAUNCH_EST_SMALL
-#undef LAUNCH_EST
-    MKF_LAUNCHED();
-    CK(cudaGetLastError());
-    return MKF_OK;
-}
+static int estimate_pose_device(mkf_batch* b, double* d_pose) { return launch_estimate(b, nullptr, d_pose); }
 
 extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const double* cand_xy, const uint8_t* cand_L,
                                    const double* roi, const double* u_cand, const double* u_ind, const double* u_post,

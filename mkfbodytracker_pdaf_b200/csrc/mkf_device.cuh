@@ -42,6 +42,16 @@ __device__ __forceinline__ dd dd_add_d(dd a, double b)
     return dd_fast_two_sum(s.hi, s.lo);
 }
 
+__device__ __forceinline__ dd dd_add(dd a, dd b) // accurate variant: error <= 2 * 2^-106 relative
+{
+    dd s = dd_two_sum(a.hi, b.hi);
+    const dd t = dd_two_sum(a.lo, b.lo);
+    s.lo = __dadd_rn(s.lo, t.hi);
+    s = dd_fast_two_sum(s.hi, s.lo);
+    s.lo = __dadd_rn(s.lo, t.lo);
+    return dd_fast_two_sum(s.hi, s.lo);
+}
+
 // ---------------------------------------------------------------------------------------------
 // exact systematic resampling count (src/pf2DRao.cpp:195-207 in closed form)
 //
@@ -85,6 +95,21 @@ __device__ __forceinline__ double mkf_resample_tol(int N, int L, double wmax, do
     return 1.0625 * 1.1102230246251565e-16 * (double)(N + L) * (wmax + step);
 }
 
+// A second bound on the same error, tighter when the weights are peaked.  beta never leaves [0, w_idx + step]: a
+// subtraction happens only while beta > w_idx (result in (0, beta)), an addition only once beta <= w_idx.  So the
+// result of the addition that emits output i is <= w_parent(i) + step and the result of the subtraction that leaves
+// weight k is <= w_{k-1} + step; each is rounded with relative error 2^-53 and the errors add.  Parent k emits
+// c_k <= N w_k + 2 outputs, hence
+//     sum over additions    <= sum_k c_k w_k + N step <= N * S2 + 2 * mass + 1        (S2 = sum_k w_k^2)
+//     sum over subtractions <= mass + L step           =  mass + L / N                 (no wrap; wraps are flagged)
+// and the accumulated error is <= 2^-53 (N S2 + 3 mass + 1 + L/N).  For uniform weights this equals the bound above;
+// at N = 65 536 with a few thousand effective parents it is ~50x smaller (the first bound charges w_max to every
+// operation).  s2 must be an upper bound of S2 (callers inflate the computed sum).
+__device__ __forceinline__ double mkf_resample_tol_s2(int N, int L, double s2, double mass)
+{
+    return 1.0625 * 1.1102230246251565e-16 * ((double)N * s2 + 4.0 * mass + 4.0 + (double)L / (double)N);
+}
+
 // cv::RNG (multiply-with-carry) as used by the degenerate fallback (src/pf2DRao.cpp:179-192)
 struct mkf_cvrng {
     uint64_t state;
@@ -118,6 +143,42 @@ __device__ __forceinline__ void mkf_resample_sequential(WF w, int L, int N, doub
         }
         beta = __dadd_rn(beta, step);
         out[i] = idx;
+    }
+}
+
+// The same loop run by a whole warp for one track: the lanes stage the (normalised) weights through shared memory
+// CH at a time, lane 0 walks them.  The arithmetic and its order are those of mkf_resample_sequential; only the
+// latency of the dependent weight loads changes (a flagged 65 536-slot track took 43 ms with one thread reading
+// global memory).  `chunk` holds CH doubles private to the warp.
+template <int CH, class WF>
+__device__ __forceinline__ void mkf_resample_sequential_warp(WF w, int L, int N, double u, int32_t* out, double* chunk)
+{
+    const int lane = threadIdx.x & 31;
+    const double step = __ddiv_rn(1.0, (double)N);
+    double beta = __dmul_rn(u, step);
+    int idx = 0, i = 0, base = 0;
+    for (;;) {
+        for (int q = lane; q < CH; q += 32) chunk[q] = (base + q < L) ? w(base + q) : 0.0;
+        __syncwarp();
+        if (lane == 0) {
+            double wi = chunk[idx - base];
+            while (i < N) {
+                if (beta > wi) {
+                    beta = __dsub_rn(beta, wi);
+                    idx = (idx + 1 == L) ? 0 : idx + 1;
+                    if (idx < base || idx >= base + CH) break; // next weight lives in another chunk
+                    wi = chunk[idx - base];
+                } else {
+                    beta = __dadd_rn(beta, step);
+                    out[i++] = idx;
+                }
+            }
+        }
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= N) break;
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        base = idx / CH * CH;
+        __syncwarp();
     }
 }
 
@@ -159,10 +220,13 @@ __device__ __forceinline__ void mkf_mbar_wait(uint64_t* bar, uint32_t phase)
 // ---------------------------------------------------------------------------------------------
 // warp / block collectives
 // ---------------------------------------------------------------------------------------------
-// block-wide exclusive scan of one double per thread (plain IEEE adds); also returns the block total
+// block-wide exclusive scan of one double per thread (plain IEEE adds); also returns the block total.
+// Rounding depth on the way to any prefix: 5 (warp scan) + BT/32 - 1 (<= 3 warp totals, BT <= 128) or + 5 (warp
+// totals scanned by shuffles, BT > 128) + 1, i.e. <= 11 for every BT -- k_resample_block's tolerance relies on it.
 template <int BT>
 __device__ __forceinline__ double mkf_block_excl_scan_d(double v, double* scratch, double& total)
 {
+    constexpr int NW = BT / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double inc = v;
 #pragma unroll
@@ -173,17 +237,69 @@ __device__ __forceinline__ double mkf_block_excl_scan_d(double v, double* scratc
     if (lane == 31) scratch[wid] = inc;
     __syncthreads();
     double pre = 0.0, tot = 0.0;
+    if constexpr (NW <= 4) {
 #pragma unroll
-    for (int w = 0; w < BT / 32; w++) {
-        const double s = scratch[w];
-        if (w < wid) pre += s;
-        tot += s;
+        for (int w = 0; w < NW; w++) {
+            const double s = scratch[w];
+            if (w < wid) pre += s;
+            tot += s;
+        }
+        __syncthreads();
+    } else {
+        if (wid == 0) {
+            double s = lane < NW ? scratch[lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double n = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += n;
+            }
+            if (lane < NW) scratch[lane] = s; // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        pre = wid > 0 ? scratch[wid - 1] : 0.0;
+        tot = scratch[NW - 1];
+        __syncthreads();
     }
-    __syncthreads();
     total = tot;
     double prev = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) prev = 0.0;
     return pre + prev;
+}
+
+// block-wide exclusive scan in double-double (the rare second-opinion pass of k_resample_block)
+template <int BT>
+__device__ __forceinline__ dd mkf_block_excl_scan_dd(dd v, double* scratch_hi, double* scratch_lo, dd& total)
+{
+    constexpr int NW = BT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    dd inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        dd n;
+        n.hi = __shfl_up_sync(0xffffffffu, inc.hi, o);
+        n.lo = __shfl_up_sync(0xffffffffu, inc.lo, o);
+        if (lane >= o) inc = dd_add(n, inc);
+    }
+    if (lane == 31) {
+        scratch_hi[wid] = inc.hi;
+        scratch_lo[wid] = inc.lo;
+    }
+    __syncthreads();
+    dd pre = dd_make(0.0), tot = dd_make(0.0);
+    for (int w = 0; w < NW; w++) {
+        dd sw;
+        sw.hi = scratch_hi[w];
+        sw.lo = scratch_lo[w];
+        if (w < wid) pre = dd_add(pre, sw);
+        tot = dd_add(tot, sw);
+    }
+    __syncthreads();
+    total = tot;
+    dd prev;
+    prev.hi = __shfl_up_sync(0xffffffffu, inc.hi, 1);
+    prev.lo = __shfl_up_sync(0xffffffffu, inc.lo, 1);
+    if (lane == 0) prev = dd_make(0.0);
+    return dd_add(pre, prev);
 }
 
 // block-wide exclusive max-scan of one int per thread (identity -1); returns block max in total

@@ -583,12 +583,52 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
     atomicOr(status + t, st);
 }
 
+// the prefix-sum / head-marker pass of k_resample_block carried in double-double throughout; kept out of line so that
+// its registers do not weigh on the common path.  Returns this thread's ambiguity flag.
+template <int BT, int ITEMS>
+__device__ __noinline__ bool mkf_resample_precise_pass(const double* __restrict__ w, int L, int N, int normalise,
+                                                       double wsum, double beta0, double step, double tol2,
+                                                       int32_t* __restrict__ out, double* sc_d, double* sc_d2)
+{
+    const int tid = threadIdx.x;
+    dd carry2 = dd_make(0.0);
+    bool amb2 = false;
+    for (int base = 0; base < L; base += BT * ITEMS) {
+        const int i0 = base + tid * ITEMS;
+        dd pre[ITEMS];
+        dd run = dd_make(0.0);
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) {
+            double x = (i0 + q < L) ? w[i0 + q] : 0.0;
+            if (normalise) x = __ddiv_rn(x, wsum);
+            run = dd_add_d(run, x);
+            pre[q] = run;
+        }
+        dd tile_tot;
+        const dd excl = mkf_block_excl_scan_dd<BT>(run, sc_d, sc_d2, tile_tot);
+        const dd start = dd_add(carry2, excl);
+        int e_prev = 0;
+        if (i0 > 0 && i0 < L) e_prev = mkf_count_le(start, beta0, step, N, tol2, amb2);
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) {
+            if (i0 + q < L) {
+                const int e = mkf_count_le(dd_add(start, pre[q]), beta0, step, N, tol2, amb2);
+                if (e > e_prev) out[e_prev] = i0 + q;
+                if (i0 + q == L - 1 && e < N) amb2 = true;
+                e_prev = e;
+            }
+        }
+        carry2 = dd_add(carry2, tile_tot);
+    }
+    return amb2;
+}
+
 // -----------------------------------------------------------------------------------------
 // per-track weight normalisation + systematic resampling, one CTA per track
 //   w_raw : T x L raw weights; out: T x N parents; wsum: T
 // -----------------------------------------------------------------------------------------
 template <int BT, int ITEMS>
-__global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict__ w_all, int L, int N,
+__global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* __restrict__ w_all, int L, int N,
                                                         const double* __restrict__ u, int u_stride, int normalise,
                                                         double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
                                                         uint32_t* __restrict__ status, int status_stride,
@@ -596,7 +636,7 @@ __global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict_
                                                         uint32_t bit_deg)
 {
     __shared__ int sc_i[BT / 32];
-    __shared__ double sc_d[BT / 32], sc_d2[BT / 32];
+    __shared__ double sc_d[BT / 32], sc_d2[BT / 32], sc_d3[BT / 32];
     __shared__ int sh_flag;
     const long long t = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -606,29 +646,34 @@ __global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict_
     // pass 1: sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172).  The sum only has to be an accurate
     // normaliser (the reference's own sequential sum is no more exact); the stored value is reused by
     // k_resample_fallback so both paths normalise identically.
-    double acc = 0.0, mx = 0.0;
+    double acc = 0.0, mx = 0.0, sq = 0.0;
     for (int i = tid; i < L; i += BT) {
         const double x = w[i];
         acc += x;
+        sq = fma(x, x, sq);
         if (x > mx) mx = x;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     if (lane == 0) {
         sc_d[wid] = acc;
         sc_d2[wid] = mx;
+        sc_d3[wid] = sq;
     }
     if (tid == 0) sh_flag = 0;
     __syncthreads();
     acc = 0.0;
     mx = 0.0;
+    sq = 0.0;
 #pragma unroll
     for (int q = 0; q < BT / 32; q++) {
         acc += sc_d[q];
         mx = fmax(mx, sc_d2[q]);
+        sq += sc_d3[q];
     }
     __syncthreads();
     const double wsum = normalise ? acc : 1.0;
@@ -644,10 +689,15 @@ __global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict_
     const double step = __ddiv_rn(1.0, (double)N);
     const double beta0 = __dmul_rn(u[t * u_stride], step);
     // ambiguity band: rounding the sequential loop may have accumulated (mkf_resample_tol) plus the error of the
-    // prefix sums below -- at most 13 roundings on the way to any C_k, each <= 2^-53 x (a partial sum <= S):
-    // bounded by 16 * 2^-53 * S with S the total mass (1 after normalisation)
+    // prefix sums below -- at most ITEMS - 1 + 11 (mkf_block_excl_scan_d) <= 14 roundings on the way to any C_k,
+    // each <= 2^-53 x (a partial sum <= S): bounded by 16 * 2^-53 * S with S the total mass (1 after normalisation)
+    static_assert(ITEMS <= 5, "prefix-sum rounding depth exceeds the 16-ulp tolerance term");
     const double mass = normalise ? 1.0 : acc;
-    const double tol = mkf_resample_tol(N, L, wmax_n, step) + 16.0 * 1.1102230246251565e-16 * (1.0 + mass);
+    // sum of squared (normalised) weights, inflated so that it is an upper bound whatever the summation order; a
+    // non-finite value drops out of the fmin and leaves the first bound
+    const double s2 = (normalise ? __ddiv_rn(sq, __dmul_rn(wsum, wsum)) : sq) * (1.0 + 1e-9);
+    const double tol_loop = fmin(mkf_resample_tol(N, L, wmax_n, step), mkf_resample_tol_s2(N, L, s2, mass));
+    const double tol = tol_loop + 16.0 * 1.1102230246251565e-16 * (1.0 + mass);
 
     for (int i = tid; i < N; i += BT) out[i] = -1;
     __syncthreads();
@@ -686,11 +736,25 @@ __global__ void __launch_bounds__(BT) k_resample_block(const double* __restrict_
     if (amb) sh_flag = 1;
     __syncthreads();
     if (sh_flag) {
-        if (tid == 0) {
-            need_fb[t] = 1u;
-            atomicOr(status + t * status_stride, bit_fb);
+        // second opinion before giving the track to the literal loop: the same pass with the prefix sums carried in
+        // double-double throughout (error ~1e-30), so only the loop's own rounding bound (plus the rounding of
+        // mkf_count_le's remainder, <= 2 ulp of step) remains in the band -- 8x narrower at N = 65 536, where one
+        // literal re-run costs milliseconds.
+        __syncthreads();
+        if (tid == 0) sh_flag = 0;
+        for (int i = tid; i < N; i += BT) out[i] = -1;
+        __syncthreads();
+        const double tol2 = tol_loop + 8.0 * 1.1102230246251565e-16 * step + 8.0e-28 * (1.0 + mass);
+        const bool amb2 = mkf_resample_precise_pass<BT, ITEMS>(w, L, N, normalise, wsum, beta0, step, tol2, out, sc_d, sc_d2);
+        if (amb2) sh_flag = 1;
+        __syncthreads();
+        if (sh_flag) {
+            if (tid == 0) {
+                need_fb[t] = 1u;
+                atomicOr(status + t * status_stride, bit_fb);
+            }
+            return;
         }
-        return;
     }
     // fill: inclusive max-scan of the head markers
     int carry_max = -1;
@@ -744,42 +808,60 @@ __global__ void k_resample_small(const double* __restrict__ w_all, long long T, 
 }
 
 // flagged tracks: literal loop on the same normalised weights, or the cv::RNG random-index
-// fallback when the maximum weight is 0 / NaN.  One thread per track.
-__global__ void k_resample_fallback(const double* __restrict__ w_all, long long T, int L, int N,
-                                    const double* __restrict__ u, int u_stride, int normalise,
-                                    const double* __restrict__ wsum_in, int32_t* __restrict__ out_all,
-                                    const uint64_t* __restrict__ seeds, int seed_stride, int seed_off,
-                                    uint32_t* __restrict__ need_fb, uint32_t* __restrict__ unsorted)
+// fallback when the maximum weight is 0 / NaN.  One thread per track looks at the flag; a flagged track is then
+// worked on by the whole warp (weights staged through shared memory, lane 0 walking them).
+__global__ void __launch_bounds__(128) k_resample_fallback(const double* __restrict__ w_all, long long T, int L, int N,
+                                                            const double* __restrict__ u, int u_stride, int normalise,
+                                                            const double* __restrict__ wsum_in,
+                                                            int32_t* __restrict__ out_all,
+                                                            const uint64_t* __restrict__ seeds, int seed_stride,
+                                                            int seed_off, uint32_t* __restrict__ need_fb,
+                                                            uint32_t* __restrict__ unsorted)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    if (unsorted) unsorted[t] = 0u;
-    if (!need_fb[t]) return;
-    need_fb[t] = 0u;
-    const double* __restrict__ w = w_all + t * L;
-    int32_t* out = out_all + t * N;
-    const double wsum = normalise ? wsum_in[t] : 1.0;
-    double mw = 0.0;
-    for (int i = 0; i < L; i++) {
-        const double x = normalise ? __ddiv_rn(w[i], wsum) : w[i];
-        if (x > mw) mw = x;
+    constexpr int CH = 512;
+    __shared__ double chunk[4][CH];
+    const long long t0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bool flagged = false;
+    if (t0 + lane < T) {
+        if (unsorted) unsorted[t0 + lane] = 0u;
+        flagged = need_fb[t0 + lane] != 0u;
+        if (flagged) need_fb[t0 + lane] = 0u;
     }
-    if (!(mw > 0.0)) {
-        mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
-        (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
-        for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
-        if (unsorted) unsorted[t] = 1u; // random indices are not sorted (matters for the literal alias mode)
-        return;
+    unsigned todo = __ballot_sync(0xffffffffu, flagged);
+    while (todo) {
+        const long long t = t0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const double* __restrict__ w = w_all + t * L;
+        int32_t* out = out_all + t * N;
+        const double wsum = normalise ? wsum_in[t] : 1.0;
+        auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
+        double mw = 0.0; // NaN-ignoring maximum, as maxWeight (src/pf2DRao.cpp:161-172)
+        for (int i = lane; i < L; i += 32) {
+            const double x = wf(i);
+            if (x > mw) mw = x;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mw = fmax(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+        if (!(mw > 0.0)) {
+            if (lane == 0) {
+                mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
+                (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
+                for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
+                if (unsorted) unsorted[t] = 1u; // random indices are not sorted (matters for the literal alias mode)
+            }
+        } else {
+            mkf_resample_sequential_warp<CH>(wf, L, N, u[t * u_stride], out, chunk[wid]);
+        }
+        __syncwarp();
     }
-    auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
-    mkf_resample_sequential(wf, L, N, u[t * u_stride], out);
 }
 
 // -----------------------------------------------------------------------------------------
 // getEstimator + reconstruction: one CTA per track
 // -----------------------------------------------------------------------------------------
 template <int D, int BT>
-__global__ void __launch_bounds__(BT) k_estimate(const double2* __restrict__ st, const int32_t* __restrict__ parent,
+__global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __restrict__ st, const int32_t* __restrict__ parent,
                                                   int N, int Dpose, const double* __restrict__ recon,
                                                   const double* __restrict__ pmean, const double* __restrict__ tinv,
                                                   double* __restrict__ xbar_out, double* __restrict__ pose_out)

@@ -98,6 +98,55 @@ def test_association_no_candidate_passes_gate(left_arm, right_arm):
     assert not (st1[1] & L.ST_CAND_DEGENERATE)
 
 
+@pytest.mark.parametrize("N,Cn", [(500, 5000), (64, 640)])
+def test_association_tied_candidate_weights_inside_a_batch(left_arm, right_arm, N, Cn):
+    """persons whose candidates are all identical (equal weights) with u = 0 put every threshold on a prefix sum: their
+    C -> N candidate resample must leave the closed form (status CAND_FALLBACK) inside a batch of ordinary persons and
+    reproduce the literal loop bit for bit"""
+    torch = pytest.importorskip("torch")
+    seed, T = 0x5EED0003, 37
+    tied = [1, 4, 33, 36]
+    tracks = list(range(T))
+    u0 = synth_u_init(seed, tracks)
+    fl = [orc.Filter(left_arm.orc, N) for _ in tracks]
+    fr_ = [orc.Filter(right_arm.orc, N) for _ in tracks]
+    for t in tracks:
+        fl[t].reset(u=u0[t])
+        fr_[t].reset(u=u0[t])
+    s = torch.cuda.Stream()
+    b0 = mk.TrackBatch(left_arm.mk, T, N, stream=s.cuda_stream)
+    b1 = mk.TrackBatch(right_arm.mk, T, N, stream=s.cuda_stream)
+    b0.reset(u0)
+    b1.reset(u0)
+    roi = np.tile(np.array([300.0, 51.0, 47.0, 47.0]), (T, 1))
+    rng = np.random.default_rng(11)
+    cand = rng.uniform(40, 400, (T, 2, 2, Cn))
+    Lv = rng.integers(1, 255, (T, 2, Cn)).astype(np.uint8)
+    u_cand = rng.random((T, 2))
+    for t in tied:
+        cand[t] = cand[t, :, :, :1]
+        Lv[t] = 128
+        u_cand[t] = 0.0
+    mk.associate(b0, b1, cand, Lv, roi, u_cand, None, None, do_update=False)
+    res = mk.assoc_results(b0, Cn)
+    for t in tracks:
+        want = orc.associate(fl[t], fr_[t], cand[t], Lv[t], roi[t], u_cand[t])
+        assert np.array_equal(res["gate"][t], want["gate"])
+        assert rel_err_weights(res["weights"][t], want["weights"]) <= RTOL
+        if t in tied:
+            # with every threshold sitting on a prefix sum the outcome hinges on the last bit of the weights, and the
+            # device's weight sum is a tree sum (the oracle's is sequential): the contract that can hold here is the
+            # literal loop applied to the weights the device itself produced
+            for h in range(2):
+                lit, _ = orc.resample(res["weights"][t, h], N, 0.0)
+                assert np.array_equal(res["bins"][t, h], lit), f"person {t} hand {h}"
+        else:
+            assert np.array_equal(res["bins"][t], want["bins"]), f"person {t}"
+    st = b0.status() | b1.status()
+    assert (st[tied] & L.ST_CAND_FALLBACK).all(), "tied persons were expected to take the literal loop"
+    assert not (st[[t for t in tracks if t not in tied]] & L.ST_CAND_FALLBACK).any()
+
+
 def spd(rng, n, scale):
     a = rng.standard_normal((n, n))
     return scale * (a @ a.T + n * np.eye(n))

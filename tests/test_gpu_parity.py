@@ -249,6 +249,39 @@ def test_resample_random_weights_bit_exact(rng, L_, N):
         assert np.array_equal(out, want), f"L={L_} N={N} trial={trial}: {(out != want).sum()} mismatches"
 
 
+@pytest.mark.parametrize("L_,N", [(500, 500), (4096, 4096), (65536, 65536), (5000, 500), (700, 1536), (64, 640)])
+def test_resample_ties_take_the_literal_path_bit_exact(rng, L_, N):
+    """thresholds that coincide with prefix sums (dyadic weights, u = 0 or a dyadic u) cannot be decided by the
+    closed form: the track goes through the double-double second opinion and then the warp-run literal loop"""
+    cases = []
+    cases.append((np.full(L_, 1.0 / L_), 0.0))                       # every C_k is a threshold when N | L or L | N
+    w = np.zeros(L_)
+    w[:: max(1, L_ // 64)] = 1.0
+    cases.append((w / w.sum(), 0.0))
+    w = rng.integers(0, 8, L_).astype(np.float64)                     # small integers / power-of-two total: exact sums
+    w[0] += 2.0 ** np.ceil(np.log2(w.sum() + 1)) - w.sum()
+    cases.append((w / w.sum(), 0.5))
+    cases.append((w / w.sum(), 0.0))
+    for w, u in cases:
+        out, deg = mk.resample(w, N, u)
+        want, wdeg = orc.resample(w, N, u)
+        assert deg == wdeg == 0
+        assert np.array_equal(out, want), f"L={L_} N={N} u={u}: {(out != want).sum()} mismatches"
+
+
+def test_resample_degenerate_and_tied_weight_vectors(rng):
+    """uniform / comb / zero / NaN weight vectors at N = 1024 (block kernel): ties go to the literal loop, zero and
+    NaN maxima to the cv::RNG branch"""
+    N = 1024
+    comb = np.zeros(N)
+    comb[::16] = 1.0 / 64
+    for w, u in ((np.full(N, 1.0 / N), 0.0), (comb, 0.0), (np.zeros(N), 0.3), (np.full(N, np.nan), 0.3)):
+        seed = int(rng.integers(1, 2**62))
+        out, deg = mk.resample(w, N, u, seed=seed)
+        want, wdeg = orc.resample(w, N, u, seed=seed)
+        assert deg == wdeg and np.array_equal(out, want)
+
+
 def test_full_size_properties_config2(left_arm):
     """config 2 at BASELINE size (4096 x 500): size-independent properties instead of the oracle"""
     torch = pytest.importorskip("torch")
