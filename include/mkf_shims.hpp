@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -140,7 +141,35 @@ inline cv::Mat unflat(const double* p, int rows, int cols)
 // the reference seeds cv::RNG(cv::getTickCount()) in every resample() call (src/pf2DRao.cpp:179)
 inline uint64_t tick_seed()
 {
+#ifdef MKF_HAVE_OPENCV
+    return (uint64_t)cv::getTickCount();
+#else
     return (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+#endif
+}
+// getSamples draws from a process-wide stream with a fixed start, as cv::randn does from cv::theRNG()
+// (src/pf2DRao.cpp:91); assign to it to reseed.  It does not touch the tick clock.
+inline uint64_t& the_sample_stream()
+{
+    static uint64_t s = 0x9E3779B97F4A7C15ull;
+    return s;
+}
+// observer of every getSamples() result (2 x N), for tests that need to know the candidates a driver drew
+inline std::function<void(const cv::Mat&)>& sample_hook()
+{
+    static std::function<void(const cv::Mat&)> h;
+    return h;
+}
+// parameters given to every my_gmm constructed afterwards (drivers such as PFTracker construct their
+// ParticleFilter objects themselves, src/pfPose.cpp:58-59)
+inline mkf_params& default_params()
+{
+    static mkf_params p = [] {
+        mkf_params q;
+        mkf_params_default(&q);
+        return q;
+    }();
+    return p;
 }
 // cv::RNG draw order of resample(): one discarded int, then uniform(0.0, 1.0)
 inline double cvrng_uniform_after_int(uint64_t seed)
@@ -236,7 +265,7 @@ class my_gmm {
     int nParticles = 0;
 
     // ---- additions (not in the reference) ----
-    mkf_params params = default_params();
+    mkf_params params = mkf::default_params();
     int device = 0;
     // refresh the host mirror `tracks` from the device (the reference keeps the state on the host)
     void syncTracks()
@@ -291,12 +320,6 @@ class my_gmm {
     int D() const { return D_; }
 
   private:
-    static mkf_params default_params()
-    {
-        mkf_params p;
-        mkf_params_default(&p);
-        return p;
-    }
     void ensure_batch()
     {
         if (!batch_) mkf::check(mkf_batch_create(&batch_, model(), 1, nParticles, device, nullptr));
@@ -399,9 +422,13 @@ class ParticleFilter {
         (void)M; // the model already holds pca_proj / pca_mean
         const double roi[4] = {0.0, 0.0, scale, scale};
         std::vector<double> xy((size_t)4 * N); // 2 hands x 2 rows x N; this filter plays both arms, hand 0 is used
-        mkf::check(mkf_batch_propose(gmm.batch(), gmm.batch(), N, roi, nullptr, nullptr, 1, next_seed(), sample_calls_++,
-                                     0, xy.data(), nullptr, MKF_MEM_HOST));
-        return mkf::unflat(xy.data(), 2, N);
+        uint64_t& stream = mkf::the_sample_stream();
+        stream = stream * 6364136223846793005ull + 1442695040888963407ull;
+        mkf::check(mkf_batch_propose(gmm.batch(), gmm.batch(), N, roi, nullptr, nullptr, 1, stream, sample_calls_++, 0,
+                                     xy.data(), nullptr, MKF_MEM_HOST));
+        cv::Mat out = mkf::unflat(xy.data(), 2, N);
+        if (mkf::sample_hook()) mkf::sample_hook()(out);
+        return out;
     }
     // ParticleFilter::getSampleProb (src/pf2DRao.cpp:105-122)
     void getSampleProb(cv::Mat H, cv::Mat M, cv::Mat input1, cv::Mat input2, std::vector<double>& weight1,

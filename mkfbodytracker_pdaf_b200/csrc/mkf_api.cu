@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -677,51 +678,50 @@ extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t se
         unsigned t = next();
         uu = (double)(((uint64_t)t << 32) | next()) * 5.4210108624275221700372640043497e-20;
     }
-    double *d_w = nullptr, *d_u = nullptr, *d_ws = nullptr;
-    int32_t* d_out = nullptr;
-    uint32_t *d_st = nullptr, *d_fb = nullptr;
-    uint64_t* d_seed = nullptr;
-    int rc = MKF_OK;
-    cudaError_t e = cudaSuccess;
-    if ((e = cudaMalloc((void**)&d_w, (size_t)L * 8)) || (e = cudaMalloc((void**)&d_u, 8)) ||
-        (e = cudaMalloc((void**)&d_ws, 8)) || (e = cudaMalloc((void**)&d_out, (size_t)N * 4)) ||
-        (e = cudaMalloc((void**)&d_st, 4)) || (e = cudaMalloc((void**)&d_fb, 4)) ||
-        (e = cudaMalloc((void**)&d_seed, 8))) {
-        rc = MKF_E_NOMEM;
+    // one grow-only device scratch per device (the call is synchronous; a mutex serialises concurrent callers):
+    //   [ w : L f64 ][ u, wsum : f64 ][ seed : u64 ][ status, need_fb : u32 ][ out : N i32 ]
+    // one packed upload of everything up to `out`, one download of status..out
+    static std::mutex mtx;
+    static void* scratch[64] = {nullptr};
+    static size_t scratch_cap[64] = {0};
+    std::lock_guard<std::mutex> lock(mtx);
+    const size_t off_hdr = (size_t)L * 8, off_st = off_hdr + 24, off_out = off_st + 8, total = off_out + (size_t)N * 4;
+    if (device >= 64) {
+        mkf_set_error("mkf_resample: bad device");
+        return MKF_E_INVALID;
     }
-    if (!rc) {
-        if ((e = cudaMemcpy(d_w, w, (size_t)L * 8, cudaMemcpyHostToDevice)) ||
-            (e = cudaMemcpy(d_u, &uu, 8, cudaMemcpyHostToDevice)) ||
-            (e = cudaMemcpy(d_seed, &seed, 8, cudaMemcpyHostToDevice)) || (e = cudaMemset(d_st, 0, 4)) ||
-            (e = cudaMemset(d_fb, 0, 4))) {
-            mkf_set_error("mkf_resample: %s", cudaGetErrorString(e));
-            rc = MKF_E_CUDA;
+    if (scratch_cap[device] < total) {
+        if (scratch[device]) cudaFree(scratch[device]);
+        scratch[device] = nullptr;
+        scratch_cap[device] = 0;
+        if (cudaMalloc(&scratch[device], total + total / 2) != cudaSuccess) {
+            mkf_set_error("mkf_resample: cudaMalloc failed");
+            return MKF_E_NOMEM;
         }
+        scratch_cap[device] = total + total / 2;
     }
-    if (!rc) {
-        // the reference applies resample() to already-normalised weights: no division here
-        rc = run_resample(0, 1, d_fb, d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, d_seed, 1, 0, MKF_ST_POST_FALLBACK,
+    char* base = (char*)scratch[device];
+    std::vector<char> host(off_out > (size_t)N * 4 + 8 ? off_out : (size_t)N * 4 + 8, 0);
+    std::memcpy(host.data(), w, (size_t)L * 8);
+    std::memcpy(host.data() + off_hdr, &uu, 8);
+    std::memcpy(host.data() + off_hdr + 16, &seed, 8);
+    CK(cudaMemcpy(base, host.data(), off_out, cudaMemcpyHostToDevice));
+    const double* d_w = (const double*)base;
+    const double* d_u = (const double*)(base + off_hdr);
+    double* d_ws = (double*)(base + off_hdr + 8);
+    const uint64_t* d_seed = (const uint64_t*)(base + off_hdr + 16);
+    uint32_t* d_st = (uint32_t*)(base + off_st);
+    uint32_t* d_fb = d_st + 1;
+    int32_t* d_out = (int32_t*)(base + off_out);
+    // the reference applies resample() to already-normalised weights: no division here
+    int rc = run_resample(0, 1, d_fb, d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, d_seed, 1, 0, MKF_ST_POST_FALLBACK,
                           MKF_ST_POST_DEGENERATE);
-    }
-    if (!rc) {
-        e = cudaMemcpy(out, d_out, (size_t)N * 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            mkf_set_error("mkf_resample: %s", cudaGetErrorString(e));
-            rc = MKF_E_CUDA;
-        }
-        uint32_t st = 0;
-        if (!rc && (e = cudaMemcpy(&st, d_st, 4, cudaMemcpyDeviceToHost)) != cudaSuccess) {
-            mkf_set_error("mkf_resample: %s", cudaGetErrorString(e));
-            rc = MKF_E_CUDA;
-        }
-        if (!rc) rc = (st & MKF_ST_POST_DEGENERATE) ? 1 : 0; // like orc_resample: 1 = degenerate fallback taken
-    } else if (rc == MKF_E_NOMEM) {
-        mkf_set_error("mkf_resample: cudaMalloc failed");
-    }
-    void* ptrs[] = {d_w, d_u, d_ws, d_out, d_st, d_fb, d_seed};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
-    return rc;
+    if (rc) return rc;
+    CK(cudaMemcpy(host.data(), base + off_st, 8 + (size_t)N * 4, cudaMemcpyDeviceToHost));
+    std::memcpy(out, host.data() + 8, (size_t)N * 4);
+    uint32_t st = 0;
+    std::memcpy(&st, host.data(), 4);
+    return (st & MKF_ST_POST_DEGENERATE) ? 1 : 0; // like orc_resample: 1 = degenerate fallback taken
 }
 
 extern "C" int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint64_t frame, int jitter,

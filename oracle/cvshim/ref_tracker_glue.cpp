@@ -1,6 +1,13 @@
 // oracle/cvshim/ref_tracker_glue.cpp -- TEST INFRASTRUCTURE: drives the reference's own PFTracker
 // (src/pfPose.{h,cpp}, compiled in place) without ROS: synthetic image / likelihood / face-ROI messages go in,
 // everything it publishes (2-D joints, TF tree, probability image) and its filter states come out.
+//
+// Two builds (oracle/Makefile):
+//   _ref/libref.so         pfPose.cpp on the reference's own KF_model / my_gmm / pf2DRao            (CPU)
+//   _ref/libref_dropin.so  the same unmodified pfPose.cpp on include/mkf_shims.hpp + libmkf_b200.so  (GPU), built with
+//                          -DMKF_DROPIN -D__PF2DRAO -D__MYGMM -D__KFMODEL (the reference headers' own include guards,
+//                          so "pf2DRao.h" contributes nothing) and -include mkf_shims.hpp: INTEGRATION.md section 2
+//                          carried out for real.
 // everything pfPose.h includes is pulled in first (include guards), so that the access override below only
 // touches the PFTracker class body and not the standard library
 #include <cstring>
@@ -52,6 +59,22 @@ void* ref_tracker_create(const char* pkg_path, const char* left_file, const char
     return new PFTracker();
 }
 void ref_tracker_destroy(void* tr) { delete (PFTracker*)tr; }
+#ifdef MKF_DROPIN
+// alias_mode for the ParticleFilter objects PFTracker constructs from now on; candidates drawn by the shim's
+// getSamples() are appended to the same log as the CPU build's cv::randn draws (interleaved x, y)
+void ref_dropin_configure(int alias_mode)
+{
+    mkf::default_params().alias_mode = alias_mode;
+    mkf::sample_hook() = [](const cv::Mat& m) {
+        std::vector<double> v((size_t)2 * m.cols);
+        for (int i = 0; i < m.cols; i++) {
+            v[2 * i] = m.at<double>(0, i);
+            v[2 * i + 1] = m.at<double>(1, i);
+        }
+        cv::cvshim_random_log().push_back(v);
+    };
+}
+#endif
 int ref_tracker_num_particles(void* tr) { return ((PFTracker*)tr)->numParticles; }
 
 void ref_set_rng_seed(uint64_t seed) { cv::cvshim_seed_the_rng(seed); }
@@ -132,6 +155,9 @@ void ref_tracker_get_state(void* trv, int arm, double* x, double* P)
     PFTracker* tr = (PFTracker*)trv;
     ParticleFilter* pf = arm ? tr->pf2 : tr->pf1;
     const int N = pf->gmm.nParticles;
+#ifdef MKF_DROPIN
+    pf->gmm.syncTracks(); // the state lives on the device
+#endif
     for (int j = 0; j < N; j++) {
         const cv::Mat& s = pf->gmm.tracks[j].state;
         const cv::Mat& c = pf->gmm.tracks[j].cov;

@@ -205,8 +205,11 @@ def _bind_tracker(L):
 class RefTracker:
     """the reference's PFTracker (src/pfPose.{h,cpp}) driven without ROS: one synthetic frame per call()"""
 
+    def _load(self):
+        return lib()
+
     def __init__(self, model_dir, left_file, right_file, tick1, tick2, rng_seed=0x12345678):
-        L = lib()
+        L = self._L = self._load()
         _bind_tracker(L)
         L.ref_set_rng_seed(int(rng_seed))  # the generator behind the node's cv::randn / cv::randu draws
         self.h = L.ref_tracker_create(os.fsencode(model_dir), os.fsencode("/" + left_file),
@@ -216,7 +219,7 @@ class RefTracker:
     def callback(self, like, roi_xywh, ticks):
         """like: (rows, cols) uint8 raw likelihood image; roi (x, y, w, h) or None (no face); ticks: 6 ints.
         returns dict(cands=[hand][2, C], blurred=(rows, cols) uint8, joints2d (8,2), tf (10,3), n_tf)"""
-        L = lib()
+        L = self._L
         like = np.ascontiguousarray(like, np.uint8)
         rows, cols = like.shape
         L.ref_random_log_clear()
@@ -248,19 +251,55 @@ class RefTracker:
     def get_state(self, arm, d=12):
         x = np.zeros((self.N, d))
         P = np.zeros((self.N, d, d))
-        lib().ref_tracker_get_state(self.h, arm, _p(x), _p(P))
+        self._L.ref_tracker_get_state(self.h, arm, _p(x), _p(P))
         return x, P
 
     def pose(self, arm, D=22):
         e = np.zeros(D)
         p3 = np.zeros((3, 5))
-        lib().ref_tracker_pose(self.h, arm, _p(e), _p(p3))
+        self._L.ref_tracker_pose(self.h, arm, _p(e), _p(p3))
         return e, p3
 
     def __del__(self):
         try:
             if self.h:
-                lib().ref_tracker_destroy(self.h)
+                self._L.ref_tracker_destroy(self.h)
                 self.h = None
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------------
+# the drop-in build: the reference's unmodified src/pfPose.cpp on include/mkf_shims.hpp + libmkf_b200.so
+# ------------------------------------------------------------------------------------------------------
+SO_DROPIN = os.path.join(_HERE, "_ref", "libref_dropin.so")
+_LIB_DROPIN = None
+
+
+def dropin_available() -> bool:
+    if os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.run(["make", "-C", _HERE, "dropin"], check=True, capture_output=True)
+        except Exception:
+            pass
+    return os.path.exists(SO_DROPIN)
+
+
+class DropinTracker(RefTracker):
+    """the same PFTracker source, but its ParticleFilter / my_gmm / KF_model are the drop-in shims: every filter
+    operation runs on the GPU through libmkf_b200.so.  alias_mode: 0 independent slots, 1 the reference binary's
+    shallow-copy behaviour (quirk B3)."""
+
+    def __init__(self, *args, alias_mode=1, **kw):
+        self._alias_mode = int(alias_mode)
+        super().__init__(*args, **kw)
+
+    def _load(self):
+        global _LIB_DROPIN
+        if _LIB_DROPIN is None:
+            if not dropin_available():
+                raise FileNotFoundError(SO_DROPIN)
+            _LIB_DROPIN = C.CDLL(SO_DROPIN)
+        _LIB_DROPIN.ref_dropin_configure.argtypes = [C.c_int]
+        _LIB_DROPIN.ref_dropin_configure(self._alias_mode)
+        return _LIB_DROPIN
