@@ -328,6 +328,15 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     return MKF_OK;
 }
 
+// function attributes are per device: true the first time a call site runs on the current device
+static bool first_on_this_device(std::atomic<uint64_t>& seen)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    return (seen.fetch_or(bit) & bit) == 0;
+}
+
 // weight normalisation + systematic resampling of `nt` tracks: w (nt x L) -> out (nt x N)
 static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, const double* d_w, int L, int N,
                         const double* d_u, int u_stride, int normalise, double* d_wsum, int32_t* d_out,
@@ -335,8 +344,12 @@ static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, co
                         uint32_t bit_deg, uint32_t* d_unsorted = nullptr)
 {
     if (L <= 64 && N <= 64) {
-        k_resample_small<<<grid_for(nt, 128), 128, 0, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
-                                                                 d_status, 1, need_fb, bit_deg);
+        const size_t smem = (size_t)129 * ((size_t)L * 8 + (size_t)N * 4); // <= 99 KB at L = N = 64
+        static std::atomic<uint64_t> seen{0};
+        if (first_on_this_device(seen))
+            CK(cudaFuncSetAttribute(k_resample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        k_resample_small<<<grid_for(nt, 128), 128, smem, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum,
+                                                                    d_out, d_status, 1, need_fb, bit_deg);
     } else {
         // one CTA per track; wider CTAs for long weight / index vectors so a track's tiles are few
         const int span = L > N ? L : N;
@@ -396,13 +409,12 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     a.r = m->prm.meas_noise_var;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
     {
-        static bool attr_done = false;
-        if (!attr_done && smem > 48 * 1024) {
+        static std::atomic<uint64_t> seen{0};
+        if (smem > 48 * 1024 && first_on_this_device(seen)) {
             CK(cudaFuncSetAttribute(k_slot_update<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CK(cudaFuncSetAttribute(k_slot_update<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CK(cudaFuncSetAttribute(k_slot_update<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CK(cudaFuncSetAttribute(k_slot_update<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_done = true;
         }
         const unsigned g = grid_for(b->total, 128);
         if (m->d == 12) {
@@ -513,12 +525,24 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
 {
     const mkf_model* m = b->m;
     const double2* st = b->st[b->cur];
-    if (b->N <= 16)
-        k_estimate_small<DD, 16><<<grid_for(b->T, 128 / 16), 128, 0, b->stream>>>(
-            st, b->parent, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose);
-    else if (b->N <= 96)
-        k_estimate_small<DD, 32><<<grid_for(b->T, 128 / 32), 128, 0, b->stream>>>(
-            st, b->parent, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose);
+    const size_t coef_bytes = (size_t)(m->D + DD) * DD * sizeof(double);
+    // tracks per CTA = TRIPS * 128 / GROUP: 8 trips amortise staging the reconstruction matrices once there are
+    // enough tracks to fill the GPU several times over; small batches keep one trip so that they still spread out
+#define MKF_EST_SMALL(G, TR)                                                                                  \
+    k_estimate_small<DD, G, TR><<<grid_for(b->T, TR * 128 / G), 128, coef_bytes, b->stream>>>(                \
+        st, b->parent, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose)
+    if (b->N <= 16) {
+        if (b->T >= 8 * 8 * 4 * 148)
+            MKF_EST_SMALL(16, 8);
+        else
+            MKF_EST_SMALL(16, 1);
+    } else if (b->N <= 96) {
+        if (b->T >= 8 * 4 * 4 * 148)
+            MKF_EST_SMALL(32, 8);
+        else
+            MKF_EST_SMALL(32, 1);
+    }
+#undef MKF_EST_SMALL
     else if (b->N <= 2048)
         k_estimate<DD, 128><<<(unsigned)b->T, 128, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
                                                                    b->d_tinv, d_xbar, d_pose);

@@ -128,8 +128,9 @@ struct mkf_cvrng {
 };
 
 // the literal sequential loop (bit-exact by construction); w(i) yields the i-th weight
-template <class WF>
-__device__ __forceinline__ void mkf_resample_sequential(WF w, int L, int N, double u, int32_t* out)
+// (out(i, idx) stores the i-th result)
+template <class WF, class OF>
+__device__ __forceinline__ void mkf_resample_sequential(WF w, int L, int N, double u, OF out)
 {
     int idx = 0;
     const double step = __ddiv_rn(1.0, (double)N);
@@ -142,7 +143,7 @@ __device__ __forceinline__ void mkf_resample_sequential(WF w, int L, int N, doub
             wi = w(idx);
         }
         beta = __dadd_rn(beta, step);
-        out[i] = idx;
+        out(i, idx);
     }
 }
 

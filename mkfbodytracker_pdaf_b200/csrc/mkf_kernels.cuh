@@ -780,31 +780,55 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
 
 // one thread per track, literal sequential semantics throughout (sequential wsum as the
 // reference, src/pf2DRao.cpp:139; then the loop of :195-207).  Used when N and L are small.
-__global__ void k_resample_small(const double* __restrict__ w_all, long long T, int L, int N,
-                                 const double* __restrict__ u, int u_stride, int normalise,
-                                 double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
-                                 uint32_t* __restrict__ status, int status_stride, uint32_t* __restrict__ need_fb,
-                                 uint32_t bit_deg)
+// The CTA's 128 weight rows are staged transposed in shared memory (coalesced loads, one division per weight instead
+// of one per visit) and the indices leave through shared memory as well (coalesced stores).  LD = 129 keeps both the
+// transposing accesses and the per-thread walks free of bank conflicts.
+__global__ void __launch_bounds__(128) k_resample_small(const double* __restrict__ w_all, long long T, int L, int N,
+                                                         const double* __restrict__ u, int u_stride, int normalise,
+                                                         double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
+                                                         uint32_t* __restrict__ status, int status_stride,
+                                                         uint32_t* __restrict__ need_fb, uint32_t bit_deg)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const double* __restrict__ w = w_all + t * L;
-    double wsum = 0.0;
-    for (int i = 0; i < L; i++) wsum = __dadd_rn(wsum, w[i]);
-    if (wsum_out) wsum_out[t] = wsum;
-    if (!normalise) wsum = 1.0;
-    double mw = 0.0;
-    for (int i = 0; i < L; i++) {
-        const double x = normalise ? __ddiv_rn(w[i], wsum) : w[i];
-        if (x > mw) mw = x;
+    constexpr int LD = 129;
+    extern __shared__ double sm_w[];                                       // [L][LD]
+    int32_t* sm_out = reinterpret_cast<int32_t*>(sm_w + (size_t)L * LD);   // [N][LD]
+    __shared__ unsigned char skip[128];
+    const int tid = threadIdx.x;
+    const long long t0 = (long long)blockIdx.x * 128;
+    const int nt = (int)((T - t0) < 128 ? (T - t0) : 128);
+    for (int i = tid; i < nt * L; i += 128) {
+        const int tr = i / L, k = i - tr * L;
+        sm_w[k * LD + tr] = w_all[t0 * L + i];
     }
-    if (!(mw > 0.0)) {
-        need_fb[t] = 1u;
-        atomicOr(status + t * status_stride, bit_deg);
-        return;
+    __syncthreads();
+    if (tid < nt) {
+        const long long t = t0 + tid;
+        double* __restrict__ w = sm_w + tid;
+        double wsum = 0.0;
+        for (int i = 0; i < L; i++) wsum = __dadd_rn(wsum, w[i * LD]);
+        if (wsum_out) wsum_out[t] = wsum;
+        double mw = 0.0;
+        for (int i = 0; i < L; i++) {
+            const double x = normalise ? __ddiv_rn(w[i * LD], wsum) : w[i * LD];
+            w[i * LD] = x;
+            if (x > mw) mw = x;
+        }
+        const bool deg = !(mw > 0.0);
+        skip[tid] = deg;
+        if (deg) {
+            need_fb[t] = 1u;
+            atomicOr(status + t * status_stride, bit_deg);
+        } else {
+            int32_t* o = sm_out + tid;
+            mkf_resample_sequential([&](int i) { return w[i * LD]; }, L, N, u[t * u_stride],
+                                    [&](int i, int idx) { o[i * LD] = idx; });
+        }
     }
-    auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
-    mkf_resample_sequential(wf, L, N, u[t * u_stride], out_all + t * N);
+    __syncthreads();
+    for (int i = tid; i < nt * N; i += 128) {
+        const int tr = i / N, k = i - tr * N;
+        if (!skip[tr]) out_all[t0 * N + i] = sm_out[k * LD + tr];
+    }
 }
 
 // flagged tracks: literal loop on the same normalised weights, or the cv::RNG random-index
@@ -912,22 +936,33 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __res
     }
 }
 
-// getEstimator + reconstruction for small N: GROUP (16 or 32) lanes per track, several tracks per CTA
-template <int D, int GROUP>
+// getEstimator + reconstruction for small N: GROUP (16 or 32) lanes per track, 128 / GROUP tracks per CTA and trip,
+// TRIPS trips per CTA.  The reconstruction matrices are staged once per CTA (transposed, so that lane r reading
+// row r is conflict-free); within a trip there is no block barrier: the butterfly reduction leaves the mean in every
+// lane of the group, which then computes its own output rows.
+template <int D, int GROUP, int TRIPS>
 __global__ void __launch_bounds__(128) k_estimate_small(const double2* __restrict__ st, const int32_t* __restrict__ parent,
                                                          long long T, int N, int Dpose, const double* __restrict__ recon,
                                                          const double* __restrict__ pmean, const double* __restrict__ tinv,
                                                          double* __restrict__ xbar_out, double* __restrict__ pose_out)
 {
     using L = SlotLay<D>;
-    constexpr int TPB = 128 / GROUP; // tracks per CTA
-    __shared__ double xb[TPB][D];
+    constexpr int TPB = 128 / GROUP; // tracks per CTA and trip
+    extern __shared__ double coef[]; // [c][r], r < Dpose + D: rows of recon (pose) then rows of tinv (xbar)
+    const int R = Dpose + D;
+    for (int i = threadIdx.x; i < R * D; i += 128) {
+        const int r = i / D, c = i - r * D;
+        coef[c * R + r] = r < Dpose ? recon[r * D + c] : tinv[(r - Dpose) * D + c];
+    }
+    __syncthreads();
     const int g = threadIdx.x / GROUP, l = threadIdx.x % GROUP;
-    const long long t = (long long)blockIdx.x * TPB + g;
-    double acc[D];
+    const double inv_n = 1.0 / (double)N;
+    for (int trip = 0; trip < TRIPS; trip++) {
+        const long long t = ((long long)blockIdx.x * TRIPS + trip) * TPB + g;
+        if (t >= T) break; // uniform within the group; groups only meet at warp shuffles of their own lanes
+        double acc[D];
 #pragma unroll
-    for (int e = 0; e < D; e++) acc[e] = 0.0;
-    if (t < T) {
+        for (int e = 0; e < D; e++) acc[e] = 0.0;
         for (int j = l; j < N; j += GROUP) {
             const long long sp = t * N + __ldg(parent + t * N + j);
             const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
@@ -938,30 +973,23 @@ __global__ void __launch_bounds__(128) k_estimate_small(const double2* __restric
                 acc[2 * p + 1] += q.y;
             }
         }
-    }
+        // lanes of one group are contiguous in a warp and GROUP divides 32: xor offsets < GROUP stay inside it
+        const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << ((threadIdx.x & 31) / GROUP * GROUP));
 #pragma unroll
-    for (int e = 0; e < D; e++) {
+        for (int e = 0; e < D; e++) {
 #pragma unroll
-        for (int o = GROUP / 2; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
-    }
-    if (l == 0) {
-#pragma unroll
-        for (int e = 0; e < D; e++) xb[g][e] = acc[e] * (1.0 / (double)N);
-    }
-    __syncthreads();
-    if (t >= T) return;
-    for (int r = l; r < Dpose + D; r += GROUP) {
-        if (r < Dpose) {
-            if (!pose_out) continue;
+            for (int o = GROUP / 2; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(gmask, acc[e], o);
+            acc[e] *= inv_n;
+        }
+        for (int r = l; r < R; r += GROUP) {
             double sacc = 0.0;
-            for (int c = 0; c < D; c++) sacc = fma(recon[r * D + c], xb[g][c], sacc);
-            pose_out[t * Dpose + r] = sacc + pmean[r];
-        } else {
-            if (!xbar_out) continue;
-            const int q = r - Dpose;
-            double sacc = 0.0;
-            for (int c = 0; c < D; c++) sacc = fma(tinv[q * D + c], xb[g][c], sacc);
-            xbar_out[t * D + q] = sacc;
+#pragma unroll
+            for (int c = 0; c < D; c++) sacc = fma(coef[c * R + r], acc[c], sacc);
+            if (r < Dpose) {
+                if (pose_out) pose_out[t * Dpose + r] = sacc + pmean[r];
+            } else if (xbar_out) {
+                xbar_out[t * D + (r - Dpose)] = sacc;
+            }
         }
     }
 }
