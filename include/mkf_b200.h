@@ -229,6 +229,9 @@ int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint64_t frame, 
  * mkf_batch_profile_read synchronises and returns the summed milliseconds of the three stages
  * (indicator bounds, fused slot update, normalise+resample) over n_updates updates, then rearms. */
 int mkf_batch_profile(mkf_batch* b, int max_updates);
+/* the same, sampling every `every`-th update (>= 1) for up to max_samples samples: the four event records of a
+ * sampled update cost ~3 us each and suspend the kernels' programmatic overlap, so a timed region samples sparsely */
+int mkf_batch_profile_every(mkf_batch* b, int max_samples, int every);
 int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_update, double* ms_resample,
                            int* n_updates);
 

@@ -4,6 +4,8 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -15,6 +17,32 @@
 static std::atomic<uint64_t> g_launches{0};
 extern "C" uint64_t mkf_launch_count(void) { return g_launches.load(); }
 #define MKF_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// Launch with the programmatic-stream-serialization attribute (PDL, see mkf_device.cuh): kernels of the per-frame
+// chain only.  MKF_PDL=0 in the environment turns the attribute off (plain stream order) for A/B measurements.
+static bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("MKF_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <class... P, class... A>
+static void mkf_launch(void (*kern)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, A&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...); // errors surface through cudaGetLastError()
+}
 
 #define CK(call)                                                                                          \
     do {                                                                                                  \
@@ -77,7 +105,6 @@ struct mkf_batch {
     double* w_raw = nullptr;
     double* wsum = nullptr;
     uint32_t* status = nullptr;
-    uint32_t* need_fb = nullptr;
     uint32_t* unsorted = nullptr;  // per track: last posterior resample left unsorted parents
     int32_t* chain_last = nullptr; // T x N scratch of the literal alias mode
     // model constants on this device
@@ -93,7 +120,8 @@ struct mkf_batch {
     int stage = 3; // see SlotArgs::stage (mkf_kf_apply runs single stages)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
-    int prof_n = 0;
+    int prof_n = 0, prof_every = 1;
+    uint64_t prof_tick = 0;
 };
 
 static bool is_device_ptr(const void* p, int mem)
@@ -171,7 +199,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->bounds, b->w_raw, b->wsum,   b->status, b->need_fb, b->unsorted, b->chain_last, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->bounds, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -245,7 +273,6 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     if ((rc = dmalloc((void**)&b->w_raw, (size_t)b->total * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->wsum, (size_t)T * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->status, (size_t)T * sizeof(uint32_t)))) return fail(rc);
-    if ((rc = dmalloc((void**)&b->need_fb, (size_t)2 * T * sizeof(uint32_t)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->unsorted, (size_t)T * sizeof(uint32_t)))) return fail(rc);
     if (m->prm.alias_mode == MKF_ALIAS_CV_SHALLOW_LITERAL &&
         (rc = dmalloc((void**)&b->chain_last, (size_t)b->total * sizeof(int32_t))))
@@ -254,7 +281,6 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     if (cudaMemset(b->st[0], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
         cudaMemset(b->st[1], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
         cudaMemset(b->status, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMemset(b->need_fb, 0, (size_t)2 * T * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemset(b->unsorted, 0, (size_t)T * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemset(b->w_raw, 0, (size_t)b->total * sizeof(double)) != cudaSuccess ||
         cudaMemset(b->wsum, 0, (size_t)T * sizeof(double)) != cudaSuccess ||
@@ -290,7 +316,7 @@ static int launch_bounds_kernel(mkf_batch* b, const double* d_u)
 {
     const mkf_model* m = b->m;
 #define LAUNCH_BOUNDS(G)                                                                                       \
-    k_indicator_bounds<G><<<grid_for(b->T * G, 128), 128, 0, b->stream>>>(d_u, b->T, b->N, m->K, b->d_cw_hi,       \
+    mkf_launch(k_indicator_bounds<G>, grid_for(b->T * G, 128), 128, 0, b->stream, d_u, b->T, b->N, m->K, b->d_cw_hi,       \
                                                                            b->d_cw_lo, b->d_wprior, m->prior_wmax, \
                                                                            b->bounds, b->status)
     if (m->K <= 16)
@@ -338,24 +364,24 @@ static bool first_on_this_device(std::atomic<uint64_t>& seen)
 }
 
 // weight normalisation + systematic resampling of `nt` tracks: w (nt x L) -> out (nt x N)
-static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, const double* d_w, int L, int N,
-                        const double* d_u, int u_stride, int normalise, double* d_wsum, int32_t* d_out,
-                        uint32_t* d_status, const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb,
-                        uint32_t bit_deg, uint32_t* d_unsorted = nullptr)
+static int run_resample(cudaStream_t stream, long long nt, const double* d_w, int L, int N, const double* d_u,
+                        int u_stride, int normalise, double* d_wsum, int32_t* d_out, uint32_t* d_status,
+                        const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb, uint32_t bit_deg,
+                        uint32_t* d_unsorted = nullptr)
 {
     if (L <= 64 && N <= 64) {
         const size_t smem = (size_t)129 * ((size_t)L * 8 + (size_t)N * 4); // <= 99 KB at L = N = 64
         static std::atomic<uint64_t> seen{0};
         if (first_on_this_device(seen))
             CK(cudaFuncSetAttribute(k_resample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        k_resample_small<<<grid_for(nt, 128), 128, smem, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum,
-                                                                    d_out, d_status, 1, need_fb, bit_deg);
+        mkf_launch(k_resample_small, grid_for(nt, 128), 128, smem, stream, d_w, nt, L, N, d_u, u_stride, normalise, d_wsum,
+                   d_out, d_status, 1, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted);
     } else {
         // one CTA per track; wider CTAs for long weight / index vectors so a track's tiles are few
         const int span = L > N ? L : N;
-#define MKF_RS_BLOCK(BT)                                                                                            \
-    k_resample_block<BT, 4><<<(unsigned)nt, BT, 0, stream>>>(d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out,    \
-                                                              d_status, 1, need_fb, bit_fb, bit_deg)
+#define MKF_RS_BLOCK(BT)                                                                                             \
+    mkf_launch(k_resample_block<BT, 4>, (unsigned)nt, BT, 0, stream, d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out, \
+               d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted)
         if (span <= 1024)
             MKF_RS_BLOCK(128);
         else if (span <= 8192)
@@ -364,10 +390,6 @@ static int run_resample(cudaStream_t stream, long long nt, uint32_t* need_fb, co
             MKF_RS_BLOCK(1024);
 #undef MKF_RS_BLOCK
     }
-    MKF_LAUNCHED();
-    CK(cudaGetLastError());
-    k_resample_fallback<<<grid_for(nt, 128), 128, 0, stream>>>(d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
-                                                                d_seeds, seed_stride, seed_off, need_fb, d_unsorted);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     return MKF_OK;
@@ -383,7 +405,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         mkf_set_error("internal: strided u_ind unsupported");
         return MKF_E_INVALID;
     }
-    const bool prof = b->prof_on && (size_t)(b->prof_n + 1) * 4 <= b->prof_ev.size();
+    const bool prof = b->prof_on && (b->prof_tick++ % (uint64_t)b->prof_every) == 0 &&
+                      (size_t)(b->prof_n + 1) * 4 <= b->prof_ev.size();
     cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * 4] : nullptr;
     if (prof) cudaEventRecord(pe[0], b->stream);
     if ((rc = launch_bounds_kernel(b, d_uind))) return rc;
@@ -419,28 +442,28 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         const unsigned g = grid_for(b->total, 128);
         if (m->d == 12) {
             if (a.alias_chain)
-                k_slot_update<12, true><<<g, 128, smem, b->stream>>>(a);
+                mkf_launch(k_slot_update<12, true>, g, 128, smem, b->stream, a);
             else
-                k_slot_update<12, false><<<g, 128, smem, b->stream>>>(a);
+                mkf_launch(k_slot_update<12, false>, g, 128, smem, b->stream, a);
         } else {
             if (a.alias_chain)
-                k_slot_update<10, true><<<g, 128, smem, b->stream>>>(a);
+                mkf_launch(k_slot_update<10, true>, g, 128, smem, b->stream, a);
             else
-                k_slot_update<10, false><<<g, 128, smem, b->stream>>>(a);
+                mkf_launch(k_slot_update<10, false>, g, 128, smem, b->stream, a);
         }
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     // rare tracks (cv::Cholesky failure flagged, or unsorted parents in the literal alias mode) are redone
     if (m->d == 12)
-        k_slot_update_repair<12><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
+        mkf_launch(k_slot_update_repair<12>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last);
     else
-        k_slot_update_repair<10><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, b->chain_last);
+        mkf_launch(k_slot_update_repair<10>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (prof) cudaEventRecord(pe[2], b->stream);
     b->cur ^= 1;
-    rc = run_resample(b->stream, b->T, b->need_fb, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status,
+    rc = run_resample(b->stream, b->T, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status,
                       d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE, b->unsorted);
     if (prof) {
         cudaEventRecord(pe[3], b->stream);
@@ -450,12 +473,17 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
 }
 
 // per-kernel device timing of mkf_batch_update with CUDA events on the batch's stream
-extern "C" int mkf_batch_profile(mkf_batch* b, int max_updates)
+extern "C" int mkf_batch_profile_every(mkf_batch* b, int max_samples, int every);
+extern "C" int mkf_batch_profile(mkf_batch* b, int max_updates) { return mkf_batch_profile_every(b, max_updates, 1); }
+
+extern "C" int mkf_batch_profile_every(mkf_batch* b, int max_updates, int every)
 {
-    if (!b || max_updates < 0) {
+    if (!b || max_updates < 0 || every < 1) {
         mkf_set_error("mkf_batch_profile: invalid argument");
         return MKF_E_INVALID;
     }
+    b->prof_every = every;
+    b->prof_tick = 0;
     CK(cudaSetDevice(b->device));
     CK(cudaStreamSynchronize(b->stream));
     for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
@@ -529,7 +557,7 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
     // tracks per CTA = TRIPS * 128 / GROUP: 8 trips amortise staging the reconstruction matrices once there are
     // enough tracks to fill the GPU several times over; small batches keep one trip so that they still spread out
 #define MKF_EST_SMALL(G, TR)                                                                                  \
-    k_estimate_small<DD, G, TR><<<grid_for(b->T, TR * 128 / G), 128, coef_bytes, b->stream>>>(                \
+    mkf_launch(k_estimate_small<DD, G, TR>, grid_for(b->T, TR * 128 / G), 128, coef_bytes, b->stream,                 \
         st, b->parent, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose)
     if (b->N <= 16) {
         if (b->T >= 8 * 8 * 4 * 148)
@@ -544,10 +572,10 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
     }
 #undef MKF_EST_SMALL
     else if (b->N <= 2048)
-        k_estimate<DD, 128><<<(unsigned)b->T, 128, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
+        mkf_launch(k_estimate<DD, 128>, (unsigned)b->T, 128, 0, b->stream, st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
                                                                    b->d_tinv, d_xbar, d_pose);
     else // long tracks: more loads in flight per track (BT = 512 is slower at N = 500: 64 vs 41 us at 4096 tracks)
-        k_estimate<DD, 512><<<(unsigned)b->T, 512, 0, b->stream>>>(st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
+        mkf_launch(k_estimate<DD, 512>, (unsigned)b->T, 512, 0, b->stream, st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
                                                                    b->d_tinv, d_xbar, d_pose);
 }
 static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
@@ -703,7 +731,7 @@ extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t se
         uu = (double)(((uint64_t)t << 32) | next()) * 5.4210108624275221700372640043497e-20;
     }
     // one grow-only device scratch per device (the call is synchronous; a mutex serialises concurrent callers):
-    //   [ w : L f64 ][ u, wsum : f64 ][ seed : u64 ][ status, need_fb : u32 ][ out : N i32 ]
+    //   [ w : L f64 ][ u, wsum : f64 ][ seed : u64 ][ status : u32, pad ][ out : N i32 ]
     // one packed upload of everything up to `out`, one download of status..out
     static std::mutex mtx;
     static void* scratch[64] = {nullptr};
@@ -735,10 +763,9 @@ extern "C" int mkf_resample(const double* w, int L, int N, double u, uint64_t se
     double* d_ws = (double*)(base + off_hdr + 8);
     const uint64_t* d_seed = (const uint64_t*)(base + off_hdr + 16);
     uint32_t* d_st = (uint32_t*)(base + off_st);
-    uint32_t* d_fb = d_st + 1;
     int32_t* d_out = (int32_t*)(base + off_out);
     // the reference applies resample() to already-normalised weights: no division here
-    int rc = run_resample(0, 1, d_fb, d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, d_seed, 1, 0, MKF_ST_POST_FALLBACK,
+    int rc = run_resample(0, 1, d_w, L, N, d_u, 1, 0, d_ws, d_out, d_st, d_seed, 1, 0, MKF_ST_POST_FALLBACK,
                           MKF_ST_POST_DEGENERATE);
     if (rc) return rc;
     CK(cudaMemcpy(host.data(), base + off_st, 8 + (size_t)N * 4, cudaMemcpyDeviceToHost));

@@ -196,7 +196,7 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
     k_assoc_weights<<<grid_for(T * 2 * 32, 128), 128, 0, b->stream>>>(aa);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
-    if ((rc = run_resample(b->stream, T * 2, b->need_fb, (const double*)b->as_w.p, C, N, d_uc, 1, 1,
+    if ((rc = run_resample(b->stream, T * 2, (const double*)b->as_w.p, C, N, d_uc, 1, 1,
                            (double*)b->as_wsum.p, (int32_t*)b->as_bins.p, (uint32_t*)b->as_status.p, d_seeds, 3, 0,
                            MKF_ST_CAND_FALLBACK, MKF_ST_CAND_DEGENERATE)))
         return rc;

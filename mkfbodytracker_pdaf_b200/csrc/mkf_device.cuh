@@ -219,6 +219,15 @@ __device__ __forceinline__ void mkf_mbar_wait(uint64_t* bar, uint32_t phase)
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of the per-frame chain lets its successor's CTAs be scheduled as
+// soon as all of its own CTAs have started (launch_dependents, first thing) and blocks until the predecessor grid has
+// completed and its writes are visible (wait) before it touches anything that grid produced -- or writes anything
+// that grid may still read.  Without the launch attribute both are no-ops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mkf_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void mkf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // warp / block collectives
 // ---------------------------------------------------------------------------------------------
 // block-wide exclusive scan of one double per thread (plain IEEE adds); also returns the block total.

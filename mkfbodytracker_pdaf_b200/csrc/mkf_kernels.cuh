@@ -6,7 +6,7 @@
 //                                                                              src/pf2DRao.cpp:34-67
 //   k_resample_block    weight sum/normalise + N->N (or C->N) resample        src/pf2DRao.cpp:145-152,175-210
 //   k_resample_small    same, one thread per track, literal loop (small N)
-//   k_resample_fallback literal loop / cv::RNG fallback for flagged tracks    src/pf2DRao.cpp:184-207
+//                       (flagged tracks: literal loop / cv::RNG branch in the same kernels, src/pf2DRao.cpp:184-207)
 //   k_estimate          getEstimator + PCA reconstruction                      src/pf2DRao.cpp:23-31, src/pfPose.cpp:347-348
 //   k_reset / k_upload / k_download / k_aux_outputs : state I/O in reference coordinates
 //
@@ -358,8 +358,10 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
     __syncthreads();
     if (threadIdx.x == 0) {
         mkf_mbar_expect_tx(&mbar, cbytes);
-        mkf_tma_load_1d(cst, a.comp_const, cbytes, &mbar);
+        mkf_tma_load_1d(cst, a.comp_const, cbytes, &mbar); // model constants: never written by the frame chain
     }
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
 
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = s < a.total;
@@ -444,6 +446,8 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
 {
     using L = SlotLay<D>;
     __shared__ uint32_t flags[128];
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
     const long long T = a.total / a.N;
     const long long base = (long long)blockIdx.x * 128;
     {
@@ -507,6 +511,8 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
                                    const double* __restrict__ wprior, double wmax, int32_t* __restrict__ bounds,
                                    uint32_t* __restrict__ status)
 {
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long t = gid / GROUP;
     const int k = (int)(gid % GROUP);
@@ -632,20 +638,26 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
                                                         const double* __restrict__ u, int u_stride, int normalise,
                                                         double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
                                                         uint32_t* __restrict__ status, int status_stride,
-                                                        uint32_t* __restrict__ need_fb, uint32_t bit_fb,
-                                                        uint32_t bit_deg)
+                                                        uint32_t bit_fb, uint32_t bit_deg,
+                                                        const uint64_t* __restrict__ seeds, int seed_stride,
+                                                        int seed_off, uint32_t* __restrict__ unsorted)
 {
+    constexpr int CH = 512;
     __shared__ int sc_i[BT / 32];
     __shared__ double sc_d[BT / 32], sc_d2[BT / 32], sc_d3[BT / 32];
+    __shared__ double chunk[CH]; // weights staged for the literal loop (rare)
     __shared__ int sh_flag;
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
     const long long t = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double* __restrict__ w = w_all + t * L;
     int32_t* __restrict__ out = out_all + t * N;
+    if (tid == 0 && unsorted) unsorted[t] = 0u;
 
     // pass 1: sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172).  The sum only has to be an accurate
-    // normaliser (the reference's own sequential sum is no more exact); the stored value is reused by
-    // k_resample_fallback so both paths normalise identically.
+    // normaliser (the reference's own sequential sum is no more exact); the literal loop below divides by the
+    // same value, so both paths see identical normalised weights.
     double acc = 0.0, mx = 0.0, sq = 0.0;
     for (int i = tid; i < L; i += BT) {
         const double x = w[i];
@@ -679,10 +691,13 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     const double wsum = normalise ? acc : 1.0;
     if (tid == 0 && wsum_out) wsum_out[t] = acc;
     const double wmax_n = normalise ? __ddiv_rn(mx, wsum) : mx;
-    if (!(wmax_n > 0.0)) { // max weight 0 / NaN -> random-index fallback (src/pf2DRao.cpp:184-192)
+    if (!(wmax_n > 0.0)) { // max weight 0 / NaN -> random indices from cv::RNG (src/pf2DRao.cpp:184-192)
         if (tid == 0) {
-            need_fb[t] = 1u;
             atomicOr(status + t * status_stride, bit_deg);
+            mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
+            (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
+            for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
+            if (unsorted) unsorted[t] = 1u; // random indices are not sorted (matters for the literal alias mode)
         }
         return;
     }
@@ -749,9 +764,12 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
         if (amb2) sh_flag = 1;
         __syncthreads();
         if (sh_flag) {
-            if (tid == 0) {
-                need_fb[t] = 1u;
-                atomicOr(status + t * status_stride, bit_fb);
+            // still undecidable in closed form: the first warp runs the reference's loop itself on the same
+            // normalised weights (staged through shared memory, lane 0 walking them)
+            if (tid == 0) atomicOr(status + t * status_stride, bit_fb);
+            if (wid == 0) {
+                auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
+                mkf_resample_sequential_warp<CH>(wf, L, N, u[t * u_stride], out, chunk);
             }
             return;
         }
@@ -787,12 +805,14 @@ __global__ void __launch_bounds__(128) k_resample_small(const double* __restrict
                                                          const double* __restrict__ u, int u_stride, int normalise,
                                                          double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
                                                          uint32_t* __restrict__ status, int status_stride,
-                                                         uint32_t* __restrict__ need_fb, uint32_t bit_deg)
+                                                         uint32_t bit_deg, const uint64_t* __restrict__ seeds,
+                                                         int seed_stride, int seed_off, uint32_t* __restrict__ unsorted)
 {
     constexpr int LD = 129;
     extern __shared__ double sm_w[];                                       // [L][LD]
     int32_t* sm_out = reinterpret_cast<int32_t*>(sm_w + (size_t)L * LD);   // [N][LD]
-    __shared__ unsigned char skip[128];
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
     const int tid = threadIdx.x;
     const long long t0 = (long long)blockIdx.x * 128;
     const int nt = (int)((T - t0) < 128 ? (T - t0) : 128);
@@ -813,71 +833,22 @@ __global__ void __launch_bounds__(128) k_resample_small(const double* __restrict
             w[i * LD] = x;
             if (x > mw) mw = x;
         }
-        const bool deg = !(mw > 0.0);
-        skip[tid] = deg;
-        if (deg) {
-            need_fb[t] = 1u;
+        int32_t* o = sm_out + tid;
+        if (!(mw > 0.0)) { // max weight 0 / NaN -> random indices from cv::RNG (src/pf2DRao.cpp:184-192)
             atomicOr(status + t * status_stride, bit_deg);
+            mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
+            (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
+            for (int i = 0; i < N; i++) o[i * LD] = rng.uniform_int(0, L);
         } else {
-            int32_t* o = sm_out + tid;
             mkf_resample_sequential([&](int i) { return w[i * LD]; }, L, N, u[t * u_stride],
                                     [&](int i, int idx) { o[i * LD] = idx; });
         }
+        if (unsorted) unsorted[t] = (mw > 0.0) ? 0u : 1u; // random indices are not sorted (literal alias mode)
     }
     __syncthreads();
     for (int i = tid; i < nt * N; i += 128) {
         const int tr = i / N, k = i - tr * N;
-        if (!skip[tr]) out_all[t0 * N + i] = sm_out[k * LD + tr];
-    }
-}
-
-// flagged tracks: literal loop on the same normalised weights, or the cv::RNG random-index
-// fallback when the maximum weight is 0 / NaN.  One thread per track looks at the flag; a flagged track is then
-// worked on by the whole warp (weights staged through shared memory, lane 0 walking them).
-__global__ void __launch_bounds__(128) k_resample_fallback(const double* __restrict__ w_all, long long T, int L, int N,
-                                                            const double* __restrict__ u, int u_stride, int normalise,
-                                                            const double* __restrict__ wsum_in,
-                                                            int32_t* __restrict__ out_all,
-                                                            const uint64_t* __restrict__ seeds, int seed_stride,
-                                                            int seed_off, uint32_t* __restrict__ need_fb,
-                                                            uint32_t* __restrict__ unsorted)
-{
-    constexpr int CH = 512;
-    __shared__ double chunk[4][CH];
-    const long long t0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    bool flagged = false;
-    if (t0 + lane < T) {
-        if (unsorted) unsorted[t0 + lane] = 0u;
-        flagged = need_fb[t0 + lane] != 0u;
-        if (flagged) need_fb[t0 + lane] = 0u;
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, flagged);
-    while (todo) {
-        const long long t = t0 + (__ffs(todo) - 1);
-        todo &= todo - 1;
-        const double* __restrict__ w = w_all + t * L;
-        int32_t* out = out_all + t * N;
-        const double wsum = normalise ? wsum_in[t] : 1.0;
-        auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
-        double mw = 0.0; // NaN-ignoring maximum, as maxWeight (src/pf2DRao.cpp:161-172)
-        for (int i = lane; i < L; i += 32) {
-            const double x = wf(i);
-            if (x > mw) mw = x;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mw = fmax(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-        if (!(mw > 0.0)) {
-            if (lane == 0) {
-                mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
-                (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
-                for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
-                if (unsorted) unsorted[t] = 1u; // random indices are not sorted (matters for the literal alias mode)
-            }
-        } else {
-            mkf_resample_sequential_warp<CH>(wf, L, N, u[t * u_stride], out, chunk[wid]);
-        }
-        __syncwarp();
+        out_all[t0 * N + i] = sm_out[k * LD + tr];
     }
 }
 
@@ -893,6 +864,8 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __res
     using L = SlotLay<D>;
     __shared__ double red[BT / 32][D];
     __shared__ double xb[D];
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
     const long long t = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double acc[D];
@@ -949,11 +922,13 @@ __global__ void __launch_bounds__(128) k_estimate_small(const double2* __restric
     using L = SlotLay<D>;
     constexpr int TPB = 128 / GROUP; // tracks per CTA and trip
     extern __shared__ double coef[]; // [c][r], r < Dpose + D: rows of recon (pose) then rows of tinv (xbar)
+    mkf_pdl_launch_dependents();
     const int R = Dpose + D;
-    for (int i = threadIdx.x; i < R * D; i += 128) {
+    for (int i = threadIdx.x; i < R * D; i += 128) { // model constants: safe before the dependency wait
         const int r = i / D, c = i - r * D;
         coef[c * R + r] = r < Dpose ? recon[r * D + c] : tinv[(r - Dpose) * D + c];
     }
+    mkf_pdl_wait();
     __syncthreads();
     const int g = threadIdx.x / GROUP, l = threadIdx.x % GROUP;
     const double inv_n = 1.0 / (double)N;

@@ -17,7 +17,7 @@ struct mkf_pf2d {
     int cur = 0;
     double *w_raw = nullptr, *wsum = nullptr;
     int32_t* parent = nullptr;
-    uint32_t *status = nullptr, *need_fb = nullptr;
+    uint32_t* status = nullptr;
     double* gmm = nullptr; // K x (d + d*d + 2): mean, sigma_i, det_s, weight
     int gstride = 0;
     DevBuf in_meas, in_u, in_noise, in_part;
@@ -145,7 +145,7 @@ extern "C" void mkf_pf2d_destroy(mkf_pf2d* p)
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->part[0], p->part[1], p->w_raw, p->wsum, p->parent, p->status, p->need_fb, p->gmm};
+    void* ptrs[] = {p->part[0], p->part[1], p->w_raw, p->wsum, p->parent, p->status, p->gmm};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     p->in_meas.release();
@@ -246,7 +246,7 @@ extern "C" int mkf_pf2d_create(mkf_pf2d** out, int64_t T, int N, int d, int K, c
     if ((e = cudaMalloc((void**)&p->part[0], tot * d * 8)) || (e = cudaMalloc((void**)&p->part[1], tot * d * 8)) ||
         (e = cudaMalloc((void**)&p->w_raw, tot * 8)) || (e = cudaMalloc((void**)&p->wsum, (size_t)T * 8)) ||
         (e = cudaMalloc((void**)&p->parent, tot * 4)) || (e = cudaMalloc((void**)&p->status, (size_t)T * 4)) ||
-        (e = cudaMalloc((void**)&p->need_fb, (size_t)T * 4)) || (e = cudaMalloc((void**)&p->gmm, g.size() * 8))) {
+        (e = cudaMalloc((void**)&p->gmm, g.size() * 8))) {
         cudaGetLastError();
         mkf_set_error("mkf_pf2d_create: cudaMalloc failed (%s)", cudaGetErrorString(e));
         mkf_pf2d_destroy(p);
@@ -257,7 +257,6 @@ extern "C" int mkf_pf2d_create(mkf_pf2d** out, int64_t T, int N, int d, int K, c
     cudaMemset(p->wsum, 0, (size_t)T * 8);
     cudaMemset(p->parent, 0, tot * 4);
     cudaMemset(p->status, 0, (size_t)T * 4);
-    cudaMemset(p->need_fb, 0, (size_t)T * 4);
     cudaMemcpy(p->gmm, g.data(), g.size() * 8, cudaMemcpyHostToDevice);
     *out = p;
     return MKF_OK;
@@ -330,7 +329,7 @@ extern "C" int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u,
 #undef LAUNCH_W
     MKF_LAUNCHED();
     CK(cudaGetLastError());
-    if ((rc = run_resample(p->stream, p->T, p->need_fb, p->w_raw, p->N, p->N, d_u, 1, 1, p->wsum, p->parent, p->status,
+    if ((rc = run_resample(p->stream, p->T, p->w_raw, p->N, p->N, d_u, 1, 1, p->wsum, p->parent, p->status,
                            nullptr, 1, 0, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE)))
         return rc;
     if (p->d == 8)

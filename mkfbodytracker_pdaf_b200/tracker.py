@@ -177,8 +177,9 @@ class TrackBatch:
     def sync(self):
         L.check(L.lib.mkf_batch_sync(self._h))
 
-    def profile(self, max_updates):
-        L.check(L.lib.mkf_batch_profile(self._h, int(max_updates)))
+    def profile(self, max_updates, every=1):
+        """arm per-stage CUDA-event timing of update(): up to max_updates samples, one every `every` updates"""
+        L.check(L.lib.mkf_batch_profile_every(self._h, int(max_updates), int(every)))
 
     def profile_read(self):
         a, b_, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
