@@ -331,6 +331,7 @@ def main():
         ea.record()
         for f in range(W, F):
             e2e_step(f, mem)
+        batch.join()  # the closing event waits for the copies on the library's internal copy streams too
         eb.record()
         barrier()
         t_ms = torch.tensor([ea.elapsed_time(eb)], dtype=torch.float64, device=dev)
@@ -372,7 +373,7 @@ def main():
                                       "normalise_resample": prof["ms_resample"] / max(prof["n"], 1)}},
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": world * T * 8 * 8, "d2h_bytes_per_step": world * T * model.D * 8,
-                    "mode": "pinned host buffers, copies ordered on the stream, one sync at the end",
+                    "mode": "pinned host buffers, MKF_MEM_HOST_ASYNC: copies on the library's copy streams overlap the neighbouring frames' kernels, one sync at the end",
                     "sync_every_step": {"value": world * T * K / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / K}},
             "gpu_launches": int(launches), "clocks": clocks,
             "status_flagged_tracks": status_bad, "pose_check": pose_check, "gathered_rows": int(gathered.shape[0]),

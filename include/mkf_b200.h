@@ -59,9 +59,12 @@ extern "C" {
 #define MKF_MEM_AUTO 0 /* ask the driver (cudaPointerGetAttributes) */
 #define MKF_MEM_HOST 1
 #define MKF_MEM_DEVICE 2
-#define MKF_MEM_HOST_ASYNC 3 /* PINNED host memory, no synchronisation: the copies are ordered on the batch's
-                                stream and the caller waits (mkf_batch_sync) before touching the buffers;
-                                honoured by mkf_batch_update and mkf_batch_estimate */
+#define MKF_MEM_HOST_ASYNC 3 /* PINNED host memory, no synchronisation; honoured by mkf_batch_update and
+                                mkf_batch_estimate.  Inputs must hold their values when the call is made; the
+                                library copies them on an internal copy stream (overlapping the previous frame's
+                                kernels), orders its kernels after them, and copies results back on a second
+                                internal stream.  The caller waits (mkf_batch_sync, which drains all three
+                                streams) before reusing the input buffers or reading the outputs. */
 
 /* measurement layouts accepted by mkf_batch_update */
 #define MKF_MEAS_SHARED 0   /* T x 6       : one column per track, replicated to its N slots */
@@ -122,6 +125,9 @@ int mkf_model_get(const mkf_model* m, double* means, double* covs, double* weigh
 int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, int N, int device, void* stream);
 void mkf_batch_destroy(mkf_batch* b);
 int mkf_batch_sync(mkf_batch* b);
+/* orders the batch's stream after every MKF_MEM_HOST_ASYNC copy issued so far (device-side waits, no host
+ * synchronisation): work or events the caller enqueues on that stream afterwards see all results delivered */
+int mkf_batch_join(mkf_batch* b);
 
 /* bins = resample(gmm.weight, N); gmm.resetTracker(bins)  (src/pfPose.cpp:68-71, src/my_gmm.cpp:30-42).
  * u_init: T uniform draws in [0,1). */

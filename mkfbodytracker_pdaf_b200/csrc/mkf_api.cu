@@ -89,6 +89,55 @@ struct DevBuf {
     }
 };
 
+// MKF_MEM_HOST_ASYNC pipeline: host->device copies of an update run on their own stream into double-buffered
+// staging, so the copies of frame f+1 overlap the kernels of frame f; the device->host copy of an estimate runs on a
+// third stream and overlaps the next frame's kernels.  Events order the three streams; mkf_batch_sync drains all.
+struct AsyncIo {
+    bool ready = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    int in_slot = 0, out_slot = 0;
+    DevBuf in_meas[2], in_u0[2], in_u1[2], in_seed[2], out_a[2], out_b[2];
+    cudaEvent_t in_done[2] = {nullptr, nullptr};   // copies into slot finished            (recorded on s_in)
+    cudaEvent_t in_free[2] = {nullptr, nullptr};   // kernels that read slot finished      (recorded on the batch stream)
+    cudaEvent_t out_ready[2] = {nullptr, nullptr}; // estimate wrote slot                  (recorded on the batch stream)
+    cudaEvent_t out_done[2] = {nullptr, nullptr};  // copy of slot to the host finished    (recorded on s_out)
+    bool in_used[2] = {false, false}, out_used[2] = {false, false};
+    int init()
+    {
+        if (ready) return MKF_OK;
+        if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) {
+            mkf_set_error("cudaStreamCreate failed");
+            return MKF_E_CUDA;
+        }
+        cudaEvent_t* ev[] = {in_done, in_free, out_ready, out_done};
+        for (cudaEvent_t* e : ev)
+            for (int i = 0; i < 2; i++)
+                if (cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) != cudaSuccess) {
+                    mkf_set_error("cudaEventCreate failed");
+                    return MKF_E_CUDA;
+                }
+        ready = true;
+        return MKF_OK;
+    }
+    void release()
+    {
+        if (s_in) cudaStreamSynchronize(s_in);
+        if (s_out) cudaStreamSynchronize(s_out);
+        DevBuf* bufs[] = {in_meas, in_u0, in_u1, in_seed, out_a, out_b};
+        for (DevBuf* d : bufs)
+            for (int i = 0; i < 2; i++) d[i].release();
+        cudaEvent_t* ev[] = {in_done, in_free, out_ready, out_done};
+        for (cudaEvent_t* e : ev)
+            for (int i = 0; i < 2; i++)
+                if (e[i]) cudaEventDestroy(e[i]);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+        s_in = s_out = nullptr;
+        ready = false;
+    }
+};
+
 struct mkf_batch {
     const mkf_model* m = nullptr;
     long long T = 0;
@@ -112,6 +161,7 @@ struct mkf_batch {
            *d_recon = nullptr, *d_pmean = nullptr, *d_tm = nullptr, *d_tinv = nullptr;
     // staging
     DevBuf in_meas, in_u0, in_u1, in_seed, out_a, out_b, in_x, in_p;
+    AsyncIo aio;
     // association scratch (arm0 owns)
     DevBuf as_cand, as_L, as_roi, as_u, as_w, as_gate, as_bins, as_meas, as_wsum, as_hand, as_status, as_seed,
         as_ui, as_up;
@@ -208,6 +258,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
                       &b->as_meas, &b->as_wsum, &b->as_hand, &b->as_status, &b->as_seed,
                       &b->as_ui,   &b->as_up};
     for (DevBuf* d : bufs) d->release();
+    b->aio.release();
     for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -307,6 +358,26 @@ extern "C" int mkf_batch_sync(mkf_batch* b)
     }
     CK(cudaSetDevice(b->device));
     CK(cudaStreamSynchronize(b->stream));
+    if (b->aio.ready) {
+        CK(cudaStreamSynchronize(b->aio.s_in));
+        CK(cudaStreamSynchronize(b->aio.s_out));
+    }
+    return MKF_OK;
+}
+
+extern "C" int mkf_batch_join(mkf_batch* b)
+{
+    if (!b) {
+        mkf_set_error("null batch");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    AsyncIo& io = b->aio;
+    if (!io.ready) return MKF_OK;
+    for (int i = 0; i < 2; i++) {
+        if (io.in_used[i]) CK(cudaStreamWaitEvent(b->stream, io.in_done[i], 0));
+        if (io.out_used[i]) CK(cudaStreamWaitEvent(b->stream, io.out_done[i], 0));
+    }
     return MKF_OK;
 }
 
@@ -539,6 +610,35 @@ extern "C" int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layou
     const double *d_meas, *d_ui, *d_up;
     const uint64_t* d_seeds;
     int rc;
+    if (mem == MKF_MEM_HOST_ASYNC) {
+        // host inputs (ready at call time) travel on the copy stream into the staging slot of this frame
+        AsyncIo& io = b->aio;
+        if ((rc = io.init())) return rc;
+        const int sl = io.in_slot;
+        io.in_slot ^= 1;
+        if (io.in_used[sl]) CK(cudaStreamWaitEvent(io.s_in, io.in_free[sl], 0));
+        auto stage = [&](const void* src, size_t bytes, DevBuf& buf, const void** out) -> int {
+            *out = nullptr;
+            if (!src) return MKF_OK;
+            int r = buf.ensure(bytes);
+            if (r) return r;
+            CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, io.s_in));
+            *out = buf.p;
+            return MKF_OK;
+        };
+        if ((rc = stage(meas, nmeas * 8, io.in_meas[sl], (const void**)&d_meas)) ||
+            (rc = stage(u_ind, (size_t)b->T * 8, io.in_u0[sl], (const void**)&d_ui)) ||
+            (rc = stage(u_post, (size_t)b->T * 8, io.in_u1[sl], (const void**)&d_up)) ||
+            (rc = stage(seeds, (size_t)b->T * 16, io.in_seed[sl], (const void**)&d_seeds)))
+            return rc;
+        CK(cudaEventRecord(io.in_done[sl], io.s_in));
+        CK(cudaStreamWaitEvent(b->stream, io.in_done[sl], 0));
+        CK(cudaMemsetAsync(b->status, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
+        rc = update_device(b, d_meas, meas_layout, d_ui, d_up, 1, d_seeds, 2, 1);
+        CK(cudaEventRecord(io.in_free[sl], b->stream));
+        io.in_used[sl] = true;
+        return rc;
+    }
     if ((rc = in_ptr(b, meas, nmeas, mem, b->in_meas, &d_meas))) return rc;
     if ((rc = in_ptr(b, u_ind, (size_t)b->T, mem, b->in_u0, &d_ui))) return rc;
     if ((rc = in_ptr(b, u_post, (size_t)b->T, mem, b->in_u1, &d_up))) return rc;
@@ -599,6 +699,26 @@ extern "C" int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int 
     const mkf_model* m = b->m;
     OutPtr<double> ox, op;
     int rc;
+    if (mem == MKF_MEM_HOST_ASYNC) {
+        // the kernel writes this call's staging slot; the copy to the host runs on the output stream
+        AsyncIo& io = b->aio;
+        if ((rc = io.init())) return rc;
+        const int sl = io.out_slot;
+        io.out_slot ^= 1;
+        const size_t nx = (size_t)b->T * m->d * 8, np = (size_t)b->T * m->D * 8;
+        if (xbar && (rc = io.out_a[sl].ensure(nx))) return rc;
+        if (pose && (rc = io.out_b[sl].ensure(np))) return rc;
+        if (io.out_used[sl]) CK(cudaStreamWaitEvent(b->stream, io.out_done[sl], 0));
+        if ((rc = launch_estimate(b, xbar ? (double*)io.out_a[sl].p : nullptr, pose ? (double*)io.out_b[sl].p : nullptr)))
+            return rc;
+        CK(cudaEventRecord(io.out_ready[sl], b->stream));
+        CK(cudaStreamWaitEvent(io.s_out, io.out_ready[sl], 0));
+        if (xbar) CK(cudaMemcpyAsync(xbar, io.out_a[sl].p, nx, cudaMemcpyDeviceToHost, io.s_out));
+        if (pose) CK(cudaMemcpyAsync(pose, io.out_b[sl].p, np, cudaMemcpyDeviceToHost, io.s_out));
+        CK(cudaEventRecord(io.out_done[sl], io.s_out));
+        io.out_used[sl] = true;
+        return MKF_OK;
+    }
     if ((rc = ox.init(b, xbar, (size_t)b->T * m->d, mem, b->out_a))) return rc;
     if ((rc = op.init(b, pose, (size_t)b->T * m->D, mem, b->out_b))) return rc;
     if ((rc = launch_estimate(b, ox.devp, op.devp))) return rc;

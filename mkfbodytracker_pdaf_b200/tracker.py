@@ -129,8 +129,8 @@ class TrackBatch:
         L.check(L.lib.mkf_batch_estimate(self._h, xbar.ctypes.data, pose.ctypes.data, L.MEM_HOST))
         return xbar, pose
 
-    def estimate_into(self, xbar, pose):
-        mem = _same_mem(xbar, pose)
+    def estimate_into(self, xbar, pose, mem=None):
+        mem = _same_mem(xbar, pose) if mem is None else mem
         L.check(L.lib.mkf_batch_estimate(self._h, _addr(xbar)[0], _addr(pose)[0], mem))
 
     def download(self, state=True, cov=True):
@@ -176,6 +176,10 @@ class TrackBatch:
 
     def sync(self):
         L.check(L.lib.mkf_batch_sync(self._h))
+
+    def join(self):
+        """order the batch's stream after all MEM_HOST_ASYNC copies issued so far (no host synchronisation)"""
+        L.check(L.lib.mkf_batch_join(self._h))
 
     def profile(self, max_updates, every=1):
         """arm per-stage CUDA-event timing of update(): up to max_updates samples, one every `every` updates"""
