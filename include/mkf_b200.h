@@ -241,6 +241,13 @@ int mkf_batch_profile_every(mkf_batch* b, int max_samples, int every);
 int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_update, double* ms_resample,
                            int* n_updates);
 
+/* Record sharing.  When the slots of a track see one measurement (MKF_MEAS_SHARED, MKF_ALIAS_INDEPENDENT), children
+ * that drew the same parent and the same component are bit-identical Gaussians; the device computes and stores such a
+ * group once per warp and lets its slots refer to the one record.  Nothing observable changes (per-slot weights,
+ * parents, states and estimates are those of N independent slots); this call reports how many distinct records the
+ * last update stored for how many slots. */
+int mkf_batch_shared_records(mkf_batch* b, int64_t* records, int64_t* slots);
+
 /* number of kernel launches issued through this library since load (bench.py "gpu_launches") */
 uint64_t mkf_launch_count(void);
 

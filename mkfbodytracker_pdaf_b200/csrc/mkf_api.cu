@@ -150,6 +150,12 @@ struct mkf_batch {
     double2* st[2] = {nullptr, nullptr};
     int cur = 0; // st[cur] holds the children of the last update (read through `parent`)
     int32_t* parent = nullptr;
+    // record sharing (k_slot_update<.., DEDUP>): rep[slot] = record of st[cur] holding the slot's state, written by
+    // the slot kernel; src[slot] = rep[parent[slot]], written by the resampler.  shared == false: src is `parent`.
+    int32_t *rep = nullptr, *src = nullptr;
+    bool shared = false; // the children of the last update share records (read state through src, not parent)
+    bool dedup_ok = true; // MKF_DEDUP=0 in the environment turns the sharing off (A/B measurements)
+    const int32_t* gather_index() const { return shared ? src : parent; }
     int32_t* bounds = nullptr;
     double* w_raw = nullptr;
     double* wsum = nullptr;
@@ -249,7 +255,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->bounds, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->bounds, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -320,6 +326,13 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     for (int i = 0; i < 2; i++)
         if ((rc = dmalloc((void**)&b->st[i], (size_t)b->n_tiles * tile_bytes))) return fail(rc);
     if ((rc = dmalloc((void**)&b->parent, (size_t)b->total * sizeof(int32_t)))) return fail(rc);
+    {
+        const char* e = getenv("MKF_DEDUP");
+        b->dedup_ok = !(e && e[0] == '0') && m->prm.alias_mode == MKF_ALIAS_INDEPENDENT;
+    }
+    if (b->dedup_ok && ((rc = dmalloc((void**)&b->rep, (size_t)b->total * sizeof(int32_t))) ||
+                        (rc = dmalloc((void**)&b->src, (size_t)b->total * sizeof(int32_t)))))
+        return fail(rc);
     if ((rc = dmalloc((void**)&b->bounds, (size_t)T * (m->K + 2) * sizeof(int32_t)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->w_raw, (size_t)b->total * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->wsum, (size_t)T * sizeof(double)))) return fail(rc);
@@ -362,6 +375,42 @@ extern "C" int mkf_batch_sync(mkf_batch* b)
         CK(cudaStreamSynchronize(b->aio.s_in));
         CK(cudaStreamSynchronize(b->aio.s_out));
     }
+    return MKF_OK;
+}
+
+__global__ void k_count_records(const int32_t* __restrict__ rep, long long total, int N, unsigned long long* out)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool first = false;
+    if (s < total) first = (s % N == 0) || rep[s] != rep[s - 1]; // rep is non-decreasing within a track
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+extern "C" int mkf_batch_shared_records(mkf_batch* b, int64_t* records, int64_t* slots)
+{
+    if (!b || !records || !slots) {
+        mkf_set_error("mkf_batch_shared_records: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    *slots = b->total;
+    *records = b->total;
+    if (!b->shared) return MKF_OK;
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, 8));
+    CK(cudaMemsetAsync(d, 0, 8, b->stream));
+    k_count_records<<<(unsigned)((b->total + 255) / 256), 256, 0, b->stream>>>(b->rep, b->total, b->N, d);
+    MKF_LAUNCHED();
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        mkf_set_error("mkf_batch_shared_records: %s", cudaGetErrorString(e));
+        return MKF_E_CUDA;
+    }
+    *records = (int64_t)h;
     return MKF_OK;
 }
 
@@ -414,6 +463,7 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if ((rc = launch_bounds_kernel(b, d_u))) return rc;
     b->cur = 0;
+    b->shared = false;
     if (b->m->d == 12)
         k_reset<12><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
                                                                     b->total, b->N, b->m->K);
@@ -438,7 +488,7 @@ static bool first_on_this_device(std::atomic<uint64_t>& seen)
 static int run_resample(cudaStream_t stream, long long nt, const double* d_w, int L, int N, const double* d_u,
                         int u_stride, int normalise, double* d_wsum, int32_t* d_out, uint32_t* d_status,
                         const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb, uint32_t bit_deg,
-                        uint32_t* d_unsorted = nullptr)
+                        uint32_t* d_unsorted = nullptr, const int32_t* d_rep = nullptr, int32_t* d_src = nullptr)
 {
     if (L <= 64 && N <= 64) {
         const size_t smem = (size_t)129 * ((size_t)L * 8 + (size_t)N * 4); // <= 99 KB at L = N = 64
@@ -446,13 +496,13 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
         if (first_on_this_device(seen))
             CK(cudaFuncSetAttribute(k_resample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         mkf_launch(k_resample_small, grid_for(nt, 128), 128, smem, stream, d_w, nt, L, N, d_u, u_stride, normalise, d_wsum,
-                   d_out, d_status, 1, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted);
+                   d_out, d_status, 1, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src);
     } else {
         // one CTA per track; wider CTAs for long weight / index vectors so a track's tiles are few
         const int span = L > N ? L : N;
 #define MKF_RS_BLOCK(BT)                                                                                             \
     mkf_launch(k_resample_block<BT, 4>, (unsigned)nt, BT, 0, stream, d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out, \
-               d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted)
+               d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src)
         if (span <= 1024)
             MKF_RS_BLOCK(128);
         else if (span <= 8192)
@@ -486,6 +536,14 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     a.st_in = b->st[b->cur];
     a.st_out = b->st[b->cur ^ 1];
     a.parent = b->parent;
+    a.src = b->gather_index();
+    // identical children exist only when the slots of a track see one measurement (and never in the literal alias
+    // mode, where duplicates are filtered one after the other)
+    // Worth it when a component owns several slots of a track (N >= 4 K); at N = K = 15 nearly every slot is its own
+    // (parent, component) pair and the bookkeeping costs more than it saves (measured: 3.65 -> 4.15 ms at 1 M x 15).
+    const bool dedup = b->dedup_ok && meas_layout == MKF_MEAS_SHARED && b->stage == 3 && b->N >= 4 * m->K;
+    a.dedup = dedup ? 1 : 0;
+    a.rep = dedup ? b->rep : nullptr;
     a.bounds = b->bounds;
     a.meas = d_meas;
     a.comp_const = b->d_comp;
@@ -505,23 +563,55 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     {
         static std::atomic<uint64_t> seen{0};
         if (smem > 48 * 1024 && first_on_this_device(seen)) {
-            CK(cudaFuncSetAttribute(k_slot_update<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_slot_update<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_slot_update<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_slot_update<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define MKF_SLOT_ATTR(DD, CH)                                                                                     \
+    CK(cudaFuncSetAttribute(k_slot_update<DD, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024))
+            MKF_SLOT_ATTR(12, false);
+            MKF_SLOT_ATTR(12, true);
+            MKF_SLOT_ATTR(10, false);
+            MKF_SLOT_ATTR(10, true);
+#undef MKF_SLOT_ATTR
         }
         const unsigned g = grid_for(b->total, 128);
-        if (m->d == 12) {
-            if (a.alias_chain)
-                mkf_launch(k_slot_update<12, true>, g, 128, smem, b->stream, a);
-            else
-                mkf_launch(k_slot_update<12, false>, g, 128, smem, b->stream, a);
-        } else {
-            if (a.alias_chain)
-                mkf_launch(k_slot_update<10, true>, g, 128, smem, b->stream, a);
-            else
-                mkf_launch(k_slot_update<10, false>, g, 128, smem, b->stream, a);
+        // slots per CTA of the record-sharing kernel = 128 * share_g (MKF_SHARE_G overrides for experiments)
+        static const int share_g = [] {
+            const char* e = getenv("MKF_SHARE_G");
+            const int v = e ? atoi(e) : 8;
+            return (v == 4 || v == 8 || v == 16) ? v : 8;
+        }();
+        const size_t smem_shared = smem + (size_t)128 * share_g * (8 + 4 * 4 + 1);
+        static std::atomic<uint64_t> seen_shared{0};
+        if (dedup && smem_shared > 48 * 1024 && first_on_this_device(seen_shared)) {
+#define MKF_SHARED_ATTR(DD, GG)                                                                                        \
+    CK(cudaFuncSetAttribute(k_slot_update_shared<DD, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024))
+            MKF_SHARED_ATTR(12, 4);
+            MKF_SHARED_ATTR(12, 8);
+            MKF_SHARED_ATTR(12, 16);
+            MKF_SHARED_ATTR(10, 4);
+            MKF_SHARED_ATTR(10, 8);
+            MKF_SHARED_ATTR(10, 16);
+#undef MKF_SHARED_ATTR
         }
+#define MKF_SHARED_LAUNCH(DD, GG)                                                                                      \
+    mkf_launch(k_slot_update_shared<DD, GG>, grid_for(b->total, 128 * GG), 128, smem_shared, b->stream, a)
+#define MKF_SLOT_LAUNCH(DD)                                                            \
+    do {                                                                               \
+        if (a.alias_chain)                                                             \
+            mkf_launch(k_slot_update<DD, true>, g, 128, smem, b->stream, a);    \
+        else if (dedup && share_g == 4)                                                \
+            MKF_SHARED_LAUNCH(DD, 4);                                                  \
+        else if (dedup && share_g == 8)                                                \
+            MKF_SHARED_LAUNCH(DD, 8);                                                  \
+        else if (dedup)                                                                \
+            MKF_SHARED_LAUNCH(DD, 16);                                                 \
+        else                                                                           \
+            mkf_launch(k_slot_update<DD, false>, g, 128, smem, b->stream, a);   \
+    } while (0)
+        if (m->d == 12)
+            MKF_SLOT_LAUNCH(12);
+        else
+            MKF_SLOT_LAUNCH(10);
+#undef MKF_SLOT_LAUNCH
+#undef MKF_SHARED_LAUNCH
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
@@ -535,7 +625,9 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     if (prof) cudaEventRecord(pe[2], b->stream);
     b->cur ^= 1;
     rc = run_resample(b->stream, b->T, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status,
-                      d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE, b->unsorted);
+                      d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE, b->unsorted,
+                      dedup ? b->rep : nullptr, dedup ? b->src : nullptr);
+    b->shared = dedup;
     if (prof) {
         cudaEventRecord(pe[3], b->stream);
         b->prof_n++;
@@ -658,7 +750,7 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
     // enough tracks to fill the GPU several times over; small batches keep one trip so that they still spread out
 #define MKF_EST_SMALL(G, TR)                                                                                  \
     mkf_launch(k_estimate_small<DD, G, TR>, grid_for(b->T, TR * 128 / G), 128, coef_bytes, b->stream,                 \
-        st, b->parent, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose)
+        st, b->gather_index(), b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose)
     if (b->N <= 16) {
         if (b->T >= 8 * 8 * 4 * 148)
             MKF_EST_SMALL(16, 8);
@@ -672,10 +764,10 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
     }
 #undef MKF_EST_SMALL
     else if (b->N <= 2048)
-        mkf_launch(k_estimate<DD, 128>, (unsigned)b->T, 128, 0, b->stream, st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
+        mkf_launch(k_estimate<DD, 128>, (unsigned)b->T, 128, 0, b->stream, st, b->gather_index(), b->N, m->D, b->d_recon, b->d_pmean,
                                                                    b->d_tinv, d_xbar, d_pose);
     else // long tracks: more loads in flight per track (BT = 512 is slower at N = 500: 64 vs 41 us at 4096 tracks)
-        mkf_launch(k_estimate<DD, 512>, (unsigned)b->T, 512, 0, b->stream, st, b->parent, b->N, m->D, b->d_recon, b->d_pmean,
+        mkf_launch(k_estimate<DD, 512>, (unsigned)b->T, 512, 0, b->stream, st, b->gather_index(), b->N, m->D, b->d_recon, b->d_pmean,
                                                                    b->d_tinv, d_xbar, d_pose);
 }
 static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
@@ -754,10 +846,10 @@ extern "C" int mkf_batch_download(mkf_batch* b, double* x, double* P, double* w_
         return done(rc);
     if (x || P) {
         if (d == 12)
-            k_download<12><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[b->cur], b->parent, b->d_tinv, ox.devp,
+            k_download<12><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[b->cur], b->gather_index(), b->d_tinv, ox.devp,
                                                                           op.devp, b->total, b->N);
         else
-            k_download<10><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[b->cur], b->parent, b->d_tinv, ox.devp,
+            k_download<10><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[b->cur], b->gather_index(), b->d_tinv, ox.devp,
                                                                           op.devp, b->total, b->N);
         MKF_LAUNCHED();
         if (cudaGetLastError() != cudaSuccess) {
@@ -809,6 +901,7 @@ extern "C" int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, 
     if ((rc = in_ptr(b, x, (size_t)b->total * d, mem, b->in_x, &dx))) return rc;
     if ((rc = in_ptr(b, P, (size_t)b->total * d * d, mem, b->in_p, &dP))) return rc;
     b->cur = 0;
+    b->shared = false;
     CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if (d == 12)
         k_upload<12><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[0], b->parent, dx, dP, b->d_tm, b->total, b->N);

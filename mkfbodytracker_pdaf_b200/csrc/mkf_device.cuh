@@ -151,8 +151,8 @@ __device__ __forceinline__ void mkf_resample_sequential(WF w, int L, int N, doub
 // CH at a time, lane 0 walks them.  The arithmetic and its order are those of mkf_resample_sequential; only the
 // latency of the dependent weight loads changes (a flagged 65 536-slot track took 43 ms with one thread reading
 // global memory).  `chunk` holds CH doubles private to the warp.
-template <int CH, class WF>
-__device__ __forceinline__ void mkf_resample_sequential_warp(WF w, int L, int N, double u, int32_t* out, double* chunk)
+template <int CH, class WF, class OF>
+__device__ __forceinline__ void mkf_resample_sequential_warp(WF w, int L, int N, double u, OF out, double* chunk)
 {
     const int lane = threadIdx.x & 31;
     const double step = __ddiv_rn(1.0, (double)N);
@@ -171,7 +171,7 @@ __device__ __forceinline__ void mkf_resample_sequential_warp(WF w, int L, int N,
                     wi = chunk[idx - base];
                 } else {
                     beta = __dadd_rn(beta, step);
-                    out[i++] = idx;
+                    out(i++, idx);
                 }
             }
         }

@@ -65,6 +65,9 @@ extern "C" int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int 
     a.st_in = b->st[b->cur];
     a.st_out = b->st[b->cur ^ 1];
     a.parent = b->parent;
+    a.src = b->parent;
+    a.rep = nullptr;
+    a.dedup = 0;
     a.bounds = b->bounds;
     a.meas = (const double*)dz.p;
     a.comp_const = b->d_comp;

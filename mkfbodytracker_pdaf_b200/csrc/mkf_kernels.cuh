@@ -44,6 +44,11 @@ struct SlotArgs {
     const double2* __restrict__ st_in;
     double2* __restrict__ st_out;
     const int32_t* __restrict__ parent; // T*N, local index of the parent slot
+    const int32_t* __restrict__ src;    // T*N, local index of the RECORD in st_in that holds the parent's state
+                                        // (== parent unless the previous frame stored identical children once)
+    int32_t* __restrict__ rep;          // T*N out (dedup only): local index of the record in st_out holding this slot
+    int dedup;                          // 1: identical children (same parent record, component, track measurement)
+                                        //    are computed and stored once per warp
     const int32_t* __restrict__ bounds; // T x (K+2): e_0..e_{K-1}, wrap_from, wrap_k
     const double* __restrict__ meas;
     const double* __restrict__ comp_const; // K x CS (global; staged to shared memory by TMA)
@@ -370,17 +375,18 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
     int k = 0, j = 0, len = 1;
     long long t = 0;
     const int32_t* __restrict__ bt = nullptr;
+
     if (active) {
         t = s / a.N;
         j = (int)(s - t * a.N);
-        const int par = __ldg(a.parent + s);
+        const int par = __ldg(a.src + s);
         if (CHAIN) {
             if (a.unsorted[t]) {
                 active = false; // unsorted parents (random-index fallback): k_slot_update_repair walks the track
-            } else if (j > 0 && __ldg(a.parent + s - 1) == par) {
+            } else if (j > 0 && __ldg(a.src + s - 1) == par) {
                 active = false; // not the first slot of its run
             } else {
-                while (j + len < a.N && __ldg(a.parent + s + len) == par) len++;
+                while (j + len < a.N && __ldg(a.src + s + len) == par) len++;
             }
         }
         if (active) {
@@ -435,6 +441,137 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// Slot update with record sharing (MKF_ALIAS_INDEPENDENT, one measurement per track).
+// Children of one parent RECORD that drew the same component are bit-identical Gaussians, and because resampled parents
+// are sorted they are consecutive slots.  A CTA takes CHUNK = 128 G consecutive slots:
+//   A  every slot's key (track, parent record, component) goes to shared memory; a slot whose key differs from its
+//      predecessor's is a HEAD; a block scan numbers the heads;
+//   B  the heads -- and only they, packed into full warps -- gather the parent record, run the slot arithmetic and
+//      store the child record.  Records of one track are packed from the track's first slot in the chunk onwards, so
+//      the next frame gathers from dense sectors;
+//   C  every slot takes its head's weight and notes in rep[] which record holds its state.
+// In steady state the 4096 x 500 benchmark keeps ~11 % distinct records.  (A first version shared per warp -- head
+// lanes compute, the others take the weight by shuffle: it saved the DRAM traffic but still issued every warp's
+// arithmetic for a few live lanes, ncu: 10 of 32 lanes active, 0.306 ms; packing the heads of a whole chunk into
+// full warps makes the arithmetic shrink with the number of distinct Gaussians as well.)
+// -----------------------------------------------------------------------------------------
+template <int D, int G>
+__global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
+{
+    using L = SlotLay<D>;
+    constexpr int CHUNK = 128 * G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cst = reinterpret_cast<double*>(smem_raw);
+    double* h_w = cst + a.K * L::CS;                          // [CHUNK] weight of head h
+    int* sm_par = reinterpret_cast<int*>(h_w + CHUNK);        // [CHUNK] per slot: parent record
+    int* sm_t = sm_par + CHUNK;                               // [CHUNK] per slot: track (-1 beyond the end)
+    int* sm_rank = sm_t + CHUNK;                              // [CHUNK] per slot: index of its head
+    int* h_slot = sm_rank + CHUNK;                            // [CHUNK] head h -> its slot offset in the chunk
+    unsigned char* sm_k = reinterpret_cast<unsigned char*>(h_slot + CHUNK); // [CHUNK] per slot: component
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int warp_tot[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t cbytes = (uint32_t)(a.K * L::CS * sizeof(double));
+    if (tid == 0) mkf_mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mkf_mbar_expect_tx(&mbar, cbytes);
+        mkf_tma_load_1d(cst, a.comp_const, cbytes, &mbar); // model constants: never written by the frame chain
+    }
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+
+    const long long base = (long long)blockIdx.x * CHUNK;
+    // ---- A: keys
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int so = g * 128 + tid;
+        const long long s = base + so;
+        int par = -1, tl = -1, k = 0;
+        if (s < a.total) {
+            tl = (int)((unsigned)s / (unsigned)a.N); // T*N < 2^32: 180 GB hold at most 1.25e8 slots
+            const int j = (int)((unsigned)s - (unsigned)tl * (unsigned)a.N);
+            par = __ldg(a.src + s);
+            k = mkf_component_of(a.bounds + (long long)tl * (a.K + 2), a.K, j);
+        }
+        sm_par[so] = par;
+        sm_t[so] = tl;
+        sm_k[so] = (unsigned char)k;
+    }
+    __syncthreads();
+    // heads, numbered in slot order (G block scans with a running carry)
+    int carry = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int so = g * 128 + tid;
+        const bool live = sm_t[so] >= 0;
+        const bool head = live && (so == 0 || sm_par[so] != sm_par[so - 1] || sm_k[so] != sm_k[so - 1] ||
+                                   sm_t[so] != sm_t[so - 1]);
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int before = carry;
+        for (int w = 0; w < wid; w++) before += warp_tot[w];
+        const int incl = before + __popc(bal & (0xffffffffu >> (31 - lane))); // heads up to and including this slot
+        carry += warp_tot[0] + warp_tot[1] + warp_tot[2] + warp_tot[3];
+        sm_rank[so] = incl - 1;
+        if (head) h_slot[incl - 1] = so;
+        __syncthreads();
+    }
+    const int H = carry;
+
+    // ---- B: one thread per head
+    mkf_mbar_wait(&mbar, 0);
+    for (int h = tid; h < H; h += 128) {
+        const int so = h_slot[h];
+        const long long s = base + so;
+        const long long t = sm_t[so];
+        const int j = (int)(s - t * a.N);
+        const int k = sm_k[so];
+        const long long sp = t * a.N + sm_par[so];
+        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+        double v[L::NE];
+#pragma unroll
+        for (int p = 0; p < L::NP; p++) {
+            const double2 q = __ldg(src + p * 32);
+            v[2 * p] = q.x;
+            if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+        }
+        double zc[MKF_M];
+        mkf_load_meas(a, t, j, zc);
+        double w;
+        const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+        if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+        // record position: the track's first slot in this chunk + the head's number within the track
+        const long long seg = t * a.N > base ? t * a.N - base : 0;
+        const long long so_rec = base + seg + (h - sm_rank[(int)seg]);
+        double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)(L::NP * 32) + (so_rec & 31);
+#pragma unroll
+        for (int p = 0; p < L::NP; p++) {
+            double2 q;
+            q.x = v[2 * p];
+            q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+            __stcs(dst + p * 32, q);
+        }
+        h_w[h] = w;
+    }
+    __syncthreads();
+
+    // ---- C: per-slot outputs
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int so = g * 128 + tid;
+        const long long t = sm_t[so];
+        if (t < 0) continue;
+        const int h = sm_rank[so];
+        const long long seg = t * a.N > base ? t * a.N - base : 0;
+        a.w_raw[base + so] = h_w[h];
+        a.rep[base + so] = (int)(base + seg + (h - sm_rank[(int)seg]) - t * a.N);
+    }
+}
+
 // Rare tracks redone after k_slot_update: (i) a cv::Cholesky failure was flagged (literal failure semantics
 // through slot_math<SLOW>), (ii) literal alias mode with UNSORTED parents (after the degenerate random-index
 // fallback of src/pf2DRao.cpp:184-192 the slots sharing a parent are not adjacent).  One CTA scans 128
@@ -469,7 +606,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
         if (!a.alias_chain || threadIdx.x == 0) {
             for (int j = j0; j < a.N; j += jstep) {
                 const long long s = t * a.N + j;
-                const int par = a.parent[s];
+                const int par = a.src[s];
                 const int snap = a.alias_chain ? lt[par] : -1;
                 const double2* base_p = snap >= 0 ? (const double2*)a.st_out : a.st_in;
                 const long long sp = t * a.N + (snap >= 0 ? snap : par);
@@ -492,6 +629,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
                     dst[p * 32] = qq;
                 }
                 a.w_raw[s] = w;
+                if (a.dedup) a.rep[s] = j; // the redone track stores every slot at its own position
                 if (a.alias_chain) lt[par] = j;
             }
         }
@@ -640,8 +778,12 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
                                                         uint32_t* __restrict__ status, int status_stride,
                                                         uint32_t bit_fb, uint32_t bit_deg,
                                                         const uint64_t* __restrict__ seeds, int seed_stride,
-                                                        int seed_off, uint32_t* __restrict__ unsorted)
+                                                        int seed_off, uint32_t* __restrict__ unsorted,
+                                                        const int32_t* __restrict__ rep_all,
+                                                        int32_t* __restrict__ src_all)
 {
+    // rep_all / src_all (both or neither): besides the parent SLOT of every output, also write the RECORD that holds
+    // that slot's state, src = rep[parent] (k_slot_update with dedup stores identical children once)
     constexpr int CH = 512;
     __shared__ int sc_i[BT / 32];
     __shared__ double sc_d[BT / 32], sc_d2[BT / 32], sc_d3[BT / 32];
@@ -653,6 +795,8 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double* __restrict__ w = w_all + t * L;
     int32_t* __restrict__ out = out_all + t * N;
+    const int32_t* __restrict__ rep = rep_all ? rep_all + t * L : nullptr;
+    int32_t* __restrict__ src = rep_all ? src_all + t * N : nullptr;
     if (tid == 0 && unsorted) unsorted[t] = 0u;
 
     // pass 1: sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172).  The sum only has to be an accurate
@@ -696,7 +840,11 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
             atomicOr(status + t * status_stride, bit_deg);
             mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
             (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
-            for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
+            for (int i = 0; i < N; i++) {
+                const int idx = rng.uniform_int(0, L);
+                out[i] = idx;
+                if (rep) src[i] = rep[idx];
+            }
             if (unsorted) unsorted[t] = 1u; // random indices are not sorted (matters for the literal alias mode)
         }
         return;
@@ -769,7 +917,12 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
             if (tid == 0) atomicOr(status + t * status_stride, bit_fb);
             if (wid == 0) {
                 auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
-                mkf_resample_sequential_warp<CH>(wf, L, N, u[t * u_stride], out, chunk);
+                mkf_resample_sequential_warp<CH>(wf, L, N, u[t * u_stride],
+                                                 [&](int i, int idx) {
+                                                     out[i] = idx;
+                                                     if (rep) src[i] = rep[idx];
+                                                 },
+                                                 chunk);
             }
             return;
         }
@@ -791,7 +944,11 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
         const int pre = max(carry_max, excl);
 #pragma unroll
         for (int q = 0; q < ITEMS; q++)
-            if (i0 + q < N) out[i0 + q] = max(pre, loc[q]);
+            if (i0 + q < N) {
+                const int idx = max(pre, loc[q]);
+                out[i0 + q] = idx;
+                if (rep) src[i0 + q] = __ldg(rep + idx);
+            }
         carry_max = max(carry_max, tile_max);
     }
 }
@@ -806,7 +963,9 @@ __global__ void __launch_bounds__(128) k_resample_small(const double* __restrict
                                                          double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
                                                          uint32_t* __restrict__ status, int status_stride,
                                                          uint32_t bit_deg, const uint64_t* __restrict__ seeds,
-                                                         int seed_stride, int seed_off, uint32_t* __restrict__ unsorted)
+                                                         int seed_stride, int seed_off, uint32_t* __restrict__ unsorted,
+                                                         const int32_t* __restrict__ rep_all,
+                                                         int32_t* __restrict__ src_all)
 {
     constexpr int LD = 129;
     extern __shared__ double sm_w[];                                       // [L][LD]
@@ -848,7 +1007,9 @@ __global__ void __launch_bounds__(128) k_resample_small(const double* __restrict
     __syncthreads();
     for (int i = tid; i < nt * N; i += 128) {
         const int tr = i / N, k = i - tr * N;
-        out_all[t0 * N + i] = sm_out[k * LD + tr];
+        const int idx = sm_out[k * LD + tr];
+        out_all[t0 * N + i] = idx;
+        if (rep_all) src_all[t0 * N + i] = __ldg(rep_all + (t0 + tr) * L + idx);
     }
 }
 

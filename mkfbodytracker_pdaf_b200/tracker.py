@@ -177,6 +177,12 @@ class TrackBatch:
     def sync(self):
         L.check(L.lib.mkf_batch_sync(self._h))
 
+    def shared_records(self):
+        """(records, slots): distinct Gaussians stored by the last update for how many slots (record sharing)"""
+        r, n = C.c_int64(), C.c_int64()
+        L.check(L.lib.mkf_batch_shared_records(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
     def join(self):
         """order the batch's stream after all MEM_HOST_ASYNC copies issued so far (no host synchronisation)"""
         L.check(L.lib.mkf_batch_join(self._h))

@@ -540,3 +540,43 @@ def test_host_async_pipeline_matches_synchronous_calls(left_arm):
     # and the synchronous path still works on the same batch afterwards
     b.update(*ins[0])
     assert np.isfinite(b.estimate()[1]).all()
+
+
+def test_record_sharing_is_invisible(left_arm):
+    """shared-measurement frames store identical children once (mkf_batch_shared_records < slots) while every per-slot
+    output stays that of N independent slots: compared with the oracle slot by slot, then a per-slot-measurement frame
+    (no sharing) on top of a shared one, then download / upload round trip of a shared state"""
+    seed, T, N = 0x5EED0002, 5, 500
+    tracks = list(range(T))
+    u0 = synth_u_init(seed, tracks)
+    fs = [orc.Filter(left_arm.orc, N) for _ in tracks]
+    for t in tracks:
+        fs[t].reset(u=u0[t])
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    b.reset(u0)
+    assert b.shared_records() == (T * N, T * N)
+    for fr in range(5):
+        m, ui, up = synth_frame(seed, tracks, fr)
+        per_slot = fr == 3
+        if per_slot:  # every slot its own column: nothing to share
+            mm = np.repeat(m[:, :, None], N, axis=2) + np.random.default_rng(fr).normal(0, 2.0, (T, 6, N))
+            b.update(mm, ui, up)
+        else:
+            b.update(m, ui, up)
+        rec, slots = b.shared_records()
+        # frame 0 starts from one record per slot (reset), so sharing shows from the second shared frame on
+        assert slots == T * N and (rec == slots if (per_slot or fr == 0) else T <= rec < 0.9 * slots), (fr, rec, slots)
+        d = b.download()
+        for t in tracks:
+            r = fs[t].update(mm[t] if per_slot else m[t], ui[t], up[t])
+            assert np.array_equal(d["parents"][t], r["parents"]) and np.array_equal(d["indicators"][t], r["indicators"])
+            assert rel_err_weights(d["w_norm"][t], r["w_norm"]) <= 1e-9
+            xo, Po = fs[t].get_state()
+            assert rel_err(d["x"][t], xo) <= 1e-9 and rel_err(d["P"][t], Po) <= 1e-9
+    # a shared state survives download -> upload (upload stores one record per slot again)
+    d = b.download()
+    b2 = mk.TrackBatch(left_arm.mk, T, N)
+    b2.reset(u0)
+    b2.upload(d["x"], d["P"])
+    d2 = b2.download()
+    assert rel_err(d2["x"], d["x"]) <= 1e-12 and rel_err(d2["P"], d["P"]) <= 1e-12
