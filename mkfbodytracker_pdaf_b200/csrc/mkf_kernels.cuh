@@ -484,43 +484,86 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
     mkf_pdl_wait();
 
     const long long base = (long long)blockIdx.x * CHUNK;
-    // ---- A: keys
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        const int so = g * 128 + tid;
-        const long long s = base + so;
-        int par = -1, tl = -1, k = 0;
-        if (s < a.total) {
-            tl = (int)((unsigned)s / (unsigned)a.N); // T*N < 2^32: 180 GB hold at most 1.25e8 slots
-            const int j = (int)((unsigned)s - (unsigned)tl * (unsigned)a.N);
-            par = __ldg(a.src + s);
-            k = mkf_component_of(a.bounds + (long long)tl * (a.K + 2), a.K, j);
+    // ---- A: keys.  A thread owns G consecutive slots (vector loads / stores; one division, then increments)
+    static_assert(G % 4 == 0, "vector accesses below assume groups of four slots");
+    const int so0 = tid * G;
+    const long long s0 = base + so0;
+    int H;
+    {
+        int par[G], tl[G], kk[G];
+        int t_run = 0, j_run = 0;
+        if (s0 < a.total) {
+            t_run = (int)((unsigned)s0 / (unsigned)a.N); // T*N < 2^32: 180 GB hold at most 1.25e8 slots
+            j_run = (int)((unsigned)s0 - (unsigned)t_run * (unsigned)a.N);
         }
-        sm_par[so] = par;
-        sm_t[so] = tl;
-        sm_k[so] = (unsigned char)k;
+        if (s0 + G <= a.total) {
+            const int4* __restrict__ sv = reinterpret_cast<const int4*>(a.src + s0);
+#pragma unroll
+            for (int q = 0; q < G / 4; q++) {
+                const int4 v4 = __ldg(sv + q);
+                par[4 * q] = v4.x;
+                par[4 * q + 1] = v4.y;
+                par[4 * q + 2] = v4.z;
+                par[4 * q + 3] = v4.w;
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; g++) par[g] = (s0 + g < a.total) ? __ldg(a.src + s0 + g) : -1;
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (s0 + g < a.total) {
+                tl[g] = t_run;
+                kk[g] = mkf_component_of(a.bounds + (long long)t_run * (a.K + 2), a.K, j_run);
+                if (++j_run == a.N) {
+                    j_run = 0;
+                    t_run++;
+                }
+            } else {
+                tl[g] = -1;
+                kk[g] = 0;
+                par[g] = -1;
+            }
+            sm_par[so0 + g] = par[g];
+            sm_t[so0 + g] = tl[g];
+            sm_k[so0 + g] = (unsigned char)kk[g];
+        }
+        __syncthreads();
+        // heads, numbered in slot order: flags of my G slots, one block scan of the per-thread counts
+        unsigned flags = 0;
+        int p_par = -2, p_t = -2, p_k = -1; // the slot before my first one (none for the chunk's first slot)
+        if (so0 > 0) {
+            p_par = sm_par[so0 - 1];
+            p_t = sm_t[so0 - 1];
+            p_k = sm_k[so0 - 1];
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (tl[g] >= 0 && (par[g] != p_par || kk[g] != p_k || tl[g] != p_t)) flags |= 1u << g;
+            p_par = par[g];
+            p_t = tl[g];
+            p_k = kk[g];
+        }
+        const int cnt = __popc(flags);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        int before = inc - cnt;
+        for (int w = 0; w < wid; w++) before += warp_tot[w];
+        H = warp_tot[0] + warp_tot[1] + warp_tot[2] + warp_tot[3];
+        int r = before - 1; // index of the head governing the slot before my first one
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (flags & (1u << g)) h_slot[++r] = so0 + g;
+            sm_rank[so0 + g] = r;
+        }
     }
     __syncthreads();
-    // heads, numbered in slot order (G block scans with a running carry)
-    int carry = 0;
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        const int so = g * 128 + tid;
-        const bool live = sm_t[so] >= 0;
-        const bool head = live && (so == 0 || sm_par[so] != sm_par[so - 1] || sm_k[so] != sm_k[so - 1] ||
-                                   sm_t[so] != sm_t[so - 1]);
-        const unsigned bal = __ballot_sync(0xffffffffu, head);
-        if (lane == 0) warp_tot[wid] = __popc(bal);
-        __syncthreads();
-        int before = carry;
-        for (int w = 0; w < wid; w++) before += warp_tot[w];
-        const int incl = before + __popc(bal & (0xffffffffu >> (31 - lane))); // heads up to and including this slot
-        carry += warp_tot[0] + warp_tot[1] + warp_tot[2] + warp_tot[3];
-        sm_rank[so] = incl - 1;
-        if (head) h_slot[incl - 1] = so;
-        __syncthreads();
-    }
-    const int H = carry;
 
     // ---- B: one thread per head
     mkf_mbar_wait(&mbar, 0);
@@ -559,16 +602,33 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
     }
     __syncthreads();
 
-    // ---- C: per-slot outputs
+    // ---- C: per-slot outputs (my G consecutive slots again)
+    {
+        double wv[G];
+        int rv[G];
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        const int so = g * 128 + tid;
-        const long long t = sm_t[so];
-        if (t < 0) continue;
-        const int h = sm_rank[so];
-        const long long seg = t * a.N > base ? t * a.N - base : 0;
-        a.w_raw[base + so] = h_w[h];
-        a.rep[base + so] = (int)(base + seg + (h - sm_rank[(int)seg]) - t * a.N);
+        for (int g = 0; g < G; g++) {
+            const int h = sm_rank[so0 + g];
+            const long long t = sm_t[so0 + g];
+            const long long seg = (t >= 0 && t * a.N > base) ? t * a.N - base : 0;
+            wv[g] = t >= 0 ? h_w[h] : 0.0;
+            rv[g] = (int)(base + seg + (h - sm_rank[(int)seg]) - t * a.N);
+        }
+        if (s0 + G <= a.total) {
+            double2* __restrict__ wo = reinterpret_cast<double2*>(a.w_raw + s0);
+            int4* __restrict__ ro = reinterpret_cast<int4*>(a.rep + s0);
+#pragma unroll
+            for (int q = 0; q < G / 2; q++) wo[q] = make_double2(wv[2 * q], wv[2 * q + 1]);
+#pragma unroll
+            for (int q = 0; q < G / 4; q++) ro[q] = make_int4(rv[4 * q], rv[4 * q + 1], rv[4 * q + 2], rv[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if (s0 + g < a.total) {
+                    a.w_raw[s0 + g] = wv[g];
+                    a.rep[s0 + g] = rv[g];
+                }
+        }
     }
 }
 
