@@ -792,8 +792,10 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
 template <int BT, int ITEMS>
 __device__ __noinline__ bool mkf_resample_precise_pass(const double* __restrict__ w, int L, int N, int normalise,
                                                        double wsum, double beta0, double step, double tol2,
-                                                       int32_t* __restrict__ out, double* sc_d, double* sc_d2)
+                                                       int32_t* __restrict__ out, double* sc_d, double* sc_d2,
+                                                       const int32_t* __restrict__ rep, int32_t* __restrict__ src)
 {
+    constexpr bool DIRECT = (BT == 128); // see k_resample_block
     const int tid = threadIdx.x;
     dd carry2 = dd_make(0.0);
     bool amb2 = false;
@@ -817,7 +819,17 @@ __device__ __noinline__ bool mkf_resample_precise_pass(const double* __restrict_
         for (int q = 0; q < ITEMS; q++) {
             if (i0 + q < L) {
                 const int e = mkf_count_le(dd_add(start, pre[q]), beta0, step, N, tol2, amb2);
-                if (e > e_prev) out[e_prev] = i0 + q;
+                if (e > e_prev) {
+                    if (DIRECT) {
+                        const int rv = rep ? __ldg(rep + i0 + q) : 0;
+                        for (int i = e_prev; i < e; i++) {
+                            out[i] = i0 + q;
+                            if (rep) src[i] = rv;
+                        }
+                    } else {
+                        out[e_prev] = i0 + q;
+                    }
+                }
                 if (i0 + q == L - 1 && e < N) amb2 = true;
                 e_prev = e;
             }
@@ -922,8 +934,14 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     const double tol_loop = fmin(mkf_resample_tol(N, L, wmax_n, step), mkf_resample_tol_s2(N, L, s2, mass));
     const double tol = tol_loop + 16.0 * 1.1102230246251565e-16 * (1.0 + mass);
 
-    for (int i = tid; i < N; i += BT) out[i] = -1;
-    __syncthreads();
+    // Short tracks (the 128-thread variant, N <= 1024): a thread that finds parent k owning the outputs [e_{k-1}, e_k)
+    // writes that range on the spot, together with the parent's record index.  Long tracks: the thread drops a head
+    // marker at e_{k-1} and a max-scan fills the ranges afterwards (a single parent may own tens of thousands).
+    constexpr bool DIRECT = (BT == 128);
+    if (!DIRECT) {
+        for (int i = tid; i < N; i += BT) out[i] = -1;
+        __syncthreads();
+    }
 
     // pass 2: prefix sums of the normalised weights -> child ranges.  Within a tile the scan is plain double;
     // the carry across tiles is kept in double-double so the error does not grow with the number of tiles.
@@ -949,7 +967,17 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
         for (int q = 0; q < ITEMS; q++) {
             if (i0 + q < L) {
                 const int e = mkf_count_le(dd_add_d(start, pre[q]), beta0, step, N, tol, amb);
-                if (e > e_prev) out[e_prev] = i0 + q;
+                if (e > e_prev) {
+                    if (DIRECT) {
+                        const int rv = rep ? __ldg(rep + i0 + q) : 0;
+                        for (int i = e_prev; i < e; i++) {
+                            out[i] = i0 + q;
+                            if (rep) src[i] = rv;
+                        }
+                    } else {
+                        out[e_prev] = i0 + q;
+                    }
+                }
                 if (i0 + q == L - 1 && e < N) amb = true; // literal loop would wrap past the last weight
                 e_prev = e;
             }
@@ -965,10 +993,12 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
         // literal re-run costs milliseconds.
         __syncthreads();
         if (tid == 0) sh_flag = 0;
-        for (int i = tid; i < N; i += BT) out[i] = -1;
+        if (!DIRECT)
+            for (int i = tid; i < N; i += BT) out[i] = -1;
         __syncthreads();
         const double tol2 = tol_loop + 8.0 * 1.1102230246251565e-16 * step + 8.0e-28 * (1.0 + mass);
-        const bool amb2 = mkf_resample_precise_pass<BT, ITEMS>(w, L, N, normalise, wsum, beta0, step, tol2, out, sc_d, sc_d2);
+        const bool amb2 = mkf_resample_precise_pass<BT, ITEMS>(w, L, N, normalise, wsum, beta0, step, tol2, out, sc_d,
+                                                               sc_d2, rep, src);
         if (amb2) sh_flag = 1;
         __syncthreads();
         if (sh_flag) {
@@ -987,6 +1017,7 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
             return;
         }
     }
+    if (DIRECT) return;
     // fill: inclusive max-scan of the head markers
     int carry_max = -1;
     for (int base = 0; base < N; base += BT * ITEMS) {
@@ -1092,14 +1123,31 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __res
     double acc[D];
 #pragma unroll
     for (int e = 0; e < D; e++) acc[e] = 0.0;
-    for (int j = tid; j < N; j += BT) {
-        const long long sp = t * N + __ldg(parent + t * N + j);
-        const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+    // a thread takes RUN consecutive children: their record indices are loaded together (one latency), sorted parents
+    // make neighbours share a record more often than not (then the gather is skipped and the registers reused), and
+    // the gathers of one thread are independent of each other
+    constexpr int RUN = 4;
+    for (int j0 = tid * RUN; j0 < N; j0 += BT * RUN) {
+        int idx[RUN];
 #pragma unroll
-        for (int p = 0; p < D / 2; p++) {
-            const double2 q = __ldg(src + p * 32);
-            acc[2 * p] += q.x;
-            acc[2 * p + 1] += q.y;
+        for (int u = 0; u < RUN; u++) idx[u] = (j0 + u < N) ? __ldg(parent + t * N + j0 + u) : -1;
+        double2 v[D / 2];
+        int have = -2;
+#pragma unroll
+        for (int u = 0; u < RUN; u++) {
+            if (idx[u] < 0) continue;
+            if (idx[u] != have) {
+                const long long sp = t * N + idx[u];
+                const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+#pragma unroll
+                for (int p = 0; p < D / 2; p++) v[p] = __ldg(src + p * 32);
+                have = idx[u];
+            }
+#pragma unroll
+            for (int p = 0; p < D / 2; p++) {
+                acc[2 * p] += v[p].x;
+                acc[2 * p + 1] += v[p].y;
+            }
         }
     }
 #pragma unroll
