@@ -451,6 +451,21 @@ def test_cholesky_failure_branch_matches_oracle(left_arm, rng):
         assert ok.sum() > N // 2
         assert rel_err(d["x"][t][ok], xo[ok]) <= RTOL and rel_err(d["P"][t][ok], Po[ok]) <= RTOL
     print("cholesky-failure slots with non-finite or extreme weights:", n_fail)
+    # a second frame on top: the repaired tracks stored one record per slot, their parents are the unsorted random
+    # indices of the NaN-weight fallback, and record sharing has to cope with both
+    meas, ui, up = synth_frame(0x5EED0002, range(T), 1, N)
+    res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+    b.update(meas, ui, up)
+    d = b.download()
+    for t in range(T):
+        wo, wg = res[t]["w_raw"], d["w_raw"][t]
+        assert np.array_equal(np.isnan(wo), np.isnan(wg))
+        assert np.array_equal(d["parents"][t], res[t]["parents"])
+        xo, Po = fs[t].get_state()
+        ok = np.isfinite(Po).all(axis=(1, 2)) & np.isfinite(xo).all(axis=1) & np.isfinite(d["x"][t]).all(axis=1)
+        assert np.array_equal(np.isfinite(xo).all(axis=1), np.isfinite(d["x"][t]).all(axis=1))
+        if ok.any():
+            assert rel_err(d["x"][t][ok], xo[ok]) <= RTOL and rel_err(d["P"][t][ok], Po[ok]) <= RTOL
 
 
 @pytest.mark.parametrize("K,d", [(25, 10), (35, 10), (26, 12)])

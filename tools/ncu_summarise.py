@@ -88,37 +88,56 @@ def main(argv):
         w.writerow(["Kernel Name", ""] + [c[1] for c in cols])
         w.writerow(["report", ""] + [c[0].split("/")[-1] for c in cols])
         for k in metrics:
-            unit = next(c[2][k][0] for c in cols if k in c[2])
-            w.writerow([k, unit] + [c[2].get(k, ("", ""))[1] for c in cols])
+            units = {c[2][k][0] for c in cols if k in c[2]}
+            if len(units) == 1:
+                w.writerow([k, units.pop()] + [c[2].get(k, ("", ""))[1] for c in cols])
+            else:  # ncu scales units per kernel (Mbyte here, Gbyte there): keep each cell's own
+                w.writerow([k, "(per cell)"] + [" ".join(reversed(c[2][k])) if k in c[2] else "" for c in cols])
     print("wrote", out_csv, "(%d launches, %d metrics)" % (len(cols), len(metrics)))
 
     if traffic_json:
-        sel = [c for c in cols if c[1].split("(")[0].strip().startswith("void k_slot_update<") and "repair" not in c[1]]
-        if not sel:
-            raise SystemExit("no k_slot_update launch in the reports; %s left untouched" % traffic_json)
+        # per slot-update kernel (plain and record-sharing): average DRAM traffic per launch, keyed by the kernel's base
+        # name; entries of kernels absent from these reports are kept
+        try:
+            with open(traffic_json) as f:
+                doc = json.load(f)
+            if "kernels" not in doc:
+                doc = {"kernels": {}}
+        except Exception:
+            doc = {"kernels": {}}
 
         def bytes_of(c, key):
             unit, val = c[2][key]
             return float(val.replace(",", "")) * UNIT_SCALE[unit]
 
-        rd = sum(bytes_of(c, "dram__bytes_read.sum") for c in sel) / len(sel)
-        wr = sum(bytes_of(c, "dram__bytes_write.sum") for c in sel) / len(sel)
-        grid = int(float(sel[0][2]["launch__grid_size"][1].replace(",", "")))
-        block = int(float(sel[0][2]["launch__block_size"][1].replace(",", "")))
-        d = {
-            "kernel": sel[0][1].split("(")[0].replace("void ", "").strip(),
-            "source": "%s (ncu --set full --clock-control none, %d launches, bench.py config 2: 4096 tracks x 500 slots, grid %d x %d threads)"
-            % (out_csv, len(sel), grid, block),
-            "dram_bytes_read_per_launch": round(rd),
-            "dram_bytes_write_per_launch": round(wr),
-            "dram_bytes_per_launch": round(rd + wr),
-            "algorithmic_bytes_per_launch": 4096 * 500 * 1500,
-            "round": 1,
-        }
+        found = 0
+        for base in ("k_slot_update_shared", "k_slot_update"):
+            sel = [c for c in cols if c[1].replace("void ", "").strip().split("<")[0] == base]
+            if not sel:
+                continue
+            found += 1
+            rd = sum(bytes_of(c, "dram__bytes_read.sum") for c in sel) / len(sel)
+            wr = sum(bytes_of(c, "dram__bytes_write.sum") for c in sel) / len(sel)
+            us = sum(float(c[2]["gpu__time_duration.sum"][1].replace(",", "")) for c in sel) / len(sel)
+            grid = int(float(sel[0][2]["launch__grid_size"][1].replace(",", "")))
+            block = int(float(sel[0][2]["launch__block_size"][1].replace(",", "")))
+            doc["kernels"][base] = {
+                "kernel": sel[0][1].split("(")[0].replace("void ", "").strip(),
+                "source": "%s (ncu --set full --clock-control none, %d launches, bench.py config 2: 4096 tracks x 500 "
+                          "slots, grid %d x %d threads)" % (out_csv, len(sel), grid, block),
+                "dram_bytes_read_per_launch": round(rd),
+                "dram_bytes_write_per_launch": round(wr),
+                "dram_bytes_per_launch": round(rd + wr),
+                "ncu_duration_us": round(us, 2),
+                "algorithmic_bytes_per_launch": 4096 * 500 * 1500,
+            }
+        if not found:
+            raise SystemExit("no slot-update launch in the reports; %s left untouched" % traffic_json)
+        doc["round"] = 1
         with open(traffic_json, "w") as f:
-            json.dump(d, f, indent=1)
+            json.dump(doc, f, indent=1)
             f.write("\n")
-        print("wrote", traffic_json, d)
+        print("wrote", traffic_json, list(doc["kernels"]))
 
 
 if __name__ == "__main__":
