@@ -203,10 +203,33 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "slot_updates_per_s": val * N, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_JSON_FD = None
+
+
+def reserve_stdout():
+    """stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr for the rest of the
+    run, so that nothing a library prints (NCCL's version banner, for one) can land next to that line"""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -236,7 +259,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         # keep stdout to the single JSON line: the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("MKF_NCCL_DEBUG", "WARN")
+        # (WARN prints the banner as well; it is dropped unless MKF_NCCL_DEBUG asks for a level)
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("MKF_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["MKF_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     T, N, K, W = args.tracks, args.slots, args.steps, args.warmup
     F = K + W
@@ -392,7 +418,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline(N)
         else:
             out["cpu_baseline"] = None
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
