@@ -2,6 +2,7 @@
 // See include/mkf_b200.h for the contract and the reference interfaces each call replaces.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +28,17 @@ static bool pdl_enabled()
         return !(e && e[0] == '0');
     }();
     return on;
+}
+static int sm_count(int device)
+{
+    static std::atomic<int> cached[64];
+    if (device < 0 || device >= 64) return 148;
+    int v = cached[device].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cached[device].store(v, std::memory_order_relaxed);
+    }
+    return v;
 }
 template <class... P, class... A>
 static void mkf_launch(void (*kern)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, A&&... args)
@@ -153,6 +165,13 @@ struct mkf_batch {
     // record sharing (k_slot_update<.., DEDUP>): rep[slot] = record of st[cur] holding the slot's state, written by
     // the slot kernel; src[slot] = rep[parent[slot]], written by the resampler.  shared == false: src is `parent`.
     int32_t *rep = nullptr, *src = nullptr;
+    // two-kernel record sharing (k_share_keys -> k_slot_update_heads_direct): list of heads, its
+    // length (two counters used alternately: the heads kernel of one frame clears the one the next frame appends
+    // with), weight per record
+    int4* hd16 = nullptr;
+    int* head_count = nullptr;
+    int head_flip = 0;
+    double* w_rec = nullptr;
     bool shared = false; // the children of the last update share records (read state through src, not parent)
     bool dedup_ok = true; // MKF_DEDUP=0 in the environment turns the sharing off (A/B measurements)
     const int32_t* gather_index() const { return shared ? src : parent; }
@@ -255,7 +274,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->rep, b->src, b->bounds, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->hd16, b->head_count, b->w_rec, b->bounds, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -333,6 +352,13 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     if (b->dedup_ok && ((rc = dmalloc((void**)&b->rep, (size_t)b->total * sizeof(int32_t))) ||
                         (rc = dmalloc((void**)&b->src, (size_t)b->total * sizeof(int32_t)))))
         return fail(rc);
+    if (b->dedup_ok) {
+        if ((rc = dmalloc((void**)&b->hd16, (size_t)b->total * sizeof(int4))) ||
+            (rc = dmalloc((void**)&b->head_count, 2 * sizeof(int))) ||
+            (rc = dmalloc((void**)&b->w_rec, (size_t)b->total * sizeof(double))))
+            return fail(rc);
+        if (cudaMemset(b->head_count, 0, 2 * sizeof(int)) != cudaSuccess) return fail(MKF_E_CUDA);
+    }
     if ((rc = dmalloc((void**)&b->bounds, (size_t)T * (m->K + 2) * sizeof(int32_t)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->w_raw, (size_t)b->total * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->wsum, (size_t)T * sizeof(double)))) return fail(rc);
@@ -488,9 +514,14 @@ static bool first_on_this_device(std::atomic<uint64_t>& seen)
 static int run_resample(cudaStream_t stream, long long nt, const double* d_w, int L, int N, const double* d_u,
                         int u_stride, int normalise, double* d_wsum, int32_t* d_out, uint32_t* d_status,
                         const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb, uint32_t bit_deg,
-                        uint32_t* d_unsorted = nullptr, const int32_t* d_rep = nullptr, int32_t* d_src = nullptr)
+                        uint32_t* d_unsorted = nullptr, const int32_t* d_rep = nullptr, int32_t* d_src = nullptr,
+                        double* d_w_slot_out = nullptr)
 {
     if (L <= 64 && N <= 64) {
+        if (d_w_slot_out) {
+            mkf_set_error("internal: per-record weights are not supported by the small-track resampler");
+            return MKF_E_INVALID;
+        }
         const size_t smem = (size_t)129 * ((size_t)L * 8 + (size_t)N * 4); // <= 99 KB at L = N = 64
         static std::atomic<uint64_t> seen{0};
         if (first_on_this_device(seen))
@@ -502,7 +533,7 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
         const int span = L > N ? L : N;
 #define MKF_RS_BLOCK(BT)                                                                                             \
     mkf_launch(k_resample_block<BT, 4>, (unsigned)nt, BT, 0, stream, d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out, \
-               d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src)
+               d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src, d_w_slot_out)
         if (span <= 1024)
             MKF_RS_BLOCK(128);
         else if (span <= 8192)
@@ -544,6 +575,9 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     const bool dedup = b->dedup_ok && meas_layout == MKF_MEAS_SHARED && b->stage == 3 && b->N >= 4 * m->K;
     a.dedup = dedup ? 1 : 0;
     a.rep = dedup ? b->rep : nullptr;
+    a.hd16 = b->hd16;
+    a.head_count = b->head_count ? b->head_count + b->head_flip : nullptr;
+    a.w_rec = b->w_rec;
     a.bounds = b->bounds;
     a.meas = d_meas;
     a.comp_const = b->d_comp;
@@ -560,6 +594,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     for (int r = 0; r < MKF_M; r++) a.bh[r] = m->BH[r];
     a.r = m->prm.meas_noise_var;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
+    bool use_split = false;
     {
         static std::atomic<uint64_t> seen{0};
         if (smem > 48 * 1024 && first_on_this_device(seen)) {
@@ -578,9 +613,17 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             const int v = e ? atoi(e) : 8;
             return (v == 4 || v == 8 || v == 16) ? v : 8;
         }();
+        // MKF_SHARE_SPLIT=0: the single-launch variant k_slot_update_shared (A/B measurements)
+        static const bool share_split = [] {
+            const char* e = getenv("MKF_SHARE_SPLIT");
+            return !(e && e[0] == '0');
+        }();
+        // (tracks of <= 64 slots go to k_resample_small, which reads per-slot weights)
+        use_split = dedup && share_split && b->N > 64;
+        a.split = use_split ? 1 : 0;
         const size_t smem_shared = smem + (size_t)128 * share_g * (8 + 4 * 4 + 1);
         static std::atomic<uint64_t> seen_shared{0};
-        if (dedup && smem_shared > 48 * 1024 && first_on_this_device(seen_shared)) {
+        if (dedup && first_on_this_device(seen_shared)) {
 #define MKF_SHARED_ATTR(DD, GG)                                                                                        \
     CK(cudaFuncSetAttribute(k_slot_update_shared<DD, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024))
             MKF_SHARED_ATTR(12, 4);
@@ -590,6 +633,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             MKF_SHARED_ATTR(10, 8);
             MKF_SHARED_ATTR(10, 16);
 #undef MKF_SHARED_ATTR
+            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         }
 #define MKF_SHARED_LAUNCH(DD, GG)                                                                                      \
     mkf_launch(k_slot_update_shared<DD, GG>, grid_for(b->total, 128 * GG), 128, smem_shared, b->stream, a)
@@ -597,7 +642,13 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     do {                                                                               \
         if (a.alias_chain)                                                             \
             mkf_launch(k_slot_update<DD, true>, g, 128, smem, b->stream, a);    \
-        else if (dedup && share_g == 4)                                                \
+        else if (use_split) {                                                          \
+            mkf_launch(k_share_keys, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);                       \
+            MKF_LAUNCHED();                                                            \
+            mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(2 * sm_count(b->device)), 128, smem, b->stream, a,   \
+                       b->head_count + (b->head_flip ^ 1));                            \
+            b->head_flip ^= 1;                                                         \
+        } else if (dedup && share_g == 4)                                                \
             MKF_SHARED_LAUNCH(DD, 4);                                                  \
         else if (dedup && share_g == 8)                                                \
             MKF_SHARED_LAUNCH(DD, 8);                                                  \
@@ -624,9 +675,10 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     CK(cudaGetLastError());
     if (prof) cudaEventRecord(pe[2], b->stream);
     b->cur ^= 1;
-    rc = run_resample(b->stream, b->T, b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent, b->status,
-                      d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE, b->unsorted,
-                      dedup ? b->rep : nullptr, dedup ? b->src : nullptr);
+    rc = run_resample(b->stream, b->T, use_split ? b->w_rec : b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent,
+                      b->status, d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE,
+                      b->unsorted, dedup ? b->rep : nullptr, dedup ? b->src : nullptr,
+                      use_split ? b->w_raw : nullptr);
     b->shared = dedup;
     if (prof) {
         cudaEventRecord(pe[3], b->stream);

@@ -49,6 +49,13 @@ struct SlotArgs {
     int32_t* __restrict__ rep;          // T*N out (dedup only): local index of the record in st_out holding this slot
     int dedup;                          // 1: identical children (same parent record, component, track measurement)
                                         //    are computed and stored once per warp
+    // three-kernel record sharing (k_share_keys -> k_slot_update_heads_flat -> k_share_expand): the batch-wide list of
+    // heads (16 bytes each: source record, destination record, track, component), its length (appended to with
+    // atomicAdd), and the weight of every record at the record's position
+    int4* __restrict__ hd16;
+    int* __restrict__ head_count;
+    double* __restrict__ w_rec;
+    int split; // 1: this frame runs k_share_keys -> k_slot_update_heads_direct (weights per record in w_rec)
     const int32_t* __restrict__ bounds; // T x (K+2): e_0..e_{K-1}, wrap_from, wrap_k
     const double* __restrict__ meas;
     const double* __restrict__ comp_const; // K x CS (global; staged to shared memory by TMA)
@@ -632,6 +639,214 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// Record sharing in two launches (the default; k_slot_update_shared above remains for models whose constants leave no
+// room and as the A/B reference, MKF_SHARE_SPLIT=0).  ncu on k_slot_update_shared showed the slot arithmetic to be
+// 20-25 % of the stall samples: the rest was a chain of dependent global loads (parent index -> record gather ... per
+// slot head index) and the bookkeeping instructions, all executed at the 8 warps per SM that 255 registers allow, and
+// the CTA barrier in front of the per-slot outputs.  So:
+//   k_share_keys                 256 threads x 4 consecutive slots = one 1024-slot chunk at full occupancy: keys, head
+//                                flags, block scan; writes rep[] (final) and appends one 16-byte record per head
+//                                {source record, destination record, track, component} to a batch-wide list (one
+//                                atomicAdd per chunk; the order of the chunks in the list is immaterial);
+//   k_slot_update_heads_direct   persistent, 2 CTAs per SM, one thread per list entry, no barrier: gather, slot
+//                                arithmetic, store; the weight goes to w_rec[] at the record's position.  One
+//                                dependent hop (the gather) in front of the arithmetic; the next step's list entry is
+//                                already in flight.  The kernel moves 1 440 B per distinct Gaussian and runs at ~65 %
+//                                of the HBM copy rate on them.
+// The resampler reads slot i's weight as w_rec[rep[i]] (k_resample_block, w_slot_out) and materialises w_raw on the way.
+// Same chunking and record placement as k_slot_update_shared, so everything downstream is unchanged.
+// Tried and dropped: staging the next step's parent record in shared memory with cp.async (per-thread slices, no
+// registers), CTA- and warp-level variants: the extra LSU traffic (48 LDGSTS + 48 LDS per head) and the spills it
+// caused cost more than the hidden latency gained (73-88 us against 67 us); prefetch.global.L2 of the next step's
+// record: 69 us.
+// -----------------------------------------------------------------------------------------
+constexpr int MKF_SHARE_CHUNK = 1024;
+
+__global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
+{
+    constexpr int CHUNK = MKF_SHARE_CHUNK, G = 4;
+    __shared__ int sm_par[CHUNK], sm_t[CHUNK], sm_rank[CHUNK];
+    __shared__ unsigned char sm_k[CHUNK];
+    __shared__ int warp_tot[8];
+    __shared__ int list_base;
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long base = (long long)blockIdx.x * CHUNK;
+    const int so0 = tid * G;
+    const long long s0 = base + so0;
+    int par[G], tl[G], kk[G];
+    int t_run = 0, j_run = 0;
+    if (s0 < a.total) {
+        t_run = (int)((unsigned)s0 / (unsigned)a.N);
+        j_run = (int)((unsigned)s0 - (unsigned)t_run * (unsigned)a.N);
+    }
+    if (s0 + G <= a.total) {
+        const int4 v4 = __ldg(reinterpret_cast<const int4*>(a.src + s0));
+        par[0] = v4.x;
+        par[1] = v4.y;
+        par[2] = v4.z;
+        par[3] = v4.w;
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; g++) par[g] = (s0 + g < a.total) ? __ldg(a.src + s0 + g) : -1;
+    }
+    {
+        // component of a slot = number of run boundaries e_0..e_{K-2} (non-decreasing) that are <= j, unless j lies in
+        // the wrapped tail (mkf_component_of).  Counted once for my first slot of a track, then carried forward.
+        const int K = a.K;
+        const int32_t* bt = a.bounds;
+        int k_lin = 0, nb = 0, wf = 0, wk = 0;
+        bool fresh = true;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (s0 + g < a.total) {
+                if (fresh) {
+                    bt = a.bounds + (long long)t_run * (K + 2);
+                    k_lin = 0;
+                    for (int q = 0; q < K - 1; q++) k_lin += (j_run >= __ldg(bt + q)) ? 1 : 0;
+                    wf = __ldg(bt + K);
+                    wk = __ldg(bt + K + 1);
+                    fresh = false;
+                    nb = (k_lin < K - 1) ? __ldg(bt + k_lin) : 0x7fffffff;
+                } else {
+                    while (j_run >= nb) {
+                        k_lin++;
+                        nb = (k_lin < K - 1) ? __ldg(bt + k_lin) : 0x7fffffff;
+                    }
+                }
+                tl[g] = t_run;
+                kk[g] = (j_run >= wf) ? wk : k_lin;
+                if (++j_run == a.N) {
+                    j_run = 0;
+                    t_run++;
+                    fresh = true;
+                }
+            } else {
+                tl[g] = -1;
+                kk[g] = 0;
+                par[g] = -1;
+            }
+            sm_par[so0 + g] = par[g];
+            sm_t[so0 + g] = tl[g];
+            sm_k[so0 + g] = (unsigned char)kk[g];
+        }
+    }
+    __syncthreads();
+    unsigned flags = 0;
+    int p_par = -2, p_t = -2, p_k = -1; // the slot before my first one (none for the chunk's first slot)
+    if (so0 > 0) {
+        p_par = sm_par[so0 - 1];
+        p_t = sm_t[so0 - 1];
+        p_k = sm_k[so0 - 1];
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        if (tl[g] >= 0 && (par[g] != p_par || kk[g] != p_k || tl[g] != p_t)) flags |= 1u << g;
+        p_par = par[g];
+        p_t = tl[g];
+        p_k = kk[g];
+    }
+    const int cnt = __popc(flags);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int before = inc - cnt;
+    for (int w = 0; w < wid; w++) before += warp_tot[w];
+    int rk[G];
+    {
+        int r = before - 1; // index of the head governing the slot before my first one
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (flags & (1u << g)) ++r;
+            rk[g] = r;
+            sm_rank[so0 + g] = r;
+        }
+    }
+    if (tid == 255) list_base = atomicAdd(a.head_count, before + cnt); // this chunk's stretch of the head list
+    __syncthreads();
+    // record position: the track's first slot in this chunk + the head's number within the track
+    int rv[G];
+    const long long lb = list_base;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const long long tN = (long long)tl[g] * a.N;
+        const long long seg = (tl[g] >= 0 && tN > base) ? tN - base : 0;
+        rv[g] = (int)(base + seg + (rk[g] - sm_rank[(int)seg]) - tN);
+        if (flags & (1u << g)) a.hd16[lb + rk[g]] = make_int4((int)(tN + par[g]), (int)(tN + rv[g]), tl[g], kk[g]);
+    }
+    if (s0 + G <= a.total) {
+        *reinterpret_cast<int4*>(a.rep + s0) = make_int4(rv[0], rv[1], rv[2], rv[3]);
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            if (s0 + g < a.total) a.rep[s0 + g] = rv[g];
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotArgs a, int* __restrict__ count_to_clear)
+{
+    using L = SlotLay<D>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cst = reinterpret_cast<double*>(smem_raw); // K x CS model constants (TMA)
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int tid = threadIdx.x;
+    const uint32_t cbytes = (uint32_t)(a.K * L::CS * sizeof(double));
+    if (tid == 0) mkf_mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mkf_mbar_expect_tx(&mbar, cbytes);
+        mkf_tma_load_1d(cst, a.comp_const, cbytes, &mbar); // model constants: never written by the frame chain
+    }
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+
+    const int n = *reinterpret_cast<const volatile int*>(a.head_count);
+    if (blockIdx.x == 0 && tid == 0) *count_to_clear = 0; // the counter the next frame's k_share_keys appends with
+    const int step = (int)gridDim.x * 128;
+    int h = (int)blockIdx.x * 128 + tid;
+    int4 rec = make_int4(-1, 0, 0, 0);
+    if (h < n) rec = __ldg(a.hd16 + h);
+    mkf_mbar_wait(&mbar, 0);
+    while (h < n) {
+        const long long sp = (unsigned)rec.x, so_rec = (unsigned)rec.y, t = rec.z;
+        const int k = rec.w;
+        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+        double v[L::NE];
+#pragma unroll
+        for (int p = 0; p < L::NP; p++) {
+            const double2 q = __ldg(src + p * 32);
+            v[2 * p] = q.x;
+            if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+        }
+        double zc[MKF_M];
+        mkf_load_meas(a, t, 0, zc); // shared layout: the track's column
+        h += step;
+        if (h < n) rec = __ldg(a.hd16 + h); // next step's head record: in flight during the arithmetic
+        double w;
+        const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+        if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+        double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)(L::NP * 32) + (so_rec & 31);
+#pragma unroll
+        for (int p = 0; p < L::NP; p++) {
+            double2 q;
+            q.x = v[2 * p];
+            q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+            __stcs(dst + p * 32, q);
+        }
+        a.w_rec[so_rec] = w;
+    }
+}
+
 // Rare tracks redone after k_slot_update: (i) a cv::Cholesky failure was flagged (literal failure semantics
 // through slot_math<SLOW>), (ii) literal alias mode with UNSORTED parents (after the degenerate random-index
 // fallback of src/pf2DRao.cpp:184-192 the slots sharing a parent are not adjacent).  One CTA scans 128
@@ -690,6 +905,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
                 }
                 a.w_raw[s] = w;
                 if (a.dedup) a.rep[s] = j; // the redone track stores every slot at its own position
+                if (a.split) a.w_rec[s] = w; // ... and the resampler reads the weights through rep[]
                 if (a.alias_chain) lt[par] = j;
             }
         }
@@ -793,7 +1009,8 @@ template <int BT, int ITEMS>
 __device__ __noinline__ bool mkf_resample_precise_pass(const double* __restrict__ w, int L, int N, int normalise,
                                                        double wsum, double beta0, double step, double tol2,
                                                        int32_t* __restrict__ out, double* sc_d, double* sc_d2,
-                                                       const int32_t* __restrict__ rep, int32_t* __restrict__ src)
+                                                       const int32_t* __restrict__ rep, int32_t* __restrict__ src,
+                                                       const bool by_record)
 {
     constexpr bool DIRECT = (BT == 128); // see k_resample_block
     const int tid = threadIdx.x;
@@ -805,7 +1022,7 @@ __device__ __noinline__ bool mkf_resample_precise_pass(const double* __restrict_
         dd run = dd_make(0.0);
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) {
-            double x = (i0 + q < L) ? w[i0 + q] : 0.0;
+            double x = (i0 + q < L) ? (by_record ? w[rep[i0 + q]] : w[i0 + q]) : 0.0;
             if (normalise) x = __ddiv_rn(x, wsum);
             run = dd_add_d(run, x);
             pre[q] = run;
@@ -852,10 +1069,13 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
                                                         const uint64_t* __restrict__ seeds, int seed_stride,
                                                         int seed_off, uint32_t* __restrict__ unsorted,
                                                         const int32_t* __restrict__ rep_all,
-                                                        int32_t* __restrict__ src_all)
+                                                        int32_t* __restrict__ src_all,
+                                                        double* __restrict__ w_slot_out)
 {
     // rep_all / src_all (both or neither): besides the parent SLOT of every output, also write the RECORD that holds
-    // that slot's state, src = rep[parent] (k_slot_update with dedup stores identical children once)
+    // that slot's state, src = rep[parent] (k_slot_update with dedup stores identical children once).
+    // w_slot_out (with rep_all): w_all holds one weight per RECORD (k_slot_update_heads_direct), slot i's weight is
+    // w[rep[i]]; pass 1 also writes the per-slot weights out (mkf_batch_download reads them)
     constexpr int CH = 512;
     __shared__ int sc_i[BT / 32];
     __shared__ double sc_d[BT / 32], sc_d2[BT / 32], sc_d3[BT / 32];
@@ -869,6 +1089,7 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     int32_t* __restrict__ out = out_all + t * N;
     const int32_t* __restrict__ rep = rep_all ? rep_all + t * L : nullptr;
     int32_t* __restrict__ src = rep_all ? src_all + t * N : nullptr;
+    const bool by_record = w_slot_out != nullptr;
     if (tid == 0 && unsorted) unsorted[t] = 0u;
 
     // pass 1: sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172).  The sum only has to be an accurate
@@ -876,7 +1097,13 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     // same value, so both paths see identical normalised weights.
     double acc = 0.0, mx = 0.0, sq = 0.0;
     for (int i = tid; i < L; i += BT) {
-        const double x = w[i];
+        double x;
+        if (by_record) {
+            x = w[rep[i]];
+            w_slot_out[t * L + i] = x;
+        } else {
+            x = w[i];
+        }
         acc += x;
         sq = fma(x, x, sq);
         if (x > mx) mx = x;
@@ -953,7 +1180,7 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
         double run = 0.0;
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) {
-            double x = (i0 + q < L) ? w[i0 + q] : 0.0;
+            double x = (i0 + q < L) ? (by_record ? w[rep[i0 + q]] : w[i0 + q]) : 0.0;
             if (normalise) x = __ddiv_rn(x, wsum);
             run += x;
             pre[q] = run;
@@ -998,7 +1225,7 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
         __syncthreads();
         const double tol2 = tol_loop + 8.0 * 1.1102230246251565e-16 * step + 8.0e-28 * (1.0 + mass);
         const bool amb2 = mkf_resample_precise_pass<BT, ITEMS>(w, L, N, normalise, wsum, beta0, step, tol2, out, sc_d,
-                                                               sc_d2, rep, src);
+                                                               sc_d2, rep, src, by_record);
         if (amb2) sh_flag = 1;
         __syncthreads();
         if (sh_flag) {
@@ -1006,7 +1233,10 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
             // normalised weights (staged through shared memory, lane 0 walking them)
             if (tid == 0) atomicOr(status + t * status_stride, bit_fb);
             if (wid == 0) {
-                auto wf = [&](int i) { return normalise ? __ddiv_rn(w[i], wsum) : w[i]; };
+                auto wf = [&](int i) {
+                    const double x = by_record ? w[rep[i]] : w[i];
+                    return normalise ? __ddiv_rn(x, wsum) : x;
+                };
                 mkf_resample_sequential_warp<CH>(wf, L, N, u[t * u_stride],
                                                  [&](int i, int idx) {
                                                      out[i] = idx;

@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu-baseline | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'],'stage',d['roofline']['stage_ms'])"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_cfg45.csv \
-    python tools/bench_configs.py 5 2b pf2d > gpurun_out/cfg45_ncu.log 2>&1
-echo "configs rc=$?"
-python tools/bench_configs.py 2b 5 pf2d 2>&1 | cut -c1-330
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for v in 0 1; do
+MKF_SHARE_SPLIT=$v timeout 300 python bench.py --no-cpu-baseline --steps 400 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('split=$v value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'],'stage',d['roofline']['stage_ms'])"
+done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_exp.csv \
+    python bench.py --steps 40 --warmup 3 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
+python tools/launch_list.py gpurun_out/launches_exp.csv 2>&1 | grep "k_"
