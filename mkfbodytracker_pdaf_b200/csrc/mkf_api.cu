@@ -172,6 +172,7 @@ struct mkf_batch {
     int* head_count = nullptr;
     int head_flip = 0;
     double* w_rec = nullptr;
+    bool share_split = true; // MKF_SHARE_SPLIT=0 at creation: the single-launch variant k_slot_update_shared (A/B runs)
     bool shared = false; // the children of the last update share records (read state through src, not parent)
     bool dedup_ok = true; // MKF_DEDUP=0 in the environment turns the sharing off (A/B measurements)
     const int32_t* gather_index() const { return shared ? src : parent; }
@@ -348,6 +349,8 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     {
         const char* e = getenv("MKF_DEDUP");
         b->dedup_ok = !(e && e[0] == '0') && m->prm.alias_mode == MKF_ALIAS_INDEPENDENT;
+        const char* e2 = getenv("MKF_SHARE_SPLIT");
+        b->share_split = !(e2 && e2[0] == '0');
     }
     if (b->dedup_ok && ((rc = dmalloc((void**)&b->rep, (size_t)b->total * sizeof(int32_t))) ||
                         (rc = dmalloc((void**)&b->src, (size_t)b->total * sizeof(int32_t)))))
@@ -613,13 +616,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             const int v = e ? atoi(e) : 8;
             return (v == 4 || v == 8 || v == 16) ? v : 8;
         }();
-        // MKF_SHARE_SPLIT=0: the single-launch variant k_slot_update_shared (A/B measurements)
-        static const bool share_split = [] {
-            const char* e = getenv("MKF_SHARE_SPLIT");
-            return !(e && e[0] == '0');
-        }();
         // (tracks of <= 64 slots go to k_resample_small, which reads per-slot weights)
-        use_split = dedup && share_split && b->N > 64;
+        use_split = dedup && b->share_split && b->N > 64;
         a.split = use_split ? 1 : 0;
         const size_t smem_shared = smem + (size_t)128 * share_g * (8 + 4 * 4 + 1);
         static std::atomic<uint64_t> seen_shared{0};
