@@ -330,7 +330,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    prof = batch.profile_read()
+    prof = batch.profile_read_stages()
     batch.profile(0)
     rec, nslots = batch.shared_records()  # distinct Gaussians the last frame stored (record sharing)
     status_bad = int((batch.status() & (mk._lib.ST_POST_DEGENERATE | mk._lib.ST_CHOL_FAIL)).astype(bool).sum())
@@ -372,16 +372,59 @@ def main():
     assert torch.equal(pose_sync, h_pose[(F - 1) & 1]), "pipelined and synchronous e2e runs must agree"
     pose_check = float(h_pose[(F - 1) & 1][:, :2].mean())
 
+    # ---------------- the same frames with every slot computed (record sharing off) ----------------
+    # what per-slot measurements (the association path, config 4) always run: k_slot_update moves SURVEY 8(d)'s
+    # 1 500 B for every slot, so this leg is the one to hold against the HBM roofline.  Rank 0, no collectives.
+    every_slot = None
+    if rank == 0 and os.environ.get("MKF_DEDUP", "1") != "0":
+        os.environ["MKF_DEDUP"] = "0"  # read when a batch is created
+        try:
+            b2 = mk.TrackBatch(model, T, N, device=local, stream=stream.cuda_stream)
+        finally:
+            del os.environ["MKF_DEDUP"]
+        K2 = min(K, 48)
+        b2.reset(u0)
+        for f in range(W):
+            b2.update(meas[f], ui[f], up[f])
+            b2.estimate_into(None, pose)
+        torch.cuda.synchronize()
+        b2.profile((K2 + 3) // 4, 4)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for f in range(W, W + K2):
+            b2.update(meas[f], ui[f], up[f])
+            b2.estimate_into(None, pose)
+        eb.record()
+        torch.cuda.synchronize()
+        p2 = b2.profile_read_stages()
+        b2.profile(0)
+        ms2 = ea.elapsed_time(eb) / K2
+        k2_ms = p2["ms_slot_kernel"] / max(p2["n"], 1)
+        every_slot = {"steps": K2, "ms_per_step": ms2, "value": T * 1e3 / ms2, "unit": UNIT,
+                      "kernel": "k_slot_update<12, 0>", "kernel_ms": k2_ms, "kernel_samples": p2["n"],
+                      "algorithmic_bytes_per_launch": T * N * BYTES_PER_SLOT_UPDATE,
+                      "achieved": T * N * BYTES_PER_SLOT_UPDATE / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None}
+        b2.close()
+
     if rank == 0:
         value = world * T * K / (ms * 1e-3)
         e2e_val = world * T * K / (ms_e2e * 1e-3)
         peak, peak_src = load_peak()
-        slot_ms = prof["ms_slot_update"] / max(prof["n"], 1)
-        achieved = T * N * BYTES_PER_SLOT_UPDATE / (slot_ms * 1e-3) / 1e9 if slot_ms > 0 else None
+        n_prof = max(prof["n"], 1)
+        slot_ms = prof["ms_slot_kernel"] / n_prof
+        sharing = rec < nslots
+        # units one launch processes: the distinct Gaussians (records) when identical children are shared -- the last
+        # frame's count, stationary after the first ~20 frames -- else every slot
+        units = rec if sharing else nslots
+        achieved = units * BYTES_PER_SLOT_UPDATE / (slot_ms * 1e-3) / 1e9 if slot_ms > 0 else None
         tr = load_traffic()
-        # the dominant kernel is the record-sharing slot update when the workload shares (one measurement per track)
-        kname = "k_slot_update_shared" if rec < nslots else "k_slot_update"
+        split = sharing and prof["ms_share_keys"] > 0
+        kname = ("k_slot_update_heads_direct" if split else "k_slot_update_shared") if sharing else "k_slot_update"
         ktr = ((tr or {}).get("kernels") or {}).get(kname) or {}
+        if every_slot and every_slot["achieved"]:
+            every_slot["peak"] = peak
+            every_slot["frac"] = every_slot["achieved"] / peak
+            every_slot["traffic"] = (((tr or {}).get("kernels") or {}).get("k_slot_update") or {}).get("dram_bytes_per_launch")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -395,18 +438,23 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": ktr.get("dram_bytes_per_launch"),
-                         "dram_gbs": (ktr["dram_bytes_per_launch"] / slot_ms / 1e6) if ktr and slot_ms else None,
                          "kernel": ktr.get("kernel", kname), "kernel_ms": slot_ms,
                          "kernel_samples": prof["n"], "kernel_sampling": f"CUDA events on every {PROF_EVERY}th step of the timed region",
-                         "algorithmic_bytes_per_launch": T * N * BYTES_PER_SLOT_UPDATE, "peak_source": peak_src,
+                         "units_per_launch": int(units), "slots_per_launch": int(nslots),
+                         "algorithmic_bytes_per_launch": int(units) * BYTES_PER_SLOT_UPDATE, "peak_source": peak_src,
                          "distinct_records_fraction": rec / max(nslots, 1),
-                         "note": "achieved counts SURVEY 8(d)'s 1500 B for every slot-update; with one measurement per "
-                                 "track, children that drew the same parent and component are identical and are computed "
-                                 "and stored once per warp (distinct_records_fraction of the slots), so the kernel moves "
-                                 "fewer bytes than that (traffic) and frac can exceed 1",
-                         "stage_ms": {"indicator_bounds": prof["ms_bounds"] / max(prof["n"], 1),
-                                      "slot_update": slot_ms,
-                                      "normalise_resample": prof["ms_resample"] / max(prof["n"], 1)}},
+                         "note": "SURVEY 8(d): 1500 B per slot-update.  With one measurement per track, children that "
+                                 "drew the same parent record and component are identical Gaussians and are computed "
+                                 "and stored once: a launch processes units_per_launch distinct slot-updates for "
+                                 "slots_per_launch slots.  every_slot_computed is the same workload with the sharing "
+                                 "off (k_slot_update, 1500 B for every slot)",
+                         "effective_all_slots_gbs": nslots * BYTES_PER_SLOT_UPDATE / (slot_ms * 1e-3) / 1e9 if slot_ms > 0 else None,
+                         "stage_ms": {"indicator_bounds": prof["ms_bounds"] / n_prof,
+                                      "share_keys": prof["ms_share_keys"] / n_prof,
+                                      "slot_kernel": slot_ms,
+                                      "repair": prof["ms_repair"] / n_prof,
+                                      "normalise_resample": prof["ms_resample"] / n_prof},
+                         "every_slot_computed": every_slot},
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": world * T * 8 * 8, "d2h_bytes_per_step": world * T * model.D * 8,
                     "mode": "pinned host buffers, MKF_MEM_HOST_ASYNC: copies on the library's copy streams overlap the neighbouring frames' kernels, one sync at the end",

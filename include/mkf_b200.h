@@ -240,6 +240,9 @@ int mkf_batch_profile(mkf_batch* b, int max_updates);
 int mkf_batch_profile_every(mkf_batch* b, int max_samples, int every);
 int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_update, double* ms_resample,
                            int* n_updates);
+/* the same per kernel: ms[5] = indicator bounds, record-sharing keys (0 when the frame has none), the slot kernel
+ * (k_slot_update / k_slot_update_heads_direct / k_slot_update_shared), the repair pass, normalise+resample */
+int mkf_batch_profile_read_stages(mkf_batch* b, double* ms, int* n_updates);
 
 /* Record sharing.  When the slots of a track see one measurement (MKF_MEAS_SHARED, MKF_ALIAS_INDEPENDENT), children
  * that drew the same parent and the same component are bit-identical Gaussians; the device computes and stores such a

@@ -15,6 +15,8 @@
 #include "mkf_internal.h"
 #include "mkf_kernels.cuh"
 
+// events per profiled update: start | bounds | share keys | slot kernel | repair | resample
+#define MKF_PROF_EV 6
 static std::atomic<uint64_t> g_launches{0};
 extern "C" uint64_t mkf_launch_count(void) { return g_launches.load(); }
 #define MKF_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
@@ -561,8 +563,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         return MKF_E_INVALID;
     }
     const bool prof = b->prof_on && (b->prof_tick++ % (uint64_t)b->prof_every) == 0 &&
-                      (size_t)(b->prof_n + 1) * 4 <= b->prof_ev.size();
-    cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * 4] : nullptr;
+                      (size_t)(b->prof_n + 1) * MKF_PROF_EV <= b->prof_ev.size();
+    cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * MKF_PROF_EV] : nullptr;
     if (prof) cudaEventRecord(pe[0], b->stream);
     if ((rc = launch_bounds_kernel(b, d_uind))) return rc;
     if (prof) cudaEventRecord(pe[1], b->stream);
@@ -619,6 +621,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         // (tracks of <= 64 slots go to k_resample_small, which reads per-slot weights)
         use_split = dedup && b->share_split && b->N > 64;
         a.split = use_split ? 1 : 0;
+        if (prof && !use_split) cudaEventRecord(pe[2], b->stream); // no k_share_keys in this frame: an empty interval
         const size_t smem_shared = smem + (size_t)128 * share_g * (8 + 4 * 4 + 1);
         static std::atomic<uint64_t> seen_shared{0};
         if (dedup && first_on_this_device(seen_shared)) {
@@ -643,6 +646,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         else if (use_split) {                                                          \
             mkf_launch(k_share_keys, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);                       \
             MKF_LAUNCHED();                                                            \
+            if (prof) cudaEventRecord(pe[2], b->stream);                               \
             mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(2 * sm_count(b->device)), 128, smem, b->stream, a,   \
                        b->head_count + (b->head_flip ^ 1));                            \
             b->head_flip ^= 1;                                                         \
@@ -664,6 +668,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    if (prof) cudaEventRecord(pe[3], b->stream);
     // rare tracks (cv::Cholesky failure flagged, or unsorted parents in the literal alias mode) are redone
     if (m->d == 12)
         mkf_launch(k_slot_update_repair<12>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last);
@@ -671,7 +676,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         mkf_launch(k_slot_update_repair<10>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
-    if (prof) cudaEventRecord(pe[2], b->stream);
+    if (prof) cudaEventRecord(pe[4], b->stream);
     b->cur ^= 1;
     rc = run_resample(b->stream, b->T, use_split ? b->w_rec : b->w_raw, b->N, b->N, d_upost, 1, 1, b->wsum, b->parent,
                       b->status, d_seeds, seed_stride, seed_off, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE,
@@ -679,7 +684,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
                       use_split ? b->w_raw : nullptr);
     b->shared = dedup;
     if (prof) {
-        cudaEventRecord(pe[3], b->stream);
+        cudaEventRecord(pe[5], b->stream);
         b->prof_n++;
     }
     return rc;
@@ -703,7 +708,7 @@ extern "C" int mkf_batch_profile_every(mkf_batch* b, int max_updates, int every)
     b->prof_ev.clear();
     b->prof_n = 0;
     b->prof_on = max_updates > 0;
-    for (int i = 0; i < max_updates * 4; i++) {
+    for (int i = 0; i < max_updates * MKF_PROF_EV; i++) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         b->prof_ev.push_back(e);
@@ -711,8 +716,7 @@ extern "C" int mkf_batch_profile_every(mkf_batch* b, int max_updates, int every)
     return MKF_OK;
 }
 
-extern "C" int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_update, double* ms_resample,
-                                      int* n_updates)
+extern "C" int mkf_batch_profile_read_stages(mkf_batch* b, double* ms /* 5 */, int* n_updates)
 {
     if (!b) {
         mkf_set_error("null batch");
@@ -720,19 +724,30 @@ extern "C" int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* m
     }
     CK(cudaSetDevice(b->device));
     CK(cudaStreamSynchronize(b->stream));
-    double acc[3] = {0, 0, 0};
+    double acc[MKF_PROF_EV - 1] = {0, 0, 0, 0, 0};
     for (int i = 0; i < b->prof_n; i++) {
-        for (int k = 0; k < 3; k++) {
-            float ms = 0;
-            CK(cudaEventElapsedTime(&ms, b->prof_ev[(size_t)i * 4 + k], b->prof_ev[(size_t)i * 4 + k + 1]));
-            acc[k] += ms;
+        for (int k = 0; k < MKF_PROF_EV - 1; k++) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, b->prof_ev[(size_t)i * MKF_PROF_EV + k], b->prof_ev[(size_t)i * MKF_PROF_EV + k + 1]));
+            acc[k] += t;
         }
     }
-    if (ms_bounds) *ms_bounds = acc[0];
-    if (ms_slot_update) *ms_slot_update = acc[1];
-    if (ms_resample) *ms_resample = acc[2];
+    if (ms)
+        for (int k = 0; k < MKF_PROF_EV - 1; k++) ms[k] = acc[k];
     if (n_updates) *n_updates = b->prof_n;
     b->prof_n = 0;
+    return MKF_OK;
+}
+
+extern "C" int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_update, double* ms_resample,
+                                      int* n_updates)
+{
+    double ms[MKF_PROF_EV - 1];
+    const int rc = mkf_batch_profile_read_stages(b, ms, n_updates);
+    if (rc) return rc;
+    if (ms_bounds) *ms_bounds = ms[0];
+    if (ms_slot_update) *ms_slot_update = ms[1] + ms[2] + ms[3]; // keys + slot kernel + repair
+    if (ms_resample) *ms_resample = ms[4];
     return MKF_OK;
 }
 

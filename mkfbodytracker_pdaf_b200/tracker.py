@@ -196,6 +196,13 @@ class TrackBatch:
         L.check(L.lib.mkf_batch_profile_read(self._h, C.byref(a), C.byref(b_), C.byref(c), C.byref(n)))
         return dict(ms_bounds=a.value, ms_slot_update=b_.value, ms_resample=c.value, n=n.value)
 
+    def profile_read_stages(self):
+        """summed milliseconds per kernel of the profiled updates: bounds, share keys, slot kernel, repair, resample"""
+        ms, n = (C.c_double * 5)(), C.c_int()
+        L.check(L.lib.mkf_batch_profile_read_stages(self._h, ms, C.byref(n)))
+        return dict(ms_bounds=ms[0], ms_share_keys=ms[1], ms_slot_kernel=ms[2], ms_repair=ms[3], ms_resample=ms[4],
+                    n=n.value)
+
     def close(self):
         if self._h:
             L.lib.mkf_batch_destroy(self._h)

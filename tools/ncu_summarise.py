@@ -111,7 +111,7 @@ def main(argv):
             return float(val.replace(",", "")) * UNIT_SCALE[unit]
 
         found = 0
-        for base in ("k_slot_update_shared", "k_slot_update"):
+        for base in ("k_slot_update_heads_direct", "k_share_keys", "k_slot_update_shared", "k_slot_update"):
             sel = [c for c in cols if c[1].replace("void ", "").strip().split("<")[0] == base]
             if not sel:
                 continue
@@ -129,8 +129,9 @@ def main(argv):
                 "dram_bytes_write_per_launch": round(wr),
                 "dram_bytes_per_launch": round(rd + wr),
                 "ncu_duration_us": round(us, 2),
-                "algorithmic_bytes_per_launch": 4096 * 500 * 1500,
             }
+            if base in ("k_slot_update_shared", "k_slot_update"):
+                doc["kernels"][base]["algorithmic_bytes_per_launch"] = 4096 * 500 * 1500
         if not found:
             raise SystemExit("no slot-update launch in the reports; %s left untouched" % traffic_json)
         doc["round"] = 1
