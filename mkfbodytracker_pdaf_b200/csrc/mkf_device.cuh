@@ -63,9 +63,9 @@ __device__ __forceinline__ dd dd_add(dd a, dd b) // accurate variant: error <= 2
 // `beta -= w; beta += step` loop can have accumulated, so outside that band the loop provably takes
 // the same decision.  Ambiguous tracks are re-run by the exact sequential kernel.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int mkf_count_le(dd C, double beta0, double step, int N, double tol, bool& amb)
+// df = C - beta0 (double-double)
+__device__ __forceinline__ int mkf_count_le_df(dd df, double step, int N, double tol, bool& amb)
 {
-    dd df = dd_add_d(C, -beta0);
     // quotient estimate: step = fl(1/N), so df.hi * N is within one unit of df.hi / step; the remainder test
     // below corrects it (a double division here would cost more than the rest of the function)
     double qi = floor(__dmul_rn(df.hi, (double)N));
@@ -86,6 +86,10 @@ __device__ __forceinline__ int mkf_count_le(dd C, double beta0, double step, int
     if (!(cnt > 0.0)) return 0;
     if (cnt >= (double)N) return N;
     return (int)cnt;
+}
+__device__ __forceinline__ int mkf_count_le(dd C, double beta0, double step, int N, double tol, bool& amb)
+{
+    return mkf_count_le_df(dd_add_d(C, -beta0), step, N, tol, amb);
 }
 
 // bound on the rounding error accumulated by the reference loop: every one of its <= N+L

@@ -1095,18 +1095,42 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     // pass 1: sum and NaN-ignoring max (src/pf2DRao.cpp:139,161-172).  The sum only has to be an accurate
     // normaliser (the reference's own sequential sum is no more exact); the literal loop below divides by the
     // same value, so both paths see identical normalised weights.
+    // A track that fits one tile (L <= BT * ITEMS) is read once: each thread keeps its ITEMS consecutive weights for
+    // pass 2.
+    const bool single = L <= BT * ITEMS;
+    double xs[ITEMS];
     double acc = 0.0, mx = 0.0, sq = 0.0;
-    for (int i = tid; i < L; i += BT) {
-        double x;
-        if (by_record) {
-            x = w[rep[i]];
-            w_slot_out[t * L + i] = x;
-        } else {
-            x = w[i];
+    if (single) {
+#pragma unroll
+        for (int q = 0; q < ITEMS; q++) {
+            const int i = tid * ITEMS + q;
+            double x = 0.0;
+            if (i < L) {
+                if (by_record) {
+                    x = w[rep[i]];
+                    w_slot_out[t * L + i] = x;
+                } else {
+                    x = w[i];
+                }
+                acc += x;
+                sq = fma(x, x, sq);
+                if (x > mx) mx = x;
+            }
+            xs[q] = x;
         }
-        acc += x;
-        sq = fma(x, x, sq);
-        if (x > mx) mx = x;
+    } else {
+        for (int i = tid; i < L; i += BT) {
+            double x;
+            if (by_record) {
+                x = w[rep[i]];
+                w_slot_out[t * L + i] = x;
+            } else {
+                x = w[i];
+            }
+            acc += x;
+            sq = fma(x, x, sq);
+            if (x > mx) mx = x;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1180,20 +1204,20 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
         double run = 0.0;
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) {
-            double x = (i0 + q < L) ? (by_record ? w[rep[i0 + q]] : w[i0 + q]) : 0.0;
+            double x = single ? xs[q] : ((i0 + q < L) ? (by_record ? w[rep[i0 + q]] : w[i0 + q]) : 0.0);
             if (normalise) x = __ddiv_rn(x, wsum);
             run += x;
             pre[q] = run;
         }
         double tile_tot;
         const double excl = mkf_block_excl_scan_d<BT>(run, sc_d, tile_tot);
-        const dd start = dd_add_d(carry, excl);
+        const dd start_b = dd_add_d(dd_add_d(carry, excl), -beta0); // prefix sum before my first weight, minus beta0
         int e_prev = 0; // e_{-1} = 0 by definition: no output precedes the first weight
-        if (i0 > 0 && i0 < L) e_prev = mkf_count_le(start, beta0, step, N, tol, amb);
+        if (i0 > 0 && i0 < L) e_prev = mkf_count_le_df(start_b, step, N, tol, amb);
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) {
             if (i0 + q < L) {
-                const int e = mkf_count_le(dd_add_d(start, pre[q]), beta0, step, N, tol, amb);
+                const int e = mkf_count_le_df(dd_add_d(start_b, pre[q]), step, N, tol, amb);
                 if (e > e_prev) {
                     if (DIRECT) {
                         const int rv = rep ? __ldg(rep + i0 + q) : 0;
