@@ -112,6 +112,11 @@ int mkf_model_create(mkf_model** out, int K, int d, int D, const double* means, 
  * same file.  (The reference reads BOTH arms' gamma from the right-arm file, src/pfPose.cpp:52-53,
  * quirk B4: pass the right-arm path here to reproduce it.) */
 int mkf_model_load_yaml(mkf_model** out, const char* path, const char* gamma_path, const mkf_params* params);
+/* the inverse: writes the model's GMM/PCA arrays in the same OpenCV-YAML-1.0 schema (the files the reference's
+ * launch parameters left_arm_training / right_arm_training name, bodyTrackingBag.launch:2-6; produced upstream by
+ * the gmm_training package, README.md:45-46).  f64 values round-trip bit-exactly; pca_proj / pca_mean keep `dt: f`
+ * when they hold widened floats.  `gamma` is the one the model uses (see gamma_path above). */
+int mkf_model_save_yaml(const mkf_model* m, const char* path);
 void mkf_model_destroy(mkf_model* m);
 int mkf_model_dims(const mkf_model* m, int* K, int* d, int* D);
 /* copies of the model arrays (any pointer may be NULL): the loaded GMM and the derived

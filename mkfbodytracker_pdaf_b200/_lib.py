@@ -23,7 +23,7 @@ ST_CAND_FALLBACK, ST_CAND_DEGENERATE, ST_IND_WRAP = 0x10, 0x20, 0x40
 # every symbol include/mkf_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "mkf_params_default", "mkf_last_error", "mkf_abi_version", "mkf_device_count", "mkf_model_create",
-    "mkf_model_load_yaml", "mkf_model_destroy", "mkf_model_dims", "mkf_model_get", "mkf_batch_create",
+    "mkf_model_load_yaml", "mkf_model_save_yaml", "mkf_model_destroy", "mkf_model_dims", "mkf_model_get", "mkf_batch_create",
     "mkf_batch_destroy", "mkf_batch_sync", "mkf_batch_reset", "mkf_batch_update", "mkf_batch_estimate",
     "mkf_batch_associate", "mkf_batch_assoc_results", "mkf_batch_download", "mkf_batch_upload", "mkf_resample",
     "mkf_pf2d_create", "mkf_pf2d_destroy", "mkf_pf2d_set_particles", "mkf_pf2d_get", "mkf_pf2d_update",
@@ -68,6 +68,7 @@ lib.mkf_device_count.restype = C.c_int
 lib.mkf_model_create.argtypes = [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
                                  C.POINTER(Params)]
 lib.mkf_model_load_yaml.argtypes = [C.POINTER(_vp), C.c_char_p, C.c_char_p, C.POINTER(Params)]
+lib.mkf_model_save_yaml.argtypes = [_vp, C.c_char_p]
 lib.mkf_model_destroy.argtypes = [_vp]
 lib.mkf_model_destroy.restype = None
 lib.mkf_model_dims.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]

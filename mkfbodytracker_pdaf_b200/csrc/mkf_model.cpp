@@ -414,6 +414,67 @@ extern "C" int mkf_model_load_yaml(mkf_model** out, const char* path, const char
                             proj.data.data(), pmean.data.data(), params);
 }
 
+// ------------------------------------------------------------------------------------------
+// OpenCV-YAML-1.0 writer: the schema src/pfPose.cpp:34-55 reads (and the gmm_training package of README.md:45-46
+// emits): means K x d, covs (K*d) x d, weights 1 x K, pca_proj d x D, pca_mean 1 x D, gamma K x 1.
+// Doubles are written with 17 significant digits (round-trip exact); pca_proj / pca_mean keep the reference
+// files' `dt: f` when every entry is a float widened to double, else `dt: d` (cv::FileStorage reads either and
+// the reference converts to CV_64F afterwards, src/pfPose.cpp:44-51).
+// ------------------------------------------------------------------------------------------
+static void yaml_write_mat(FILE* f, const char* key, int rows, int cols, const std::vector<double>& v, bool allow_f32)
+{
+    bool f32 = allow_f32;
+    for (size_t i = 0; f32 && i < v.size(); ++i) f32 = ((double)(float)v[i] == v[i]);
+    fprintf(f, "%s: !!opencv-matrix\n   rows: %d\n   cols: %d\n   dt: %c\n   data: [ ", key, rows, cols, f32 ? 'f' : 'd');
+    int col = 11;
+    for (size_t i = 0; i < v.size(); ++i) {
+        char buf[40];
+        int n = snprintf(buf, sizeof buf, f32 ? "%.9g" : "%.17g", v[i]);
+        // cv::FileStorage wants a real-number token: make sure integers carry a '.'
+        if (!strpbrk(buf, ".eEn")) {
+            buf[n++] = '.';
+            buf[n] = 0;
+        }
+        if (col + n + 2 > 100) {
+            fputs("\n       ", f);
+            col = 7;
+        }
+        fputs(buf, f);
+        col += n;
+        if (i + 1 < v.size()) {
+            fputs(", ", f);
+            col += 2;
+        }
+    }
+    fputs(" ]\n", f);
+}
+
+extern "C" int mkf_model_save_yaml(const mkf_model* m, const char* path)
+{
+    if (!m || !path) {
+        mkf_set_error("mkf_model_save_yaml: null argument");
+        return MKF_E_INVALID;
+    }
+    FILE* f = fopen(path, "w");
+    if (!f) {
+        mkf_set_error("cannot write model file '%s'", path);
+        return MKF_E_IO;
+    }
+    fputs("%YAML:1.0\n", f);
+    yaml_write_mat(f, "means", m->K, m->d, m->means, false);
+    yaml_write_mat(f, "covs", m->K * m->d, m->d, m->covs, false);
+    yaml_write_mat(f, "weights", 1, m->K, m->weights, false);
+    yaml_write_mat(f, "pca_proj", m->d, m->D, m->proj, true);
+    yaml_write_mat(f, "pca_mean", 1, m->D, m->pmean, true);
+    yaml_write_mat(f, "gamma", m->K, 1, m->gamma, false);
+    const bool bad = ferror(f) != 0;
+    if (fclose(f) != 0 || bad) {
+        mkf_set_error("write error on model file '%s'", path);
+        return MKF_E_IO;
+    }
+    return MKF_OK;
+}
+
 extern "C" void mkf_model_destroy(mkf_model* m) { delete m; }
 
 extern "C" int mkf_model_dims(const mkf_model* m, int* K, int* d, int* D)

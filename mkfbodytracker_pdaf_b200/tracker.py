@@ -81,6 +81,10 @@ class Model:
                                           C.byref(params) if params is not None else None))
         return cls(h)
 
+    def save(self, path):
+        """writes the model back in the reference's OpenCV-YAML-1.0 schema (src/pfPose.cpp:34-55 reads it)"""
+        L.check(L.lib.mkf_model_save_yaml(self._h, os.fsencode(path)))
+
     def arrays(self):
         K, d, D = self.K, self.d, self.D
         out = dict(means=np.zeros((K, d)), covs=np.zeros((K, d, d)), weights=np.zeros(K), gamma=np.zeros(K),

@@ -65,6 +65,39 @@ def test_model_loader_against_cv_filestorage(left_arm):
     assert np.array_equal(fs2.getNode("gamma").mat().reshape(-1), left_arm.arrays["gamma"])  # quirk B4
 
 
+def test_model_writer_round_trip(left_arm, tmp_path, rng):
+    """mkf_model_save_yaml emits the schema src/pfPose.cpp:34-55 reads; values survive bit for bit"""
+    out = tmp_path / "left.yml"
+    left_arm.mk.save(str(out))
+    back = mk.Model.load(str(out)).arrays()
+    for k in ("means", "covs", "weights", "gamma", "pca_proj", "pca_mean", "Q", "B", "H", "BH"):
+        assert np.array_equal(back[k], left_arm.arrays[k]), k
+    txt = out.read_text()
+    assert txt.startswith("%YAML:1.0\n") and txt.count("!!opencv-matrix") == 6
+    assert "pca_proj: !!opencv-matrix\n   rows: 12\n   cols: 22\n   dt: f" in txt   # widened floats stay f32 on disk
+    # another shape (launch/ChaLearn.launch:7-8 names K = 20, d = 10 files); a true-f64 pca_proj is kept as dt: d
+    K, d, D = 20, 10, 22
+    covs = np.stack([(lambda a: a @ a.T + d * np.eye(d))(rng.normal(size=(d, d))) for _ in range(K)])
+    w = rng.random(K)
+    m = mk.Model.from_arrays(rng.normal(size=(K, d)) * 30, covs.reshape(K * d, d), w / w.sum(), 0.85 + 0.1 * rng.random(K),
+                             np.linalg.qr(rng.normal(size=(D, d)))[0].T.copy(), rng.normal(size=D) * 100)
+    out2 = tmp_path / "k20.yml"
+    m.save(str(out2))
+    assert "pca_proj: !!opencv-matrix\n   rows: 10\n   cols: 22\n   dt: d" in out2.read_text()
+    a, b = m.arrays(), mk.Model.load(str(out2)).arrays()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    cv2 = pytest.importorskip("cv2")   # the parser the reference uses must accept the file as well
+    fs = cv2.FileStorage(str(out), cv2.FILE_STORAGE_READ)
+    for k in ("means", "covs", "weights", "pca_proj", "pca_mean", "gamma"):
+        got = fs.getNode(k).mat()
+        assert got.dtype == (np.float32 if k.startswith("pca_") else np.float64), k
+        assert np.array_equal(got.astype(np.float64).reshape(-1), left_arm.arrays[k].reshape(-1)), k
+    with pytest.raises(mk.MkfError) as e:
+        left_arm.mk.save(str(tmp_path / "no_such_dir" / "x.yml"))
+    assert e.value.code == L.E_IO
+
+
 def test_loader_errors(tmp_path):
     with pytest.raises(mk.MkfError) as e:
         mk.Model.load(str(tmp_path / "missing.yml"))
