@@ -112,7 +112,7 @@ def main(argv):
 
         found = 0
         for base in ("k_slot_update_heads_direct", "k_share_keys", "k_slot_update_shared", "k_slot_update"):
-            sel = [c for c in cols if c[1].replace("void ", "").strip().split("<")[0] == base]
+            sel = [c for c in cols if c[1].replace("void ", "").strip().split("<")[0].split("(")[0] == base]
             if not sel:
                 continue
             found += 1
