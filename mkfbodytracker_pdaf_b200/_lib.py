@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmkf_b200.so")
+# MKF_LIB_VARIANT=cw4 loads an experiment build of the SAME sources (csrc/Makefile `variant`) for A/B runs
+_VARIANT = os.environ.get("MKF_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "libmkf_b200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 OK = 0
 E_INVALID, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6

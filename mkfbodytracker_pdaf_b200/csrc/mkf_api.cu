@@ -336,7 +336,8 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
         }
         b->own_stream = true;
     }
-    const size_t tile_bytes = (size_t)b->lay.np * 32 * sizeof(double2);
+    constexpr int CH2 = MKF_CW / 2; // double2 per storage chunk (SlotLay::H)
+    const size_t tile_bytes = (size_t)((b->lay.np + CH2 - 1) / CH2 * CH2) * 32 * sizeof(double2);
     auto dmalloc = [&](void** p, size_t bytes) {
         if (cudaMalloc(p, bytes) != cudaSuccess) {
             cudaGetLastError();
@@ -568,7 +569,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     if (prof) cudaEventRecord(pe[0], b->stream);
     if ((rc = launch_bounds_kernel(b, d_uind))) return rc;
     if (prof) cudaEventRecord(pe[1], b->stream);
-    SlotArgs a;
+    SlotArgs a{};
     a.st_in = b->st[b->cur];
     a.st_out = b->st[b->cur ^ 1];
     a.parent = b->parent;

@@ -61,7 +61,7 @@ extern "C" int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int 
                                                                      b->parent);
     MKF_LAUNCHED();
     // run the slot kernel alone (no indicator draw, no resampling)
-    SlotArgs a;
+    SlotArgs a{};
     a.st_in = b->st[b->cur];
     a.st_out = b->st[b->cur ^ 1];
     a.parent = b->parent;

@@ -22,6 +22,10 @@
 #include "../../include/mkf_synth.h"
 
 #define MKF_M 6
+#ifndef MKF_CW
+#define MKF_CW 2 // doubles per storage chunk (2: 16-byte chunks, 4: 32-byte chunks); see SlotLay
+#endif
+static_assert(MKF_CW == 2 || MKF_CW == 4 || MKF_CW == 8, "chunk width");
 
 template <int D>
 struct SlotLay {
@@ -32,6 +36,13 @@ struct SlotLay {
     static constexpr int NC = D2 * (D2 + 1) / 2;
     static constexpr int NE = D + NA + NB + NC;
     static constexpr int NP = (NE + 1) / 2;
+    // a lane's record is stored in chunks of H consecutive double2 (MKF_CW = 2 H doubles): pair p sits in chunk p / H.
+    // H = 1 is the plain tile[pair][lane] arrangement (16-byte chunks); H = 2 gives 32-byte chunks, so a gathered
+    // record uses whole 32-byte sectors even when the neighbouring lane's record is not wanted
+    static constexpr int H = MKF_CW / 2;
+    static constexpr int NCH = (NP + H - 1) / H;   // chunks per record (the last one may hold padding pairs)
+    static constexpr int TILE2 = NCH * H * 32;     // double2 per tile of 32 records
+    __host__ __device__ static constexpr int po(int p) { return (p / H) * (32 * H) + (p % H); } // double2 offset of pair p
     static constexpr int OA = D;
     static constexpr int OB = D + NA;
     static constexpr int OC = D + NA + NB;
@@ -398,10 +409,10 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
         }
         if (active) {
             const long long sp = t * a.N + par;
-            const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+            const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
 #pragma unroll
             for (int p = 0; p < L::NP; p++) {
-                const double2 q = __ldg(src + p * 32);
+                const double2 q = __ldg(src + L::po(p));
                 v[2 * p] = q.x;
                 if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
             }
@@ -417,13 +428,13 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
         double w;
         const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
         if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
-        double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+        double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)L::TILE2 + (s & 31) * L::H;
 #pragma unroll
         for (int p = 0; p < L::NP; p++) {
             double2 q;
             q.x = v[2 * p];
             q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-            __stcs(dst + p * 32, q);
+            __stcs(dst + L::po(p), q);
         }
         a.w_raw[s] = w;
     } else {
@@ -432,13 +443,13 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
             const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
             if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
             const long long so = s + i;
-            double2* __restrict__ dst = a.st_out + (so >> 5) * (long long)(L::NP * 32) + (so & 31);
+            double2* __restrict__ dst = a.st_out + (so >> 5) * (long long)L::TILE2 + (so & 31) * L::H;
 #pragma unroll
             for (int p = 0; p < L::NP; p++) {
                 double2 q;
                 q.x = v[2 * p];
                 q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-                __stcs(dst + p * 32, q);
+                __stcs(dst + L::po(p), q);
             }
             a.w_raw[so] = w;
             if (++i >= len) break;
@@ -581,11 +592,11 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
         const int j = (int)(s - t * a.N);
         const int k = sm_k[so];
         const long long sp = t * a.N + sm_par[so];
-        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
         double v[L::NE];
 #pragma unroll
         for (int p = 0; p < L::NP; p++) {
-            const double2 q = __ldg(src + p * 32);
+            const double2 q = __ldg(src + L::po(p));
             v[2 * p] = q.x;
             if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
         }
@@ -597,13 +608,13 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
         // record position: the track's first slot in this chunk + the head's number within the track
         const long long seg = t * a.N > base ? t * a.N - base : 0;
         const long long so_rec = base + seg + (h - sm_rank[(int)seg]);
-        double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)(L::NP * 32) + (so_rec & 31);
+        double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)L::TILE2 + (so_rec & 31) * L::H;
 #pragma unroll
         for (int p = 0; p < L::NP; p++) {
             double2 q;
             q.x = v[2 * p];
             q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-            __stcs(dst + p * 32, q);
+            __stcs(dst + L::po(p), q);
         }
         h_w[h] = w;
     }
@@ -820,11 +831,11 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
     while (h < n) {
         const long long sp = (unsigned)rec.x, so_rec = (unsigned)rec.y, t = rec.z;
         const int k = rec.w;
-        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+        const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
         double v[L::NE];
 #pragma unroll
         for (int p = 0; p < L::NP; p++) {
-            const double2 q = __ldg(src + p * 32);
+            const double2 q = __ldg(src + L::po(p));
             v[2 * p] = q.x;
             if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
         }
@@ -835,13 +846,13 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
         double w;
         const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
         if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
-        double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)(L::NP * 32) + (so_rec & 31);
+        double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)L::TILE2 + (so_rec & 31) * L::H;
 #pragma unroll
         for (int p = 0; p < L::NP; p++) {
             double2 q;
             q.x = v[2 * p];
             q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-            __stcs(dst + p * 32, q);
+            __stcs(dst + L::po(p), q);
         }
         a.w_rec[so_rec] = w;
     }
@@ -885,10 +896,10 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
                 const int snap = a.alias_chain ? lt[par] : -1;
                 const double2* base_p = snap >= 0 ? (const double2*)a.st_out : a.st_in;
                 const long long sp = t * a.N + (snap >= 0 ? snap : par);
-                const double2* src = base_p + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+                const double2* src = base_p + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
                 double v[L::NE];
                 for (int p = 0; p < L::NP; p++) {
-                    const double2 qq = src[p * 32]; // plain load: may be a snapshot this thread stored earlier
+                    const double2 qq = src[L::po(p)]; // plain load: may be a snapshot this thread stored earlier
                     v[2 * p] = qq.x;
                     if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
                 }
@@ -896,12 +907,12 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
                 mkf_load_meas(a, t, j, zc);
                 const int k = mkf_component_of(bt, a.K, j);
                 slot_math<D, true>(v, a.comp_const + (long long)k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
-                double2* dst = a.st_out + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+                double2* dst = a.st_out + (s >> 5) * (long long)L::TILE2 + (s & 31) * L::H;
                 for (int p = 0; p < L::NP; p++) {
                     double2 qq;
                     qq.x = v[2 * p];
                     qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-                    dst[p * 32] = qq;
+                    dst[L::po(p)] = qq;
                 }
                 a.w_raw[s] = w;
                 if (a.dedup) a.rep[s] = j; // the redone track stores every slot at its own position
@@ -1392,9 +1403,9 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __res
             if (idx[u] < 0) continue;
             if (idx[u] != have) {
                 const long long sp = t * N + idx[u];
-                const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+                const double2* __restrict__ src = st + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
 #pragma unroll
-                for (int p = 0; p < D / 2; p++) v[p] = __ldg(src + p * 32);
+                for (int p = 0; p < D / 2; p++) v[p] = __ldg(src + L::po(p));
                 have = idx[u];
             }
 #pragma unroll
@@ -1404,15 +1415,43 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __res
             }
         }
     }
+    // warp reduction that halves the vector at every step: at offset o the lanes with bit o clear keep the lower half
+    // of their n partial sums and receive the partner's lower half, the others keep the upper half -- 6+3+2+1+1 = 13
+    // shuffles for D = 12 instead of 5 per element (60).  A lane ends with the warp total of ONE element in acc[0].
+    int e_mine = 0;   // which element my acc[0] ends up holding
+    bool valid = true; // false: my acc[0] is padding
+    {
+        int n = D;
 #pragma unroll
-    for (int e = 0; e < D; e++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const int h = (n + 1) / 2;
+            const bool upper = (lane & o) != 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+            for (int e = 0; e < h; e++) {
+                const double lo = acc[e];
+                const double hi = (e + h < n) ? acc[e + h] : 0.0;
+                const double got = __shfl_xor_sync(0xffffffffu, upper ? lo : hi, o);
+                acc[e] = (upper ? hi : lo) + got;
+            }
+            n = h;
+        }
+        // element index: walk the steps backwards; taking the upper half at a step with (n, h) maps local e to e + h
+        int ns[5], nn = D;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            ns[q] = nn;
+            nn = (nn + 1) / 2;
+        }
+#pragma unroll
+        for (int q = 4; q >= 0; q--) {
+            const int o = 16 >> q, hq = (ns[q] + 1) / 2;
+            if (lane & o) {
+                if (e_mine + hq >= ns[q]) valid = false;
+                e_mine += hq;
+            }
+        }
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int e = 0; e < D; e++) red[wid][e] = acc[e];
-    }
+    if (valid) red[wid][e_mine] = acc[0];
     __syncthreads();
     if (tid < D) {
         double s = 0.0;
@@ -1463,10 +1502,10 @@ __global__ void __launch_bounds__(128) k_estimate_small(const double2* __restric
         for (int e = 0; e < D; e++) acc[e] = 0.0;
         for (int j = l; j < N; j += GROUP) {
             const long long sp = t * N + __ldg(parent + t * N + j);
-            const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+            const double2* __restrict__ src = st + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
 #pragma unroll
             for (int p = 0; p < D / 2; p++) {
-                const double2 q = __ldg(src + p * 32);
+                const double2 q = __ldg(src + L::po(p));
                 acc[2 * p] += q.x;
                 acc[2 * p + 1] += q.y;
             }
@@ -1507,12 +1546,12 @@ __global__ void k_reset(double2* __restrict__ st, int32_t* __restrict__ parent, 
     const int j = (int)(s - t * N);
     const int k = mkf_component_of(bounds + t * (K + 2), K, j);
     const double* __restrict__ ic = init_const + (long long)k * L::NE;
-    double2* __restrict__ dst = st + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+    double2* __restrict__ dst = st + (s >> 5) * (long long)L::TILE2 + (s & 31) * L::H;
     for (int p = 0; p < L::NP; p++) {
         double2 q;
         q.x = ic[2 * p];
         q.y = (2 * p + 1 < L::NE) ? ic[2 * p + 1] : 0.0;
-        dst[p * 32] = q;
+        dst[L::po(p)] = q;
     }
     parent[s] = j;
 }
@@ -1564,12 +1603,12 @@ __global__ void k_upload(double2* __restrict__ st, int32_t* __restrict__ parent,
             }
             v[D + packed_index_dev<D>(r, c)] = 0.5 * (a1 + a2);
         }
-    double2* __restrict__ dst = st + (s >> 5) * (long long)(L::NP * 32) + (s & 31);
+    double2* __restrict__ dst = st + (s >> 5) * (long long)L::TILE2 + (s & 31) * L::H;
     for (int p = 0; p < L::NP; p++) {
         double2 q;
         q.x = v[2 * p];
         q.y = v[2 * p + 1];
-        dst[p * 32] = q;
+        dst[L::po(p)] = q;
     }
     parent[s] = (int)(s % N);
 }
@@ -1585,10 +1624,10 @@ __global__ void k_download(const double2* __restrict__ st, const int32_t* __rest
     if (s >= total) return;
     const long long t = s / N;
     const long long sp = t * N + parent[s];
-    const double2* __restrict__ src = st + (sp >> 5) * (long long)(L::NP * 32) + (sp & 31);
+    const double2* __restrict__ src = st + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
     double v[L::NP * 2];
     for (int p = 0; p < L::NP; p++) {
-        const double2 q = src[p * 32];
+        const double2 q = src[L::po(p)];
         v[2 * p] = q.x;
         v[2 * p + 1] = q.y;
     }

@@ -414,10 +414,11 @@ def test_degenerate_frame_then_recovery(left_arm, alias):
             assert rel_err(d["x"][t], xo) <= RTOL and rel_err(d["P"][t], Po) <= RTOL
 
 
-def test_cholesky_failure_branch_matches_oracle(left_arm, rng):
+@pytest.mark.parametrize("N", [64, 200])  # 200: the two-launch record-sharing path (k_slot_update_heads_direct)
+def test_cholesky_failure_branch_matches_oracle(left_arm, rng, N):
     """S not positive definite: cv::Cholesky fails, chol() returns the partially factored clone and the
     reference carries on with LU inverses (src/pf2DRao.cpp:37,52; src/KF_model.cpp:21)"""
-    T, N = 2, 64
+    T = 2
     fs = oracle_filters(left_arm, T, N, [0.3, 0.8])
     H = left_arm.np.H
     xs, Ps = [], []
