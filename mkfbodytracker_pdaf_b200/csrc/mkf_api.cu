@@ -619,6 +619,15 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             const int v = e ? atoi(e) : 8;
             return (v == 4 || v == 8 || v == 16) ? v : 8;
         }();
+        // CTAs of k_slot_update_heads_direct per SM: 2 are resident; with more, the later ones start as earlier ones
+        // finish and the gather / arithmetic / store phases of the resident CTAs drift apart (measured at 4096 x 500:
+        // 77.7 us with 2, 74.5 with 4, 72.1 with 12-24).  The kernel strides over the list, so any grid is correct.
+        // MKF_HEADS_CTAS_PER_SM overrides for experiments.
+        static const int heads_ctas_per_sm = [] {
+            const char* e = getenv("MKF_HEADS_CTAS_PER_SM");
+            const int v = e ? atoi(e) : 12;
+            return (v >= 1 && v <= 64) ? v : 12;
+        }();
         // (tracks of <= 64 slots go to k_resample_small, which reads per-slot weights)
         use_split = dedup && b->share_split && b->N > 64;
         a.split = use_split ? 1 : 0;
@@ -648,7 +657,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             mkf_launch(k_share_keys, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);                       \
             MKF_LAUNCHED();                                                            \
             if (prof) cudaEventRecord(pe[2], b->stream);                               \
-            mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(2 * sm_count(b->device)), 128, smem, b->stream, a,   \
+            mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(heads_ctas_per_sm * sm_count(b->device)), 128, smem, b->stream, a,   \
                        b->head_count + (b->head_flip ^ 1));                            \
             b->head_flip ^= 1;                                                         \
         } else if (dedup && share_g == 4)                                                \
