@@ -228,6 +228,11 @@ int mkf_pf2d_get(mkf_pf2d* p, double* particles, double* w_norm, int32_t* parent
  * isotropic 2-D likelihoods), normalise, systematic resample, random-walk predict.
  * meas T x 2 x 2, u T, noise T x N x d standard normals (NULL: no predict noise). */
 int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u, const double* noise, int mem);
+/* ParticleFilter::getEstimator of src/pf2D.cpp:79-88: est (T x d) = sum_i weights[i] * particles.row(i), the weights
+ * being the normalised ones the last update computed (resample() does not reset them, src/pf2D.cpp:225-268) and the
+ * particles the resampled + predicted ones; before the first update, or after a degenerate one, weights are 1/N.
+ * Device outputs are ordered on the filter's stream; host outputs are complete on return. */
+int mkf_pf2d_estimate(mkf_pf2d* p, double* est, int mem);
 int mkf_pf2d_sync(mkf_pf2d* p);
 
 /* ---- synthetic workload (include/mkf_synth.h), generated on the device ---- */

@@ -262,6 +262,45 @@ extern "C" int mkf_pf2d_create(mkf_pf2d** out, int64_t T, int N, int d, int K, c
     return MKF_OK;
 }
 
+// ParticleFilter::getEstimator of the legacy filter (src/pf2D.cpp:79-88): sum_i weights[i] * particles.row(i), with
+// the weights as update() left them -- normalised but NOT reset by resample() (src/pf2D.cpp:174-177,225-268), so they
+// pair the pre-resample weights with the resampled, predicted particles exactly as the reference does; 1/N after the
+// degenerate branch (:246-250).  One CTA per filter, tree sum (the reference sums in index order).
+__global__ void __launch_bounds__(256) k_pf2d_estimate(const double* __restrict__ part, const double* __restrict__ w_raw,
+                                                        const double* __restrict__ wsum,
+                                                        const uint32_t* __restrict__ status, int N, int d,
+                                                        double* __restrict__ est)
+{
+    __shared__ double red[8][12];
+    const long long t = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double ws = wsum[t];
+    const bool flat = (status[t] & MKF_ST_POST_DEGENERATE) != 0 || !(ws > 0.0); // (no update yet: weights are 1/N)
+    const double inv_n = __ddiv_rn(1.0, (double)N);
+    double acc[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) acc[c] = 0.0;
+    for (int i = tid; i < N; i += 256) {
+        const double w = flat ? inv_n : __ddiv_rn(w_raw[t * N + i], ws);
+        const double* __restrict__ x = part + (t * N + i) * d;
+#pragma unroll
+        for (int c = 0; c < 12; c++)
+            if (c < d) acc[c] = fma(w, x[c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        if (lane == 0) red[wid][c] = acc[c];
+    }
+    __syncthreads();
+    if (tid < d) {
+        double s = 0.0;
+        for (int q = 0; q < 8; q++) s += red[q][tid];
+        est[t * d + tid] = s;
+    }
+}
+
 template <class Tp>
 static int pf_in_ptr(mkf_pf2d* p, const Tp* ptr, size_t count, int mem, DevBuf& stage, const Tp** out)
 {
@@ -378,6 +417,37 @@ extern "C" int mkf_pf2d_get(mkf_pf2d* p, double* particles, double* w_norm, int3
     if (e != cudaSuccess) {
         mkf_set_error("mkf_pf2d_get: %s", cudaGetErrorString(e));
         return MKF_E_CUDA;
+    }
+    return MKF_OK;
+}
+
+extern "C" int mkf_pf2d_estimate(mkf_pf2d* p, double* est, int mem)
+{
+    if (!p || !est) {
+        mkf_set_error("mkf_pf2d_estimate: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    const bool host = !is_device_ptr(est, mem);
+    const size_t bytes = (size_t)p->T * p->d * 8;
+    DevBuf tmp;
+    double* dst = est;
+    if (host) {
+        int rc = tmp.ensure(bytes);
+        if (rc) return rc;
+        dst = (double*)tmp.p;
+    }
+    k_pf2d_estimate<<<(unsigned)p->T, 256, 0, p->stream>>>(p->part[p->cur], p->w_raw, p->wsum, p->status, p->N, p->d, dst);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if (host) {
+        CK(cudaMemcpyAsync(est, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        tmp.release();
+        if (e != cudaSuccess) {
+            mkf_set_error("mkf_pf2d_estimate: %s", cudaGetErrorString(e));
+            return MKF_E_CUDA;
+        }
     }
     return MKF_OK;
 }

@@ -303,6 +303,12 @@ class Pf2dBatch:
         L.check(L.lib.mkf_pf2d_get(self._h, p.ctypes.data, w.ctypes.data, par.ctypes.data, L.MEM_HOST))
         return p, w, par
 
+    def estimate(self):
+        """legacy getEstimator (src/pf2D.cpp:79-88): sum_i weights[i] * particles.row(i) per filter, T x d"""
+        est = np.zeros((self.T, self.d))
+        L.check(L.lib.mkf_pf2d_estimate(self._h, est.ctypes.data, L.MEM_HOST))
+        return est
+
     def sync(self):
         L.check(L.lib.mkf_pf2d_sync(self._h))
 

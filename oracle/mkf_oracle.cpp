@@ -875,6 +875,14 @@ extern "C" void orc_pf2d_get_particles(const orc_pf2d* p, double* particles, dou
     if (particles) std::copy(p->particles.begin(), p->particles.end(), particles);
     if (weights) std::copy(p->weights.begin(), p->weights.end(), weights);
 }
+// getEstimator (src/pf2D.cpp:79-88): `estimate = estimate + weights[i]*particles.row(i)` from an empty Mat, taken as
+// zeros(1, d); the weights are whatever update() / the constructor left (resample() does not reset them)
+extern "C" void orc_pf2d_estimate(const orc_pf2d* p, double* est)
+{
+    for (int c = 0; c < p->d; c++) est[c] = 0.0;
+    for (int i = 0; i < p->N; i++)
+        for (int c = 0; c < p->d; c++) est[c] = est[c] + p->weights[i] * p->particles[(size_t)i * p->d + c];
+}
 extern "C" void orc_pf2d_get_gmm(const orc_pf2d* p, double* sigma_i, double* det_s)
 {
     if (sigma_i) std::copy(p->sigma_i.begin(), p->sigma_i.end(), sigma_i);

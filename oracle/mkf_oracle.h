@@ -111,6 +111,8 @@ orc_pf2d* orc_pf2d_create(int N, int d, int K, const double* means, const double
 void orc_pf2d_destroy(orc_pf2d* p);
 void orc_pf2d_set_particles(orc_pf2d* p, const double* particles /* N x d */);
 void orc_pf2d_get_particles(const orc_pf2d* p, double* particles, double* weights);
+/* ParticleFilter::getEstimator (src/pf2D.cpp:79-88): est[d] = sum_i weights[i] * particles.row(i), index order */
+void orc_pf2d_estimate(const orc_pf2d* p, double* est);
 void orc_pf2d_get_gmm(const orc_pf2d* p, double* sigma_i /* K x d x d */, double* det_s /* K */);
 /* update(measurement 2 x 2) = weight + normalise + resample + predict (src/pf2D.cpp:148-210).
  * u: injected uniform for resample (replaces rand()/RAND_MAX); noise N x d standard normals scaled by 5

@@ -88,6 +88,7 @@ def lib():
     L.orc_pf2d_set_particles.argtypes = [C.c_void_p, _dp]
     L.orc_pf2d_get_particles.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_pf2d_get_gmm.argtypes = [C.c_void_p, _dp, _dp]
+    L.orc_pf2d_estimate.argtypes = [C.c_void_p, _dp]
     L.orc_pf2d_update.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp, _ip]
     L.orc_bench_tracks.restype = C.c_double
     L.orc_bench_tracks.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
@@ -290,6 +291,11 @@ class Pf2d:
         w = np.zeros(self.N)
         lib().orc_pf2d_get_particles(self.h, _ptr(p, _dp), _ptr(w, _dp))
         return p, w
+
+    def estimate(self):
+        est = np.zeros(self.d)
+        lib().orc_pf2d_estimate(self.h, _ptr(est, _dp))
+        return est
 
     def gmm(self):
         si = np.zeros((self.K, self.d, self.d))

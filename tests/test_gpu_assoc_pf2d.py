@@ -167,6 +167,10 @@ def test_pf2d_matches_oracle(d, N):
         o = orc.Pf2d(N, means, covs, wts)
         o.set_particles(parts[t])
         ofs.append(o)
+    # legacy getEstimator (src/pf2D.cpp:79-88) before any update: weights are the constructor's 1/N
+    est0 = pb.estimate()
+    for t in range(T):
+        assert np.max(np.abs(est0[t] - ofs[t].estimate()) / np.abs(ofs[t].estimate())) <= 1e-12
     mism = 0
     for frame in range(3):
         cur = np.stack([o.get()[0] for o in ofs])
@@ -176,8 +180,10 @@ def test_pf2d_matches_oracle(d, N):
         pb.set_particles(cur)  # teacher-forced: float-expf rounding may differ by 1 float ulp (quirk B12)
         pb.update(meas, u, noise)
         p, w, par = pb.get()
+        rs = []
         for t in range(T):
             r = ofs[t].update(meas[t], u[t], noise[t])
+            rs.append(r)
             assert rel_err_weights(w[t], r["w_norm"]) <= 1e-6
             # the resampler itself is exact: indices equal the oracle loop applied to the GPU's weights
             want, _ = orc.resample(w[t], N, u[t])
@@ -186,5 +192,13 @@ def test_pf2d_matches_oracle(d, N):
             exp = cur[t][par[t]].copy()
             exp[:, :8] = exp[:, :8] + noise[t][:, :8] * 5.0
             assert np.array_equal(p[t], exp)
+        # getEstimator after the update: the un-reset normalised weights against the resampled, predicted particles
+        est = pb.estimate()
+        for t in range(T):
+            want = (w[t][:, None] * p[t]).sum(axis=0)
+            assert np.max(np.abs(est[t] - want) / np.abs(want)) <= 1e-12
+            if np.array_equal(par[t], rs[t]["parents"]):
+                eo = ofs[t].estimate()
+                assert np.max(np.abs(est[t] - eo) / np.abs(eo)) <= 1e-5  # weights carry the float-expf ulp (quirk B12)
     print(f"pf2d d={d} N={N}: index mismatches vs oracle weights {mism}")
     assert mism <= 3 * T * N * 0.01

@@ -84,3 +84,67 @@ def test_shim_driver_against_oracle(left_arm):
     assert np.abs(sm - pose[:2]).max() < 4.0  # 2000 draws with sd 37.6
     assert lines["COPY"] == ["deep", "1", "shallow", "1"]
     assert lines["ERR"] == ["-1"]
+
+
+def test_legacy_shim_header_mirrors_reference_interfaces():
+    """CPU check: every public name of src/pf2D.h exists in the legacy shim"""
+    txt = open(os.path.join(ROOT, "include", "mkf_shims_pf2d.hpp")).read()
+    for name in ("class my_gmm", "void loadGaussian(cv::Mat u, cv::Mat s, double w)", "std::vector<cv::Mat> mean;",
+                 "std::vector<cv::Mat> sigma_i;", "std::vector<double> det_s;", "std::vector<double> weight;", "int N;",
+                 "class ParticleFilter", "ParticleFilter(int numParticles, int numDims, bool side1)", "ParticleFilter()",
+                 "void predict()", "void update(cv::Mat measurement)", "cv::Mat getEstimator()", "my_gmm gmm;"):
+        assert name in txt, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,d", [(300, 8), (1000, 12)])
+def test_legacy_shim_driver_against_oracle(N, d):
+    """mkf_legacy::ParticleFilter (src/pf2D.h:25-51) driven from C++; the trace is replayed through the oracle's
+    restatement of src/pf2D.cpp with the same particles, uniform and noise"""
+    drv = os.path.join(ROOT, "tests", "shim_pf2d_driver")
+    if not os.path.exists(drv):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests"), "shim_pf2d_driver"], check=True)
+    frames = 3
+    out = subprocess.run([drv, str(N), str(d), str(frames), "11"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr
+    recs = []
+    for ln in out.stdout.splitlines():
+        tok = ln.split()
+        if tok[0] in ("DET_S", "U", "RANGE"):
+            recs.append((tok[0], np.array(tok[1:], float)))
+        else:
+            r, c = int(tok[1]), int(tok[2])
+            recs.append((tok[0], np.array(tok[3:], float).reshape(r, c)))
+    get = lambda tag: [v for t, v in recs if t == tag]
+    means = np.concatenate(get("MEAN"))
+    covs = np.stack(get("SIGMA"))
+    K = means.shape[0]
+    o = orc.Pf2d(N, means, covs, np.full(K, 1.0 / K))
+    si, ds = o.gmm()
+    # my_gmm::loadGaussian's public members (src/pf2D.cpp:28-37)
+    assert np.allclose(np.stack(get("SIGMA_I")), si, rtol=1e-9, atol=0)
+    assert np.allclose(np.concatenate(get("DET_S")), ds, rtol=1e-12)
+    # constructor: column 6 on the half of the image `side` selects, others across the image (src/pf2D.cpp:58-70)
+    rg = get("RANGE")[0]
+    assert 321 <= rg[0] < 640 and 321 <= rg[1] < 640 and 1 <= rg[2] < 640 and 1 <= rg[3] < 480
+    parts, meas, us, noise, after, est = (get(t) for t in ("PART", "MEAS", "U", "NOISE", "AFTER", "EST"))
+    assert len(parts) == frames
+    o.set_particles(parts[0])
+    assert np.allclose(get("EST0")[0][0], o.estimate(), rtol=1e-12)
+    for f in range(frames):
+        o.set_particles(parts[f])  # teacher-forced per frame (float-expf ulp, quirk B12, may move an index)
+        r = o.update(meas[f], float(us[f][0]), noise[f])
+        po, wo = o.get()
+        same = np.array_equal(after[f], po)
+        # resampled + predicted particles: identical rows wherever the index agrees
+        agree = (after[f] == po).all(axis=1).mean()
+        assert agree >= 0.99, agree
+        if same:
+            eo = o.estimate()
+            assert np.max(np.abs(est[f][0] - eo) / np.abs(eo)) <= 1e-5
+        if f + 1 < frames:
+            assert np.array_equal(parts[f + 1], after[f])
+    # stand-alone predict(): N(0, 5) on the first eight dimensions only (src/pf2D.cpp:90-102)
+    pred = get("PRED")[0]
+    dlt = pred - after[-1]
+    assert np.all(dlt[:, 8:] == 0) and 3.5 < dlt[:, :8].std() < 6.5
