@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
 //                                flags, block scan; writes rep[] (final) and appends one 16-byte record per head
 //                                {source record, destination record, track, component} to a batch-wide list (one
 //                                atomicAdd per chunk; the order of the chunks in the list is immaterial);
-//   k_slot_update_heads_direct   persistent, 2 CTAs per SM, one thread per list entry, no barrier: gather, slot
+//   k_slot_update_heads_direct   grid-stride over the list (12 CTAs per SM, 2 resident), one thread per list entry, no barrier: gather, slot
 //                                arithmetic, store; the weight goes to w_rec[] at the record's position.  One
 //                                dependent hop (the gather) in front of the arithmetic; the next step's list entry is
 //                                already in flight.  The kernel moves 1 440 B per distinct Gaussian and runs at ~65 %

@@ -130,3 +130,39 @@ def test_config3_full_size_gate_and_bins(left_arm, right_arm):
         want = orc.associate(fL, fR, cand[t], Lv[t], roi[t], u_c[t])
         assert np.array_equal(res["gate"][t], want["gate"]) and np.array_equal(bins[t], want["bins"])
         assert rel_err_weights(w[t], want["weights"]) <= RTOL
+
+
+def test_legacy_pf2d_full_size():
+    """config 4's size for the legacy plain filter (src/pf2D.cpp): 256 filters x 65 536 particles, d = 8, K = 15.
+    Size-independent properties on every filter, the oracle on one (65 536 particles take it a second)."""
+    rng = np.random.default_rng(4)
+    T, N, d, K = 256, 65536, 8, 15
+    means = rng.uniform(100, 400, (K, d))
+    a = rng.standard_normal((K, d, d))
+    covs = 40.0 * (a @ a.transpose(0, 2, 1) + d * np.eye(d))
+    wts = rng.dirichlet(np.ones(K))
+    pb = mk.Pf2dBatch(T, N, means, covs, wts)
+    parts = means[rng.integers(0, K, (T, N))] + rng.standard_normal((T, N, d)) * 6
+    pb.set_particles(parts)
+    meas = np.stack([parts[:, :, 6].mean(1), parts[:, :, 7].mean(1), parts[:, :, 0].mean(1), parts[:, :, 1].mean(1)],
+                    axis=1).reshape(T, 2, 2)
+    u = rng.random(T)
+    noise = rng.standard_normal((T, N, d))
+    pb.update(meas, u, noise)
+    p, w, par = pb.get()
+    est = pb.estimate()
+    assert np.allclose(w.sum(1), 1.0, rtol=0, atol=1e-10)
+    check_resample_properties(par, w, N, range(0, T, 37))
+    exp = np.take_along_axis(parts, par[:, :, None].astype(np.int64), axis=1)
+    exp[:, :, :8] += noise[:, :, :8] * 5.0
+    assert np.array_equal(p, exp)                       # particles.row(i) = old.row(parent_i) + N(0,5) (:90-102,:262)
+    want = np.einsum("tn,tnd->td", w, p)
+    assert np.max(np.abs(est - want) / np.abs(want)) <= 1e-11
+    t = 101
+    o = orc.Pf2d(N, means, covs, wts)
+    o.set_particles(parts[t])
+    r = o.update(meas[t], u[t], noise[t])
+    assert rel_err_weights(w[t], r["w_norm"]) <= 1e-6    # float expf inside (quirk B12)
+    ref_par, _ = orc.resample(w[t], N, u[t])            # the reference's loop on the device's weights: bit-exact
+    assert np.array_equal(par[t], ref_par)
+    assert (par[t] != r["parents"]).mean() <= 0.01
