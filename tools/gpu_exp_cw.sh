@@ -1,4 +1,4 @@
-# A/B of the storage chunk width (SlotLay::H): default build vs csrc `make variant CW=4`
+# A/B of the storage chunk width (SlotLay::H): default build vs `make -C mkfbodytracker_pdaf_b200/csrc variant NAME=cw4 DEFS=-DMKF_CW=4` (and NAME=cw8 DEFS=-DMKF_CW=8)
 mkdir -p gpurun_out
 V=${V:-cw4}
 MKF_LIB_VARIANT=$V timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
