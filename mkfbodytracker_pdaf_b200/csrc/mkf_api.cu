@@ -191,6 +191,11 @@ struct mkf_batch {
     DevBuf in_meas, in_u0, in_u1, in_seed, out_a, out_b, in_x, in_p;
     AsyncIo aio;
     // association scratch (arm0 owns)
+    // MKF_MEAS_CAND source of the next update_device call (set and cleared by mkf_batch_associate)
+    const double* cm_cand = nullptr;
+    const int32_t* cm_bins = nullptr;
+    const double* cm_roi = nullptr;
+    int cm_C = 0, cm_hand = 0;
     DevBuf as_cand, as_L, as_roi, as_u, as_w, as_gate, as_bins, as_meas, as_wsum, as_hand, as_status, as_seed,
         as_ui, as_up;
     int as_C = 0;
@@ -578,7 +583,21 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     // mode, where duplicates are filtered one after the other)
     // Worth it when a component owns several slots of a track (N >= 4 K); at N = K = 15 nearly every slot is its own
     // (parent, component) pair and the bookkeeping costs more than it saves (measured: 3.65 -> 4.15 ms at 1 M x 15).
-    const bool dedup = b->dedup_ok && meas_layout == MKF_MEAS_SHARED && b->stage == 3 && b->N >= 4 * m->K;
+    // ... or one of a few candidate columns (MKF_MEAS_CAND): the candidate bin is then part of the key, which only the
+    // two-launch path carries
+    const bool dedup = b->dedup_ok && b->stage == 3 && b->N >= 4 * m->K &&
+                       (meas_layout == MKF_MEAS_SHARED ||
+                        (meas_layout == MKF_MEAS_CAND && b->share_split && b->N > 64));
+    a.cand = b->cm_cand;
+    a.bins = b->cm_bins;
+    a.roi = b->cm_roi;
+    a.cand_C = b->cm_C;
+    a.hand = b->cm_hand;
+    a.neck = m->prm.neck_offset;
+    if (meas_layout == MKF_MEAS_CAND && (!a.cand || !a.bins || !a.roi)) {
+        mkf_set_error("internal: MKF_MEAS_CAND without a candidate source");
+        return MKF_E_INVALID;
+    }
     a.dedup = dedup ? 1 : 0;
     a.rep = dedup ? b->rep : nullptr;
     a.hd16 = b->hd16;

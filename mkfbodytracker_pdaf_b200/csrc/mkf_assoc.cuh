@@ -123,6 +123,16 @@ __global__ void k_assoc_meas(const double* __restrict__ cand_xy, const double* _
     }
 }
 
+// the status part of k_assoc_meas alone: candidate-resample flags of (person, hand) -> the arm batch's track status
+__global__ void k_assoc_status(const uint32_t* __restrict__ as_status, long long T, uint32_t* __restrict__ status0,
+                               uint32_t* __restrict__ status1)
+{
+    const long long th = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (th >= T * 2) return;
+    const uint32_t st = as_status[th];
+    if (st) atomicOr(((th & 1) ? status1 : status0) + (th >> 1), st);
+}
+
 static int estimate_pose_device(mkf_batch* b, double* d_pose) { return launch_estimate(b, nullptr, d_pose); }
 
 extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const double* cand_xy, const uint8_t* cand_L,
@@ -159,13 +169,18 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
         if ((rc = in_ptr(b, u_ind, (size_t)T * 2, mem, b->as_ui, &d_ui))) return rc;
         if ((rc = in_ptr(b, u_post, (size_t)T * 2, mem, b->as_up, &d_up))) return rc;
     }
+    static const bool materialise = [] {
+        const char* e = getenv("MKF_ASSOC_MATERIALISE");
+        return e && e[0] == '1';
+    }();
+    const bool gather = do_update && !materialise; // see below, in front of the update
     // keep the device copy of the candidates alive for mkf_batch_assoc_results / the measurement gather
     if ((rc = b->as_w.ensure((size_t)T * 2 * C * sizeof(double))) || (rc = b->as_gate.ensure((size_t)T * 2 * C)) ||
         (rc = b->as_bins.ensure((size_t)T * 2 * N * sizeof(int32_t))) ||
         (rc = b->as_wsum.ensure((size_t)T * 2 * sizeof(double))) ||
         (rc = b->as_status.ensure((size_t)T * 2 * sizeof(uint32_t))) ||
         (rc = b->as_hand.ensure((size_t)T * (a0->m->D + a1->m->D) * sizeof(double))) ||
-        (rc = b->as_meas.ensure((size_t)T * 2 * 6 * N * sizeof(double))))
+        (!gather && (rc = b->as_meas.ensure((size_t)T * 2 * 6 * N * sizeof(double)))))
         return rc;
     b->as_C = C;
     double* d_pose0 = (double*)b->as_hand.p;
@@ -200,12 +215,21 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
                            (double*)b->as_wsum.p, (int32_t*)b->as_bins.p, (uint32_t*)b->as_status.p, d_seeds, 3, 0,
                            MKF_ST_CAND_FALLBACK, MKF_ST_CAND_DEGENERATE)))
         return rc;
+    // With the update following at once the per-slot columns are not materialised: the slot kernels assemble a
+    // slot's column from the ROI and the candidate its bin selects (MKF_MEAS_CAND; 4 bytes per slot instead of 48
+    // written and read back), and slots that drew the same parent record, component AND candidate share one child.
+    // MKF_ASSOC_MATERIALISE=1 keeps the T x 6 x N columns (A/B runs).
     double* d_meas0 = (double*)b->as_meas.p;
     double* d_meas1 = d_meas0 + (size_t)T * 6 * N;
-    k_assoc_meas<<<grid_for(T * 2 * N, 256), 256, 0, b->stream>>>(d_cand, d_roi, (const int32_t*)b->as_bins.p,
-                                                                  (const uint32_t*)b->as_status.p, T, N, C,
-                                                                  prm.neck_offset, d_meas0, d_meas1, a0->status,
-                                                                  a1->status);
+    if (gather) {
+        k_assoc_status<<<grid_for(T * 2, 256), 256, 0, b->stream>>>((const uint32_t*)b->as_status.p, T, a0->status,
+                                                                    a1->status);
+    } else {
+        k_assoc_meas<<<grid_for(T * 2 * N, 256), 256, 0, b->stream>>>(d_cand, d_roi, (const int32_t*)b->as_bins.p,
+                                                                      (const uint32_t*)b->as_status.p, T, N, C,
+                                                                      prm.neck_offset, d_meas0, d_meas1, a0->status,
+                                                                      a1->status);
+    }
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (!do_update) return MKF_OK;
@@ -222,9 +246,24 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
     CK(cudaMemcpy2DAsync(s1.p, 8, d_up, 16, 8, (size_t)T, cudaMemcpyDeviceToDevice, b->stream));
     CK(cudaMemcpy2DAsync(s3.p, 8, d_up + 1, 16, 8, (size_t)T, cudaMemcpyDeviceToDevice, b->stream));
     // seeds layout T x 2 x 3: per arm [candidate resample, indicator resample (unused), posterior resample]
-    if ((rc = update_device(a0, d_meas0, MKF_MEAS_PER_SLOT, (const double*)s0.p, (const double*)s1.p, 1, d_seeds, 6, 2)))
-        return rc;
-    return update_device(a1, d_meas1, MKF_MEAS_PER_SLOT, (const double*)s2.p, (const double*)s3.p, 1, d_seeds, 6, 5);
+    const int lay = gather ? MKF_MEAS_CAND : MKF_MEAS_PER_SLOT;
+    mkf_batch* arms[2] = {a0, a1};
+    const double* ui[2] = {(const double*)s0.p, (const double*)s2.p};
+    const double* up[2] = {(const double*)s1.p, (const double*)s3.p};
+    for (int h = 0; h < 2; h++) {
+        mkf_batch* ab = arms[h];
+        ab->cm_cand = d_cand;
+        ab->cm_bins = (const int32_t*)b->as_bins.p;
+        ab->cm_roi = d_roi;
+        ab->cm_C = C;
+        ab->cm_hand = h;
+        rc = update_device(ab, gather ? nullptr : (h ? d_meas1 : d_meas0), lay, ui[h], up[h], 1, d_seeds, 6, h ? 5 : 2);
+        ab->cm_cand = nullptr;
+        ab->cm_bins = nullptr;
+        ab->cm_roi = nullptr;
+        if (rc) return rc;
+    }
+    return MKF_OK;
 }
 
 extern "C" int mkf_batch_assoc_results(mkf_batch* b, uint8_t* gate, double* weights, int32_t* bins, int mem)

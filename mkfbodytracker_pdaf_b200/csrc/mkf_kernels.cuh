@@ -79,7 +79,16 @@ struct SlotArgs {
     const uint32_t* __restrict__ unsorted; // per track: parents are not sorted (random-index fallback ran)
     double bh[MKF_M];
     double r; // measurement noise variance (R = r * I)
+    // MKF_MEAS_CAND (internal, mkf_batch_associate): a slot's column is assembled on the fly from the person's face
+    // ROI and the candidate its bin selects -- [roi.x + w/2, roi.y + h/2, cand_x(bin), cand_y(bin), roi.x + w/2,
+    // roi.y + neck h] (src/pfPose.cpp:303-323) -- instead of being materialised as T x 6 x N doubles
+    const double* __restrict__ cand;   // T x 2 hands x 2 (x row, y row) x cand_C
+    const int32_t* __restrict__ bins;  // T x 2 hands x N
+    const double* __restrict__ roi;    // T x 4
+    double neck;
+    int cand_C, hand;
 };
+#define MKF_MEAS_CAND 2 // internal third value of meas_layout (the public ones: include/mkf_b200.h)
 
 // -----------------------------------------------------------------------------------------
 // cv::Cholesky failure branch (a pivot < DBL_EPSILON, src/pf2DRao.cpp:37,52), literal:
@@ -348,11 +357,28 @@ __device__ __forceinline__ int mkf_component_of(const int32_t* __restrict__ bt, 
 }
 
 // measurement column of local slot j of track t, minus BH
+// the column of a slot whose candidate bin is bsel (MKF_MEAS_CAND); same operations as k_assoc_meas
+__device__ __forceinline__ void mkf_load_meas_cand(const SlotArgs& a, long long t, int bsel, double (&zc)[MKF_M])
+{
+    const double rx = __ldg(a.roi + t * 4 + 0), ry = __ldg(a.roi + t * 4 + 1), rw = __ldg(a.roi + t * 4 + 2),
+                 rh = __ldg(a.roi + t * 4 + 3);
+    const double* __restrict__ px = a.cand + (t * 2 + a.hand) * 2 * (long long)a.cand_C;
+    const double cxv = __dadd_rn(rx, __ddiv_rn(rw, 2.0));
+    zc[0] = cxv - a.bh[0];
+    zc[1] = __dadd_rn(ry, __dmul_rn(0.5, rh)) - a.bh[1];
+    zc[2] = __ldg(px + bsel) - a.bh[2];
+    zc[3] = __ldg(px + a.cand_C + bsel) - a.bh[3];
+    zc[4] = cxv - a.bh[4];
+    zc[5] = __dadd_rn(ry, __dmul_rn(a.neck, rh)) - a.bh[5];
+}
+
 __device__ __forceinline__ void mkf_load_meas(const SlotArgs& a, long long t, int j, double (&zc)[MKF_M])
 {
     if (a.meas_layout == MKF_MEAS_SHARED) {
 #pragma unroll
         for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + t * MKF_M + r) - a.bh[r];
+    } else if (a.meas_layout == MKF_MEAS_CAND) {
+        mkf_load_meas_cand(a, t, __ldg(a.bins + (t * 2 + a.hand) * (long long)a.N + j), zc);
     } else {
 #pragma unroll
         for (int r = 0; r < MKF_M; r++) zc[r] = __ldg(a.meas + (t * MKF_M + r) * a.N + j) - a.bh[r];
@@ -678,7 +704,7 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
 {
     constexpr int CHUNK = MKF_SHARE_CHUNK, G = 4;
     __shared__ int sm_par[CHUNK], sm_t[CHUNK], sm_rank[CHUNK];
-    __shared__ unsigned char sm_k[CHUNK];
+    __shared__ int sm_k[CHUNK]; // component | candidate bin << 8 (the bin only with MKF_MEAS_CAND)
     __shared__ int warp_tot[8];
     __shared__ int list_base;
     mkf_pdl_launch_dependents();
@@ -708,6 +734,7 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
         // component of a slot = number of run boundaries e_0..e_{K-2} (non-decreasing) that are <= j, unless j lies in
         // the wrapped tail (mkf_component_of).  Counted once for my first slot of a track, then carried forward.
         const int K = a.K;
+        const bool with_bin = a.meas_layout == MKF_MEAS_CAND;
         const int32_t* bt = a.bounds;
         int k_lin = 0, nb = 0, wf = 0, wk = 0;
         bool fresh = true;
@@ -730,6 +757,8 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
                 }
                 tl[g] = t_run;
                 kk[g] = (j_run >= wf) ? wk : k_lin;
+                // slots of a track that drew the same candidate see the same measurement column
+                if (with_bin) kk[g] |= __ldg(a.bins + ((long long)t_run * 2 + a.hand) * a.N + j_run) << 8;
                 if (++j_run == a.N) {
                     j_run = 0;
                     t_run++;
@@ -742,7 +771,7 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
             }
             sm_par[so0 + g] = par[g];
             sm_t[so0 + g] = tl[g];
-            sm_k[so0 + g] = (unsigned char)kk[g];
+            sm_k[so0 + g] = kk[g];
         }
     }
     __syncthreads();
@@ -830,7 +859,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
     mkf_mbar_wait(&mbar, 0);
     while (h < n) {
         const long long sp = (unsigned)rec.x, so_rec = (unsigned)rec.y, t = rec.z;
-        const int k = rec.w;
+        const int k = rec.w & 0xff;
         const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
         double v[L::NE];
 #pragma unroll
@@ -840,7 +869,10 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
             if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
         }
         double zc[MKF_M];
-        mkf_load_meas(a, t, 0, zc); // shared layout: the track's column
+        if (a.meas_layout == MKF_MEAS_CAND)
+            mkf_load_meas_cand(a, t, rec.w >> 8, zc); // the column of the head's candidate bin
+        else
+            mkf_load_meas(a, t, 0, zc); // shared layout: the track's column
         h += step;
         if (h < n) rec = __ldg(a.hd16 + h); // next step's head record: in flight during the arithmetic
         double w;
