@@ -539,6 +539,10 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
             CK(cudaFuncSetAttribute(k_resample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         mkf_launch(k_resample_small, grid_for(nt, 128), 128, smem, stream, d_w, nt, L, N, d_u, u_stride, normalise, d_wsum,
                    d_out, d_status, 1, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src);
+    } else if (L <= 32 && !d_rep && !d_src && !d_w_slot_out) {
+        // few weights, many outputs (candidate resample): a warp per track
+        mkf_launch(k_resample_warp, grid_for(nt, 4), 128, 0, stream, d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
+                   d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted);
     } else {
         // one CTA per track; wider CTAs for long weight / index vectors so a track's tiles are few
         const int span = L > N ? L : N;

@@ -1341,6 +1341,87 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     }
 }
 
+// Few weights, many outputs (the C -> N candidate resample of the association step with C <= 32 candidates per hand,
+// src/pfPose.cpp:300-301): one WARP per track, lane k owns weight k.  Same closed form, same ambiguity band and
+// the same normaliser semantics as k_resample_block (whose CTA of 128 threads would idle on 17 weights: 61 us for
+// 8192 tracks against 9 us here); an ambiguous track is handed to the literal loop at once (lane 0, weights in shared
+// memory).  max weight == 0 / NaN -> cv::RNG indices, as everywhere.
+__global__ void __launch_bounds__(128) k_resample_warp(const double* __restrict__ w_all, long long T, int L, int N,
+                                                        const double* __restrict__ u, int u_stride, int normalise,
+                                                        double* __restrict__ wsum_out, int32_t* __restrict__ out_all,
+                                                        uint32_t* __restrict__ status, int status_stride,
+                                                        uint32_t bit_fb, uint32_t bit_deg,
+                                                        const uint64_t* __restrict__ seeds, int seed_stride,
+                                                        int seed_off, uint32_t* __restrict__ unsorted)
+{
+    __shared__ double xn_s[4][32];
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * 4 + wid;
+    if (t >= T) return;
+    int32_t* __restrict__ out = out_all + t * N;
+    const double x = (lane < L) ? w_all[t * L + lane] : 0.0;
+    double acc = x, mx = (x > 0.0) ? x : 0.0, sq = x * x; // NaN-ignoring max starting at 0 (src/pf2DRao.cpp:161-172)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const double wsum = normalise ? acc : 1.0;
+    if (lane == 0 && wsum_out) wsum_out[t] = acc;
+    if (lane == 0 && unsorted) unsorted[t] = 0u;
+    const double wmax_n = normalise ? __ddiv_rn(mx, wsum) : mx;
+    if (!(wmax_n > 0.0)) { // src/pf2DRao.cpp:184-192
+        if (lane == 0) {
+            atomicOr(status + t * status_stride, bit_deg);
+            mkf_cvrng rng(seeds ? seeds[t * seed_stride + seed_off] : 1ull);
+            (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
+            for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
+            if (unsorted) unsorted[t] = 1u;
+        }
+        return;
+    }
+    const double step = __ddiv_rn(1.0, (double)N);
+    const double beta0 = __dmul_rn(u[t * u_stride], step);
+    const double mass = normalise ? 1.0 : acc;
+    const double s2 = (normalise ? __ddiv_rn(sq, __dmul_rn(wsum, wsum)) : sq) * (1.0 + 1e-9);
+    const double tol_loop = fmin(mkf_resample_tol(N, L, wmax_n, step), mkf_resample_tol_s2(N, L, s2, mass));
+    // the inclusive scan below reaches any prefix sum through <= 5 roundings (<= 14 is what this term allows)
+    const double tol = tol_loop + 16.0 * 1.1102230246251565e-16 * (1.0 + mass);
+    const double xn = (lane < L) ? (normalise ? __ddiv_rn(x, wsum) : x) : 0.0;
+    double incl = xn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    bool amb = false;
+    int e = N;
+    if (lane < L) {
+        e = mkf_count_le_df(dd_add_d(dd_make(incl), -beta0), step, N, tol, amb);
+        if (lane == L - 1 && e < N) amb = true; // the literal loop would wrap past the last weight
+    }
+    int e_prev = __shfl_up_sync(0xffffffffu, e, 1);
+    if (lane == 0) e_prev = 0;
+    if (__any_sync(0xffffffffu, amb)) {
+        xn_s[wid][lane] = xn;
+        __syncwarp();
+        if (lane == 0) {
+            atomicOr(status + t * status_stride, bit_fb);
+            const double* xs = xn_s[wid];
+            mkf_resample_sequential([&](int i) { return xs[i]; }, L, N, u[t * u_stride],
+                                    [&](int i, int idx) { out[i] = idx; });
+        }
+        return;
+    }
+    for (int k = 0; k < L; k++) {
+        const int lo = __shfl_sync(0xffffffffu, e_prev, k), hi = __shfl_sync(0xffffffffu, e, k);
+        for (int i = lo + lane; i < hi; i += 32) out[i] = k;
+    }
+}
+
 // one thread per track, literal sequential semantics throughout (sequential wsum as the
 // reference, src/pf2DRao.cpp:139; then the loop of :195-207).  Used when N and L are small.
 // The CTA's 128 weight rows are staged transposed in shared memory (coalesced loads, one division per weight instead

@@ -68,10 +68,11 @@ def test_association_config3_small(left_arm, right_arm, N, Cn):
     assert not (d0["status"] | d1["status"]).any()
 
 
-def test_association_no_candidate_passes_gate(left_arm, right_arm):
+@pytest.mark.parametrize("N", [64, 200])  # 200: the warp-per-track candidate resampler (k_resample_warp)
+def test_association_no_candidate_passes_gate(left_arm, right_arm, N):
     """quirk B11: all weights NaN -> random candidates from cv::RNG (seeded)"""
     torch = pytest.importorskip("torch")
-    T, N, Cn = 3, 64, 9
+    T, Cn = 3, 9
     s = torch.cuda.Stream()
     b0 = mk.TrackBatch(left_arm.mk, T, N, stream=s.cuda_stream)
     b1 = mk.TrackBatch(right_arm.mk, T, N, stream=s.cuda_stream)
@@ -98,7 +99,7 @@ def test_association_no_candidate_passes_gate(left_arm, right_arm):
     assert not (st1[1] & L.ST_CAND_DEGENERATE)
 
 
-@pytest.mark.parametrize("N,Cn", [(500, 5000), (64, 640)])
+@pytest.mark.parametrize("N,Cn", [(500, 5000), (64, 640), (340, 17)])  # (340, 17): k_resample_warp, 340 = 20 x 17
 def test_association_tied_candidate_weights_inside_a_batch(left_arm, right_arm, N, Cn):
     """persons whose candidates are all identical (equal weights) with u = 0 put every threshold on a prefix sum: their
     C -> N candidate resample must leave the closed form (status CAND_FALLBACK) inside a batch of ordinary persons and
