@@ -256,7 +256,8 @@ int mkf_batch_profile_read_stages(mkf_batch* b, double* ms, int* n_updates);
 
 /* Record sharing.  When the slots of a track see one measurement (MKF_MEAS_SHARED, MKF_ALIAS_INDEPENDENT), children
  * that drew the same parent and the same component are bit-identical Gaussians; the device computes and stores such a
- * group once per warp and lets its slots refer to the one record.  Nothing observable changes (per-slot weights,
+ * group once and lets its slots refer to the one record.  The same holds inside mkf_batch_associate(do_update != 0)
+ * for slots that also drew the same candidate (few candidates per hand, src/pfPose.cpp:300-323).  Nothing observable changes (per-slot weights,
  * parents, states and estimates are those of N independent slots); this call reports how many distinct records the
  * last update stored for how many slots. */
 int mkf_batch_shared_records(mkf_batch* b, int64_t* records, int64_t* slots);
