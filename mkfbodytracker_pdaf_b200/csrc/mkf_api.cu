@@ -191,6 +191,10 @@ struct mkf_batch {
     DevBuf in_meas, in_u0, in_u1, in_seed, out_a, out_b, in_x, in_p;
     AsyncIo aio;
     // association scratch (arm0 owns)
+    // the pose of every track as the last estimate computed it, kept for the next association step (which needs the
+    // posterior hand position, src/pf2DRao.cpp:111-116); switched on by the first mkf_batch_associate
+    DevBuf pose_cache;
+    bool pose_cache_on = false, pose_valid = false;
     // MKF_MEAS_CAND source of the next update_device call (set and cleared by mkf_batch_associate)
     const double* cm_cand = nullptr;
     const int32_t* cm_bins = nullptr;
@@ -288,7 +292,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
         if (p) cudaFree(p);
     DevBuf* bufs[] = {&b->in_meas, &b->in_u0, &b->in_u1, &b->in_seed, &b->out_a,   &b->out_b,  &b->in_x,   &b->in_p,
                       &b->as_cand, &b->as_L,  &b->as_roi, &b->as_u,   &b->as_w,    &b->as_gate, &b->as_bins,
-                      &b->as_meas, &b->as_wsum, &b->as_hand, &b->as_status, &b->as_seed,
+                      &b->as_meas, &b->as_wsum, &b->as_hand, &b->as_status, &b->as_seed, &b->pose_cache,
                       &b->as_ui,   &b->as_up};
     for (DevBuf* d : bufs) d->release();
     b->aio.release();
@@ -501,6 +505,7 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     if ((rc = launch_bounds_kernel(b, d_u))) return rc;
     b->cur = 0;
     b->shared = false;
+    b->pose_valid = false;
     if (b->m->d == 12)
         k_reset<12><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
                                                                     b->total, b->N, b->m->K);
@@ -575,6 +580,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     const bool prof = b->prof_on && (b->prof_tick++ % (uint64_t)b->prof_every) == 0 &&
                       (size_t)(b->prof_n + 1) * MKF_PROF_EV <= b->prof_ev.size();
     cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * MKF_PROF_EV] : nullptr;
+    b->pose_valid = false;
     if (prof) cudaEventRecord(pe[0], b->stream);
     if ((rc = launch_bounds_kernel(b, d_uind))) return rc;
     if (prof) cudaEventRecord(pe[1], b->stream);
@@ -843,12 +849,13 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
 {
     const mkf_model* m = b->m;
     const double2* st = b->st[b->cur];
+    double* d_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
     const size_t coef_bytes = (size_t)(m->D + DD) * DD * sizeof(double);
     // tracks per CTA = TRIPS * 128 / GROUP: 8 trips amortise staging the reconstruction matrices once there are
     // enough tracks to fill the GPU several times over; small batches keep one trip so that they still spread out
 #define MKF_EST_SMALL(G, TR)                                                                                  \
     mkf_launch(k_estimate_small<DD, G, TR>, grid_for(b->T, TR * 128 / G), 128, coef_bytes, b->stream,                 \
-        st, b->gather_index(), b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose)
+        st, b->gather_index(), b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose, d_pose2)
     if (b->N <= 16) {
         if (b->T >= 8 * 8 * 4 * 148)
             MKF_EST_SMALL(16, 8);
@@ -863,10 +870,10 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
 #undef MKF_EST_SMALL
     else if (b->N <= 2048)
         mkf_launch(k_estimate<DD, 128>, (unsigned)b->T, 128, 0, b->stream, st, b->gather_index(), b->N, m->D, b->d_recon, b->d_pmean,
-                                                                   b->d_tinv, d_xbar, d_pose);
+                                                                   b->d_tinv, d_xbar, d_pose, d_pose2);
     else // long tracks: more loads in flight per track (BT = 512 is slower at N = 500: 64 vs 41 us at 4096 tracks)
         mkf_launch(k_estimate<DD, 512>, (unsigned)b->T, 512, 0, b->stream, st, b->gather_index(), b->N, m->D, b->d_recon, b->d_pmean,
-                                                                   b->d_tinv, d_xbar, d_pose);
+                                                                   b->d_tinv, d_xbar, d_pose, d_pose2);
 }
 static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
 {
@@ -876,6 +883,7 @@ static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
         launch_estimate_d<10>(b, d_xbar, d_pose);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    if (b->pose_cache_on) b->pose_valid = true;
     return MKF_OK;
 }
 
@@ -1000,6 +1008,7 @@ extern "C" int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, 
     if ((rc = in_ptr(b, P, (size_t)b->total * d * d, mem, b->in_p, &dP))) return rc;
     b->cur = 0;
     b->shared = false;
+    b->pose_valid = false;
     CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if (d == 12)
         k_upload<12><<<grid_for(b->total, 64), 64, 0, b->stream>>>(b->st[0], b->parent, dx, dP, b->d_tm, b->total, b->N);

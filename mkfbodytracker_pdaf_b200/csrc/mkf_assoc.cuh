@@ -135,6 +135,24 @@ __global__ void k_assoc_status(const uint32_t* __restrict__ as_status, long long
 
 static int estimate_pose_device(mkf_batch* b, double* d_pose) { return launch_estimate(b, nullptr, d_pose); }
 
+// the pose of every track of an arm batch (device, T x D): the copy the last estimate left, or a fresh one
+static int posterior_pose_device(mkf_batch* b, const double** d_pose)
+{
+    int rc;
+    if (!b->pose_cache_on) {
+        if ((rc = b->pose_cache.ensure((size_t)b->T * b->m->D * sizeof(double)))) return rc;
+        b->pose_cache_on = true;
+        b->pose_valid = false;
+    }
+    static const bool reuse = [] { // MKF_POSE_CACHE=0: always recompute (A/B runs)
+        const char* e = getenv("MKF_POSE_CACHE");
+        return !(e && e[0] == '0');
+    }();
+    if ((!b->pose_valid || !reuse) && (rc = launch_estimate(b, nullptr, nullptr))) return rc; // writes the copy
+    *d_pose = (const double*)b->pose_cache.p;
+    return MKF_OK;
+}
+
 extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const double* cand_xy, const uint8_t* cand_L,
                                    const double* roi, const double* u_cand, const double* u_ind, const double* u_post,
                                    const uint64_t* seeds, int do_update, int mem)
@@ -179,17 +197,15 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
         (rc = b->as_bins.ensure((size_t)T * 2 * N * sizeof(int32_t))) ||
         (rc = b->as_wsum.ensure((size_t)T * 2 * sizeof(double))) ||
         (rc = b->as_status.ensure((size_t)T * 2 * sizeof(uint32_t))) ||
-        (rc = b->as_hand.ensure((size_t)T * (a0->m->D + a1->m->D) * sizeof(double))) ||
         (!gather && (rc = b->as_meas.ensure((size_t)T * 2 * 6 * N * sizeof(double)))))
         return rc;
     b->as_C = C;
-    double* d_pose0 = (double*)b->as_hand.p;
-    double* d_pose1 = d_pose0 + (size_t)T * a0->m->D;
+    const double *d_pose0, *d_pose1;
     CK(cudaMemsetAsync(b->as_status.p, 0, (size_t)T * 2 * sizeof(uint32_t), b->stream));
     CK(cudaMemsetAsync(a0->status, 0, (size_t)T * sizeof(uint32_t), b->stream));
     CK(cudaMemsetAsync(a1->status, 0, (size_t)T * sizeof(uint32_t), b->stream));
     // posterior hand position of both arms: rows 0..1 of pca_proj^T xbar + pca_mean^T (src/pf2DRao.cpp:111-116)
-    if ((rc = estimate_pose_device(a0, d_pose0)) || (rc = estimate_pose_device(a1, d_pose1))) return rc;
+    if ((rc = posterior_pose_device(a0, &d_pose0)) || (rc = posterior_pose_device(a1, &d_pose1))) return rc;
     AssocArgs aa;
     aa.cand_xy = d_cand;
     aa.cand_L = d_L;

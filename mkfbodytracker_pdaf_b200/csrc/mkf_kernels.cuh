@@ -1489,7 +1489,8 @@ template <int D, int BT>
 __global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __restrict__ st, const int32_t* __restrict__ parent,
                                                   int N, int Dpose, const double* __restrict__ recon,
                                                   const double* __restrict__ pmean, const double* __restrict__ tinv,
-                                                  double* __restrict__ xbar_out, double* __restrict__ pose_out)
+                                                  double* __restrict__ xbar_out, double* __restrict__ pose_out,
+                                                  double* __restrict__ pose_out2)
 {
     using L = SlotLay<D>;
     __shared__ double red[BT / 32][D];
@@ -1572,10 +1573,11 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_estimate(const double2* __res
         xb[tid] = s * (1.0 / (double)N);
     }
     __syncthreads();
-    if (pose_out && tid < Dpose) {
+    if ((pose_out || pose_out2) && tid < Dpose) { // pose_out2: the batch's copy for the next association step
         double s = 0.0;
         for (int c = 0; c < D; c++) s = fma(recon[tid * D + c], xb[c], s);
-        pose_out[t * Dpose + tid] = s + pmean[tid];
+        if (pose_out) pose_out[t * Dpose + tid] = s + pmean[tid];
+        if (pose_out2) pose_out2[t * Dpose + tid] = s + pmean[tid];
     }
     if (xbar_out && tid < D) {
         double s = 0.0;
@@ -1592,7 +1594,8 @@ template <int D, int GROUP, int TRIPS>
 __global__ void __launch_bounds__(128) k_estimate_small(const double2* __restrict__ st, const int32_t* __restrict__ parent,
                                                          long long T, int N, int Dpose, const double* __restrict__ recon,
                                                          const double* __restrict__ pmean, const double* __restrict__ tinv,
-                                                         double* __restrict__ xbar_out, double* __restrict__ pose_out)
+                                                         double* __restrict__ xbar_out, double* __restrict__ pose_out,
+                                                         double* __restrict__ pose_out2)
 {
     using L = SlotLay<D>;
     constexpr int TPB = 128 / GROUP; // tracks per CTA and trip
@@ -1637,6 +1640,7 @@ __global__ void __launch_bounds__(128) k_estimate_small(const double2* __restric
             for (int c = 0; c < D; c++) sacc = fma(coef[c * R + r], acc[c], sacc);
             if (r < Dpose) {
                 if (pose_out) pose_out[t * Dpose + r] = sacc + pmean[r];
+                if (pose_out2) pose_out2[t * Dpose + r] = sacc + pmean[r];
             } else if (xbar_out) {
                 xbar_out[t * D + (r - Dpose)] = sacc;
             }

@@ -97,12 +97,22 @@ def assoc(name, left, right, T, N, C, steps, seed):
     def full(f):
         mk.associate(b0, b1, cand, L, roi, us[0], us[1], us[2], do_update=True)
 
+    pose0 = torch.empty((T, left.D), dtype=torch.float64, device=dev)
+    pose1 = torch.empty((T, right.D), dtype=torch.float64, device=dev)
+
+    def tracker_frame(f):  # what a tracker loop runs per frame: associate + update both arms, then the output estimate
+        mk.associate(b0, b1, cand, L, roi, us[0], us[1], us[2], do_update=True)
+        b0.estimate_into(None, pose0)
+        b1.estimate_into(None, pose1)
+
     ms_a = timed(only_assoc, steps)
     ms_f = timed(full, steps)
+    ms_t = timed(tracker_frame, steps)
     st = b0.status() | b1.status()
     print(json.dumps(dict(config=name, persons=T, slots=N, candidates_per_hand=C, assoc_only_ms=ms_a,
                           assoc_only_person_frames_per_s=T / ms_a * 1e3,
                           candidate_weights_per_s=T * 2 * C / ms_a * 1e3, assoc_plus_update_ms=ms_f,
+                          assoc_update_estimate_ms=ms_t,
                           frame_updates_per_s=2 * T / ms_f * 1e3, slot_updates_per_s=2 * T * N / ms_f * 1e3,
                           degenerate=int(((st & 0x24) != 0).sum()))), flush=True)
     b0.close()
