@@ -683,7 +683,10 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         if (a.alias_chain)                                                             \
             mkf_launch(k_slot_update<DD, true>, g, 128, smem, b->stream, a);    \
         else if (use_split) {                                                          \
-            mkf_launch(k_share_keys, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);                       \
+            if (meas_layout == MKF_MEAS_CAND)                                                                          \
+                mkf_launch(k_share_keys<true>, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);            \
+            else                                                                                                       \
+                mkf_launch(k_share_keys<false>, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);           \
             MKF_LAUNCHED();                                                            \
             if (prof) cudaEventRecord(pe[2], b->stream);                               \
             mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(heads_ctas_per_sm * sm_count(b->device)), 128, smem, b->stream, a,   \

@@ -18,6 +18,8 @@
 
 #include <float.h>
 
+#include <type_traits>
+
 #include "mkf_device.cuh"
 #include "../../include/mkf_synth.h"
 
@@ -700,11 +702,13 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
 // -----------------------------------------------------------------------------------------
 constexpr int MKF_SHARE_CHUNK = 1024;
 
+template <bool WITH_BIN> // WITH_BIN: MKF_MEAS_CAND, the candidate bin is part of the key
 __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
 {
+    using key_t = typename std::conditional<WITH_BIN, int, unsigned char>::type;
     constexpr int CHUNK = MKF_SHARE_CHUNK, G = 4;
     __shared__ int sm_par[CHUNK], sm_t[CHUNK], sm_rank[CHUNK];
-    __shared__ int sm_k[CHUNK]; // component | candidate bin << 8 (the bin only with MKF_MEAS_CAND)
+    __shared__ key_t sm_k[CHUNK]; // component (| candidate bin << 8 with MKF_MEAS_CAND)
     __shared__ int warp_tot[8];
     __shared__ int list_base;
     mkf_pdl_launch_dependents();
@@ -734,7 +738,6 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
         // component of a slot = number of run boundaries e_0..e_{K-2} (non-decreasing) that are <= j, unless j lies in
         // the wrapped tail (mkf_component_of).  Counted once for my first slot of a track, then carried forward.
         const int K = a.K;
-        const bool with_bin = a.meas_layout == MKF_MEAS_CAND;
         const int32_t* bt = a.bounds;
         int k_lin = 0, nb = 0, wf = 0, wk = 0;
         bool fresh = true;
@@ -758,7 +761,7 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
                 tl[g] = t_run;
                 kk[g] = (j_run >= wf) ? wk : k_lin;
                 // slots of a track that drew the same candidate see the same measurement column
-                if (with_bin) kk[g] |= __ldg(a.bins + ((long long)t_run * 2 + a.hand) * a.N + j_run) << 8;
+                if (WITH_BIN) kk[g] |= __ldg(a.bins + ((long long)t_run * 2 + a.hand) * a.N + j_run) << 8;
                 if (++j_run == a.N) {
                     j_run = 0;
                     t_run++;
@@ -771,7 +774,7 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
             }
             sm_par[so0 + g] = par[g];
             sm_t[so0 + g] = tl[g];
-            sm_k[so0 + g] = kk[g];
+            sm_k[so0 + g] = (key_t)kk[g];
         }
     }
     __syncthreads();

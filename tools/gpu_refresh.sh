@@ -18,6 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on \
 MKF_DEDUP=0 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:^k_slot_update\$" -s 3 -c 2 -f \
     -o gpurun_out/prof_k_slot_update_$R python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/b_ncu_k_slot_update.log 2>&1
 timeout 300 python tools/soak_parity.py 64 500 300 0 > gpurun_out/soak_$R.jsonl 2>&1
+timeout 600 python tools/bench_configs.py > gpurun_out/configs_$R.jsonl 2> gpurun_out/configs_$R.err; tail -c 300 gpurun_out/configs_$R.err
 python -c "
 import json; d=json.loads(open('gpurun_out/bench_$R.json').read())
 print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'],'launches',d['gpu_launches'])
