@@ -56,10 +56,17 @@ __device__ __forceinline__ double mkf_iso2_pdf(const Iso2& g, double x, double y
     return exp(__dadd_rn(__dmul_rn(q, -0.5), g.shift));
 }
 
+// one warp per (person, hand, stretch of MKF_ASSOC_SPAN candidates): with the reference's 5000 candidates per hand a
+// (person, hand) is 40 warps, not one lane-strided loop of 157 trips (256 persons: 512 warps on 148 SMs)
+constexpr int MKF_ASSOC_SPAN = 128;
 __global__ void __launch_bounds__(128) k_assoc_weights(const AssocArgs a)
 {
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    const int spans = (a.C + MKF_ASSOC_SPAN - 1) / MKF_ASSOC_SPAN;
+    const long long wid = gw / spans;
+    const int c_begin = (int)(gw - wid * spans) * MKF_ASSOC_SPAN;
+    const int c_end = min(a.C, c_begin + MKF_ASSOC_SPAN);
     if (wid >= a.T * 2) return;
     const long long t = wid >> 1;
     const int h = (int)(wid & 1);
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(128) k_assoc_weights(const AssocArgs a)
     const uint8_t* __restrict__ pl = a.cand_L + (t * 2 + h) * (long long)a.C;
     double* __restrict__ wo = a.w_raw + (t * 2 + h) * (long long)a.C;
     uint8_t* __restrict__ go = a.gate + (t * 2 + h) * (long long)a.C;
-    for (int c = lane; c < a.C; c += 32) {
+    for (int c = c_begin + lane; c < c_end; c += 32) {
         const double x = px[c], y = py[c];
         double w = 0.0;
         uint8_t gt = 0;
@@ -224,7 +231,7 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
     aa.pa = prm.assoc_pa;
     aa.clutter = prm.assoc_clutter;
     aa.spread = prm.proposal_spread;
-    k_assoc_weights<<<grid_for(T * 2 * 32, 128), 128, 0, b->stream>>>(aa);
+    k_assoc_weights<<<grid_for(T * 2 * 32 * ((C + MKF_ASSOC_SPAN - 1) / MKF_ASSOC_SPAN), 128), 128, 0, b->stream>>>(aa);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if ((rc = run_resample(b->stream, T * 2, (const double*)b->as_w.p, C, N, d_uc, 1, 1,
