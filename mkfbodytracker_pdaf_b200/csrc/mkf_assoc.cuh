@@ -140,8 +140,6 @@ __global__ void k_assoc_status(const uint32_t* __restrict__ as_status, long long
     if (st) atomicOr(((th & 1) ? status1 : status0) + (th >> 1), st);
 }
 
-static int estimate_pose_device(mkf_batch* b, double* d_pose) { return launch_estimate(b, nullptr, d_pose); }
-
 // the pose of every track of an arm batch (device, T x D): the copy the last estimate left, or a fresh one
 static int posterior_pose_device(mkf_batch* b, const double** d_pose)
 {

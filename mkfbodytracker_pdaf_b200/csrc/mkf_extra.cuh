@@ -123,13 +123,12 @@ extern "C" int mkf_batch_sample_prob(mkf_batch* b, int64_t track, const double* 
     }
     CK(cudaSetDevice(b->device));
     int rc;
-    if ((rc = b->as_hand.ensure((size_t)b->T * b->m->D * 8)) || (rc = b->as_cand.ensure((size_t)2 * C * 8)) ||
-        (rc = b->as_w.ensure((size_t)C * 8)))
-        return rc;
-    if ((rc = estimate_pose_device(b, (double*)b->as_hand.p))) return rc;
+    if ((rc = b->as_cand.ensure((size_t)2 * C * 8)) || (rc = b->as_w.ensure((size_t)C * 8))) return rc;
+    const double* d_pose; // the estimate the caller's loop has already computed, if the state has not changed since
+    if ((rc = posterior_pose_device(b, &d_pose))) return rc;
     CK(cudaMemcpyAsync(b->as_cand.p, cand_xy, (size_t)2 * C * 8, cudaMemcpyHostToDevice, b->stream));
     const mkf_params& prm = b->m->prm;
-    k_sample_prob<<<grid_for(C, 128), 128, 0, b->stream>>>((const double*)b->as_hand.p, b->m->D, track,
+    k_sample_prob<<<grid_for(C, 128), 128, 0, b->stream>>>(d_pose, b->m->D, track,
                                                             (const double*)b->as_cand.p, C,
                                                             prm.proposal_spread * scale * 1.0, prm.chol_mode,
                                                             (double*)b->as_w.p);
@@ -307,11 +306,11 @@ extern "C" int mkf_batch_pose3d(mkf_batch* b, const double* Kcam, double* pos3d,
     }
     CK(cudaSetDevice(b->device));
     int rc;
-    if ((rc = b->as_hand.ensure((size_t)b->T * b->m->D * 8))) return rc;
-    if ((rc = estimate_pose_device(b, (double*)b->as_hand.p))) return rc;
+    const double* d_pose;
+    if ((rc = posterior_pose_device(b, &d_pose))) return rc;
     OutPtr<double> o;
     if ((rc = o.init(b, pos3d, (size_t)b->T * 15, mem, b->out_a))) return rc;
-    k_pose3d<<<grid_for(b->T, 128), 128, 0, b->stream>>>((const double*)b->as_hand.p, b->m->D, b->T, make_cam(Kcam),
+    k_pose3d<<<grid_for(b->T, 128), 128, 0, b->stream>>>(d_pose, b->m->D, b->T, make_cam(Kcam),
                                                          o.devp);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
@@ -333,10 +332,8 @@ extern "C" int mkf_batch_skeleton(mkf_batch* a0, mkf_batch* a1, const double* Kc
     }
     CK(cudaSetDevice(a0->device));
     int rc;
-    if ((rc = a0->as_hand.ensure((size_t)a0->T * (a0->m->D + a1->m->D) * 8))) return rc;
-    double* p1 = (double*)a0->as_hand.p;
-    double* p2 = p1 + (size_t)a0->T * a0->m->D;
-    if ((rc = estimate_pose_device(a0, p1)) || (rc = estimate_pose_device(a1, p2))) return rc;
+    const double *p1, *p2;
+    if ((rc = posterior_pose_device(a0, &p1)) || (rc = posterior_pose_device(a1, &p2))) return rc;
     OutPtr<double> otf, oj;
     if ((rc = otf.init(a0, tf, (size_t)a0->T * 30, mem, a0->out_a))) return rc;
     if ((rc = oj.init(a0, joints2d, (size_t)a0->T * 16, mem, a0->out_b))) return rc;
@@ -401,10 +398,8 @@ extern "C" int mkf_batch_propose(mkf_batch* a0, mkf_batch* a1, int C, const doub
     if ((rc = in_ptr(b, tracking, (size_t)T, mem, b->as_u, &d_trk))) return rc;
     if ((rc = in_ptr(b, like, cand_L ? (size_t)n_img * prm.img_rows * prm.img_cols : 0, mem, b->as_L, &d_like)))
         return rc;
-    if ((rc = b->as_hand.ensure((size_t)T * (a0->m->D + a1->m->D) * 8))) return rc;
-    double* p0 = (double*)b->as_hand.p;
-    double* p1 = p0 + (size_t)T * a0->m->D;
-    if ((rc = estimate_pose_device(a0, p0)) || (rc = estimate_pose_device(a1, p1))) return rc;
+    const double *p0, *p1;
+    if ((rc = posterior_pose_device(a0, &p0)) || (rc = posterior_pose_device(a1, &p1))) return rc;
     OutPtr<double> oxy;
     OutPtr<uint8_t> oL;
     if ((rc = oxy.init(b, cand_xy, (size_t)T * 4 * C, mem, b->out_a))) return rc;
