@@ -195,6 +195,7 @@ struct mkf_batch {
     // posterior hand position, src/pf2DRao.cpp:111-116); switched on by the first mkf_batch_associate
     DevBuf pose_cache;
     bool pose_cache_on = false, pose_valid = false;
+    bool clear_status_next = false; // the next update_device's first kernel zeroes the status words
     // MKF_MEAS_CAND source of the next update_device call (set and cleared by mkf_batch_associate)
     const double* cm_cand = nullptr;
     const int32_t* cm_bins = nullptr;
@@ -473,13 +474,13 @@ extern "C" int mkf_batch_join(mkf_batch* b)
 
 static inline unsigned grid_for(long long n, int bt) { return (unsigned)((n + bt - 1) / bt); }
 
-static int launch_bounds_kernel(mkf_batch* b, const double* d_u)
+static int launch_bounds_kernel(mkf_batch* b, const double* d_u, int clear_status = 0)
 {
     const mkf_model* m = b->m;
 #define LAUNCH_BOUNDS(G)                                                                                       \
     mkf_launch(k_indicator_bounds<G>, grid_for(b->T * G, 128), 128, 0, b->stream, d_u, b->T, b->N, m->K, b->d_cw_hi,       \
                                                                            b->d_cw_lo, b->d_wprior, m->prior_wmax, \
-                                                                           b->bounds, b->status)
+                                                                           b->bounds, b->status, clear_status)
     if (m->K <= 16)
         LAUNCH_BOUNDS(16);
     else
@@ -582,7 +583,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * MKF_PROF_EV] : nullptr;
     b->pose_valid = false;
     if (prof) cudaEventRecord(pe[0], b->stream);
-    if ((rc = launch_bounds_kernel(b, d_uind))) return rc;
+    if ((rc = launch_bounds_kernel(b, d_uind, b->clear_status_next ? 1 : 0))) return rc;
+    b->clear_status_next = false;
     if (prof) cudaEventRecord(pe[1], b->stream);
     SlotArgs a{};
     a.st_in = b->st[b->cur];
@@ -832,7 +834,7 @@ extern "C" int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layou
             return rc;
         CK(cudaEventRecord(io.in_done[sl], io.s_in));
         CK(cudaStreamWaitEvent(b->stream, io.in_done[sl], 0));
-        CK(cudaMemsetAsync(b->status, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
+        b->clear_status_next = true; // k_indicator_bounds zeroes the status words (no memset node in the chain)
         rc = update_device(b, d_meas, meas_layout, d_ui, d_up, 1, d_seeds, 2, 1);
         CK(cudaEventRecord(io.in_free[sl], b->stream));
         io.in_used[sl] = true;
@@ -842,7 +844,7 @@ extern "C" int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layou
     if ((rc = in_ptr(b, u_ind, (size_t)b->T, mem, b->in_u0, &d_ui))) return rc;
     if ((rc = in_ptr(b, u_post, (size_t)b->T, mem, b->in_u1, &d_up))) return rc;
     if ((rc = in_ptr(b, seeds, (size_t)b->T * 2, mem, b->in_seed, &d_seeds))) return rc;
-    CK(cudaMemsetAsync(b->status, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
+    b->clear_status_next = true;
     return update_device(b, d_meas, meas_layout, d_ui, d_up, 1, d_seeds, 2, 1);
 }
 

@@ -969,7 +969,7 @@ template <int GROUP>
 __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, int N, int K,
                                    const double* __restrict__ cw_hi, const double* __restrict__ cw_lo,
                                    const double* __restrict__ wprior, double wmax, int32_t* __restrict__ bounds,
-                                   uint32_t* __restrict__ status)
+                                   uint32_t* __restrict__ status, int clear_status)
 {
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
@@ -977,6 +977,9 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
     const long long t = gid / GROUP;
     const int k = (int)(gid % GROUP);
     const bool live = t < T;
+    // first kernel of a frame update: the track's status word starts from zero (no memset node in front of the
+    // chain); the only writer of status in this kernel is this same thread, below
+    if (clear_status && live && k == 0) status[t] = 0u;
     const double step = __ddiv_rn(1.0, (double)N);
     const double beta0 = live ? __dmul_rn(u[t], step) : 0.0;
     const double tol = mkf_resample_tol(N, K, wmax, step);
