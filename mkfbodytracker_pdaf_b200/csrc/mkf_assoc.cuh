@@ -21,6 +21,11 @@ struct AssocArgs {
     long long T;
     int C, D0, D1, chol_mode, img_rows, img_cols;
     double pa, clutter, spread;
+    // zeroed by k_assoc_weights (first kernel of the step; no memset nodes): per (person, hand) candidate-resample
+    // flags, and the two arm batches' track status words
+    uint32_t* __restrict__ as_status;
+    uint32_t* __restrict__ status0;
+    uint32_t* __restrict__ status1;
 };
 
 // 2-D isotropic proposal density exactly as mvnpdf_multiple evaluates it for cov = s2 * I:
@@ -70,6 +75,10 @@ __global__ void __launch_bounds__(128) k_assoc_weights(const AssocArgs a)
     if (wid >= a.T * 2) return;
     const long long t = wid >> 1;
     const int h = (int)(wid & 1);
+    if (c_begin == 0 && lane == 0) {
+        a.as_status[wid] = 0u;
+        (h ? a.status1 : a.status0)[t] = 0u;
+    }
     const double scale = a.roi[t * 4 + 2]; // (double)msg->ROIs[0].width
     const Iso2 g = mkf_iso2_setup(__dmul_rn(__dmul_rn(a.spread, scale), 1.0), a.chol_mode);
     const double h0x = a.pose0[t * a.D0 + 0], h0y = a.pose0[t * a.D0 + 1];
@@ -206,9 +215,6 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
         return rc;
     b->as_C = C;
     const double *d_pose0, *d_pose1;
-    CK(cudaMemsetAsync(b->as_status.p, 0, (size_t)T * 2 * sizeof(uint32_t), b->stream));
-    CK(cudaMemsetAsync(a0->status, 0, (size_t)T * sizeof(uint32_t), b->stream));
-    CK(cudaMemsetAsync(a1->status, 0, (size_t)T * sizeof(uint32_t), b->stream));
     // posterior hand position of both arms: rows 0..1 of pca_proj^T xbar + pca_mean^T (src/pf2DRao.cpp:111-116)
     if ((rc = posterior_pose_device(a0, &d_pose0)) || (rc = posterior_pose_device(a1, &d_pose1))) return rc;
     AssocArgs aa;
@@ -229,6 +235,9 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
     aa.pa = prm.assoc_pa;
     aa.clutter = prm.assoc_clutter;
     aa.spread = prm.proposal_spread;
+    aa.as_status = (uint32_t*)b->as_status.p;
+    aa.status0 = a0->status;
+    aa.status1 = a1->status;
     k_assoc_weights<<<grid_for(T * 2 * 32 * ((C + MKF_ASSOC_SPAN - 1) / MKF_ASSOC_SPAN), 128), 128, 0, b->stream>>>(aa);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
