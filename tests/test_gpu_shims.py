@@ -148,3 +148,15 @@ def test_legacy_shim_driver_against_oracle(N, d):
     pred = get("PRED")[0]
     dlt = pred - after[-1]
     assert np.all(dlt[:, 8:] == 0) and 3.5 < dlt[:, :8].std() < 6.5
+
+
+def test_shim_drivers_fail_loudly_without_a_gpu():
+    """no CPU fallback behind the C++ shims either: without a device the drivers exit non-zero naming the reason"""
+    if mk.device_count() > 0:
+        pytest.skip("a GPU is present")
+    for exe, args in (("shim_pf2d_driver", ["50", "8", "1", "3"]),):
+        path = os.path.join(ROOT, "tests", exe)
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "tests"), exe], check=True)
+        out = subprocess.run([path] + args, capture_output=True, text=True, timeout=60)
+        assert out.returncode != 0 and "no CPU fallback" in out.stderr, out.stderr
