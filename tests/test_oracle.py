@@ -355,6 +355,16 @@ def test_pf2d_matches_numpy(rng):
     assert np.array_equal(r["parents"], par)
     p2, _ = pf.get()
     assert np.array_equal(p2, parts[par])
+    # getEstimator (src/pf2D.cpp:79-88): the normalised weights update() left (resample() does not reset them, :225-268)
+    # against the resampled particles, summed in index order
+    est = pf.estimate()
+    want = np.zeros(d)
+    for i in range(N):
+        want = want + r["w_norm"][i] * p2[i]
+    assert np.array_equal(est, want)
+    fresh = orc.Pf2d(N, means, covs, wts)
+    fresh.set_particles(parts)
+    assert np.allclose(fresh.estimate(), parts.mean(0), rtol=1e-13)  # constructor weights 1/N (:52-55)
 
 
 # ---------------- synthetic generator ----------------
