@@ -223,10 +223,22 @@ int mkf_pf2d_create(mkf_pf2d** out, int64_t T, int N, int d, int K, const double
                     const double* weights, int device, void* stream);
 void mkf_pf2d_destroy(mkf_pf2d* p);
 int mkf_pf2d_set_particles(mkf_pf2d* p, const double* particles /* T x N x d */, int mem);
+/* The particle randomisation of the constructor ParticleFilter(numParticles, numDims, side1) (src/pf2D.cpp:44-71) and of
+ * resample()'s degenerate branch (max weight 0: every particle re-drawn across the image, weights back to 1/N,
+ * src/pf2D.cpp:232-250).  The reference draws with cv::randu from the global cv::theRNG(), which the class interface
+ * cannot seed; here the draws come from the counter generator of mkf_synth.h keyed (seed, track0 + t, epoch, particle,
+ * dim), epoch 0 = constructor, epoch n = the n-th mkf_pf2d_update.  Column `dim` is uniform on [1, im_width) (even dim)
+ * or [1, im_height) (odd dim); column 6 on [im_width/2*side + 1, im_width/2 + im_width/2*side).
+ * mkf_pf2d_set_random fixes the parameters (side: T flags, host or device, NULL = all 0; defaults without the call:
+ * seed 0, track0 0, side 0, 640 x 480); mkf_pf2d_randomise performs the constructor's draw (and the 1/N weights). */
+int mkf_pf2d_set_random(mkf_pf2d* p, uint64_t seed, int64_t track0, const uint8_t* side, int im_width, int im_height);
+int mkf_pf2d_randomise(mkf_pf2d* p);
 int mkf_pf2d_get(mkf_pf2d* p, double* particles, double* w_norm, int32_t* parents, int mem);
 /* ParticleFilter::update of src/pf2D.cpp:148-210: weights (GMM prior with float expf x two
  * isotropic 2-D likelihoods), normalise, systematic resample, random-walk predict.
- * meas T x 2 x 2, u T, noise T x N x d standard normals (NULL: no predict noise). */
+ * meas T x 2 x 2, u T, noise T x N x d standard normals (NULL: no predict noise).  expf is glibc's algorithm, restated
+ * in include/mkf_expf.h and shared with the oracle, so weights and resampled indices agree with the CPU path bit for bit.
+ * A filter whose weights are all 0 takes the degenerate branch (status bit MKF_ST_POST_DEGENERATE; parents[i] = i). */
 int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u, const double* noise, int mem);
 /* ParticleFilter::getEstimator of src/pf2D.cpp:79-88: est (T x d) = sum_i weights[i] * particles.row(i), the weights
  * being the normalised ones the last update computed (resample() does not reset them, src/pf2D.cpp:225-268) and the

@@ -13,6 +13,8 @@
 // discarded, then `rand()/RAND_MAX`, src/pf2D.cpp:228,255), so srand() reproduces the reference's uniform.  cv::randu
 // (constructor) and cv::randn (predict) draw from OpenCV's global generator, which cannot be reproduced without
 // OpenCV: the shim draws from its own counter generator (seedable: mkf_legacy::the_stream()), same distributions.
+// The re-randomisation inside resample() when every weight is 0 (src/pf2D.cpp:232-250) happens on the device, from
+// the counter generator of mkf_synth.h (mkf_pf2d_set_random).
 #ifndef MKF_SHIMS_PF2D_HPP
 #define MKF_SHIMS_PF2D_HPP
 
@@ -176,6 +178,7 @@ class ParticleFilter {
     }
     double last_u = 0;
     std::vector<double> last_noise;
+    uint64_t random_seed = 0; // seed of the degenerate branch's draws (mkf_pf2d_set_random)
 
   protected:
     void randomise()
@@ -204,6 +207,11 @@ class ParticleFilter {
             covs.insert(covs.end(), gmm.sigma_raw()[k].begin(), gmm.sigma_raw()[k].end());
         }
         mkf::check(mkf_pf2d_create(&h_, 1, N, d, gmm.N, means.data(), covs.data(), gmm.weight.data(), 0, nullptr));
+        // arm resample()'s degenerate branch (max weight 0: particles re-drawn across the image, src/pf2D.cpp:232-250)
+        // with this filter's side / image size and a seed taken from the shim's stream
+        const uint8_t sd = side ? 1 : 0;
+        random_seed = next_u64();
+        mkf::check(mkf_pf2d_set_random(h_, random_seed, 0, &sd, im_width, im_height));
         dirty_ = true;
     }
     void push()

@@ -199,6 +199,29 @@ MKF_HD void mkf_synth_proposal(uint64_t seed, uint64_t track, uint64_t frame, in
     }
 }
 
+/* Legacy pf2D particle randomisation (constructor, src/pf2D.cpp:58-70, and the degenerate branch of resample(),
+ * src/pf2D.cpp:232-250): column `dim` of the N x d particle matrix is cv::randu on [1, im_width) for even dim,
+ * [1, im_height) for odd dim, and [im_width/2*side + 1, im_width/2 + im_width/2*side) for dim 6.  cv::randu draws
+ * from the global cv::theRNG(), which is not reproducible through the class interface, so the draw comes from the
+ * counter generator keyed (seed, track, epoch, particle, dim): epoch 0 = constructor, epoch n = the n-th update.
+ * Value = lo + u * (hi - lo), the affine map cv::randu applies to its unit draw. */
+#define MKF_SYNTH_LANE_PF2D 0x60000000u /* + particle*16 + dim */
+MKF_HD double mkf_synth_pf2d_uniform(uint64_t seed, uint64_t track, uint64_t epoch, int particle, int dim, int side,
+                                     int im_width, int im_height)
+{
+    double lo = 1.0, hi;
+    const double half = MKF_SMUL((double)im_width, 0.5); /* im_width/2.0 */
+    if (dim == 6) {
+        lo = MKF_SADD(MKF_SMUL(half, (double)(side ? 1 : 0)), 1.0);
+        hi = MKF_SADD(half, MKF_SMUL(half, (double)(side ? 1 : 0)));
+    } else {
+        hi = (dim % 2 == 0) ? (double)im_width : (double)im_height;
+    }
+    const double u = mkf_u01(mkf_hash4(seed, track, epoch,
+                                       (uint64_t)MKF_SYNTH_LANE_PF2D + 16ull * (uint64_t)particle + (uint64_t)dim));
+    return MKF_SADD(lo, MKF_SMUL(u, MKF_SSUB(hi, lo)));
+}
+
 /* likelihood.at<uchar>(y, x) with the implicit double -> int truncation of src/pfPose.cpp:254, guarded by the
  * inside-image test of :251 (outside candidates never reach the lookup; they get L = 0 here) */
 MKF_HD uint8_t mkf_likelihood_lookup(const uint8_t* img, int rows, int cols, double x, double y)

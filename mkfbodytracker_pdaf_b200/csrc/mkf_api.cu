@@ -14,6 +14,7 @@
 
 #include "mkf_internal.h"
 #include "mkf_kernels.cuh"
+#include "../../include/mkf_expf.h"
 
 // events per profiled update: start | bounds | share keys | slot kernel | repair | resample
 #define MKF_PROF_EV 6

@@ -8,6 +8,13 @@
 #ifndef MKF_PF2D_CUH
 #define MKF_PF2D_CUH
 
+struct PfRand {
+    uint64_t seed = 0, epoch = 0;
+    long long track0 = 0;
+    const uint8_t* side = nullptr; // T flags on the device (nullptr: all 0)
+    int im_w = 640, im_h = 480;
+};
+
 struct mkf_pf2d {
     long long T = 0;
     int N = 0, d = 0, K = 0, device = 0;
@@ -21,6 +28,11 @@ struct mkf_pf2d {
     double* gmm = nullptr; // K x (d + d*d + 2): mean, sigma_i, det_s, weight
     int gstride = 0;
     DevBuf in_meas, in_u, in_noise, in_part;
+    // particle randomisation of the constructor and of resample()'s degenerate branch (src/pf2D.cpp:58-70,232-250),
+    // drawn from the counter generator keyed (seed, track0 + t, epoch, particle, dim); epoch 0 = constructor,
+    // epoch n = the n-th update
+    PfRand rnd;
+    uint8_t* d_side = nullptr;
 };
 
 template <int D>
@@ -63,9 +75,9 @@ __global__ void __launch_bounds__(128) k_pf2d_weight(const double* __restrict__ 
                 s4[0] = __dadd_rn(s4[0], __dmul_rn(tc, xu[c]));
         }
         const double q = __dadd_rn(__dadd_rn(__dadd_rn(s4[0], s4[1]), s4[2]), s4[3]);
-        // quirk B12: expf(float(q)).  Evaluated as the correctly rounded float of the double exp, which is
-        // what glibc's expf returns except for ~0.4% of arguments where it is off by one float ulp.
-        const double e = (double)(float)exp((double)(float)q);
+        // quirk B12: expf(float(q)) -- glibc's expf, restated operation by operation in include/mkf_expf.h (shared
+        // with the oracle; 0 mismatches against the host libm over all 2^32 arguments)
+        const double e = (double)mkf_expf((float)q);
         prior = __dadd_rn(prior, __dmul_rn(__dmul_rn(mu[D + D * D + 1], mu[D + D * D]), e));
     }
     // eyemvnpdf(x_u, 15): alpha = -0.5*1.0/15; 1/pow(2 pi 15, 1) * exp(alpha*(dx^2 + dy^2))
@@ -88,17 +100,22 @@ __global__ void __launch_bounds__(128) k_pf2d_weight(const double* __restrict__ 
 
 __global__ void k_pf2d_resample_predict(const double* __restrict__ old_p, double* __restrict__ new_p,
                                         const int32_t* __restrict__ parent, const uint32_t* __restrict__ status,
-                                        const double* __restrict__ noise, long long T, int N, int d)
+                                        const double* __restrict__ noise, long long T, int N, int d, const PfRand rnd)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T * N * d) return;
     const long long s = i / d;
     const int c = (int)(i - s * d);
     const long long t = s / N;
-    // degenerate weights: the reference re-randomises the particles with cv::randu (global RNG);
-    // not reproducible -> particles are kept and the status bit reports it
-    const long long sp = (status[t] & MKF_ST_POST_DEGENERATE) ? s : t * N + parent[s];
-    double v = __dadd_rn(0.0, old_p[sp * d + c]); // particles.row(i) = zeros + old_particles.row(idx)
+    double v;
+    if (status[t] & MKF_ST_POST_DEGENERATE) {
+        // max weight 0: every particle is re-randomised across the image (src/pf2D.cpp:232-244)
+        v = mkf_synth_pf2d_uniform(rnd.seed, (uint64_t)(rnd.track0 + t), rnd.epoch, (int)(s - t * N), c,
+                                   rnd.side ? (int)rnd.side[t] : 0, rnd.im_w, rnd.im_h);
+    } else {
+        const long long sp = t * N + parent[s];
+        v = __dadd_rn(0.0, old_p[sp * d + c]); // particles.row(i) = zeros + old_particles.row(idx)
+    }
     if (noise && c < 8) v = __dadd_rn(v, __dmul_rn(noise[i], 5.0));
     new_p[i] = v;
 }
@@ -110,17 +127,29 @@ __global__ void __launch_bounds__(256) k_pf2d_resample_predict_v(const double* _
                                                                   double* __restrict__ new_p,
                                                                   const int32_t* __restrict__ parent,
                                                                   const uint32_t* __restrict__ status,
-                                                                  const double* __restrict__ noise, long long T, int N)
+                                                                  const double* __restrict__ noise, long long T, int N,
+                                                                  const PfRand rnd)
 {
     static_assert(D % 2 == 0, "vector path needs an even dimension");
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= T * N) return;
     const long long t = s / N;
-    const long long sp = (__ldg(status + t) & MKF_ST_POST_DEGENERATE) ? s : t * N + __ldg(parent + s);
-    const double2* __restrict__ src = reinterpret_cast<const double2*>(old_p + sp * D);
     double2 v[D / 2], nz[D / 2];
+    if (__ldg(status + t) & MKF_ST_POST_DEGENERATE) {
+        // max weight 0: every particle is re-randomised across the image (src/pf2D.cpp:232-244)
+        const int side = rnd.side ? (int)rnd.side[t] : 0, j = (int)(s - t * N);
 #pragma unroll
-    for (int p = 0; p < D / 2; p++) v[p] = __ldg(src + p);
+        for (int p = 0; p < D / 2; p++) {
+            // "- 0.0": the common tail below adds 0.0 to what it takes for a gathered row (x + 0.0 == x here)
+            v[p].x = mkf_synth_pf2d_uniform(rnd.seed, (uint64_t)(rnd.track0 + t), rnd.epoch, j, 2 * p, side, rnd.im_w, rnd.im_h);
+            v[p].y = mkf_synth_pf2d_uniform(rnd.seed, (uint64_t)(rnd.track0 + t), rnd.epoch, j, 2 * p + 1, side, rnd.im_w, rnd.im_h);
+        }
+    } else {
+        const long long sp = t * N + __ldg(parent + s);
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(old_p + sp * D);
+#pragma unroll
+        for (int p = 0; p < D / 2; p++) v[p] = __ldg(src + p);
+    }
     if (noise) {
         const double2* __restrict__ ns = reinterpret_cast<const double2*>(noise + s * D);
 #pragma unroll
@@ -140,12 +169,24 @@ __global__ void __launch_bounds__(256) k_pf2d_resample_predict_v(const double* _
     }
 }
 
+// the constructor's randomisation (src/pf2D.cpp:58-70): one thread per matrix element
+__global__ void k_pf2d_randomise(double* __restrict__ part, long long T, int N, int d, const PfRand rnd)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * N * d) return;
+    const long long s = i / d;
+    const int c = (int)(i - s * d);
+    const long long t = s / N;
+    part[i] = mkf_synth_pf2d_uniform(rnd.seed, (uint64_t)(rnd.track0 + t), rnd.epoch, (int)(s - t * N), c,
+                                     rnd.side ? (int)rnd.side[t] : 0, rnd.im_w, rnd.im_h);
+}
+
 extern "C" void mkf_pf2d_destroy(mkf_pf2d* p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->part[0], p->part[1], p->w_raw, p->wsum, p->parent, p->status, p->gmm};
+    void* ptrs[] = {p->part[0], p->part[1], p->w_raw, p->wsum, p->parent, p->status, p->gmm, p->d_side};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     p->in_meas.release();
@@ -333,6 +374,46 @@ extern "C" int mkf_pf2d_set_particles(mkf_pf2d* p, const double* particles, int 
     return MKF_OK;
 }
 
+extern "C" int mkf_pf2d_set_random(mkf_pf2d* p, uint64_t seed, int64_t track0, const uint8_t* side, int im_width,
+                                   int im_height)
+{
+    if (!p || im_width < 2 || im_height < 2) {
+        mkf_set_error("mkf_pf2d_set_random: invalid argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    p->rnd.seed = seed;
+    p->rnd.track0 = track0;
+    p->rnd.im_w = im_width;
+    p->rnd.im_h = im_height;
+    p->rnd.side = nullptr;
+    if (side) {
+        if (!p->d_side) CK(cudaMalloc((void**)&p->d_side, (size_t)p->T));
+        CK(cudaMemcpyAsync(p->d_side, side, (size_t)p->T, cudaMemcpyDefault, p->stream));
+        CK(cudaStreamSynchronize(p->stream)); // `side` may be pageable host memory
+        p->rnd.side = p->d_side;
+    }
+    return MKF_OK;
+}
+
+extern "C" int mkf_pf2d_randomise(mkf_pf2d* p)
+{
+    if (!p) {
+        mkf_set_error("null pf2d");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    p->rnd.epoch = 0;
+    const long long n = p->T * p->N * p->d;
+    k_pf2d_randomise<<<grid_for(n, 256), 256, 0, p->stream>>>(p->part[p->cur], p->T, p->N, p->d, p->rnd);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    // uniform weights (src/pf2D.cpp:53-56): wsum = 0 makes k_pf2d_estimate take 1/N
+    CK(cudaMemsetAsync(p->wsum, 0, (size_t)p->T * 8, p->stream));
+    CK(cudaMemsetAsync(p->status, 0, (size_t)p->T * 4, p->stream));
+    return MKF_OK;
+}
+
 extern "C" int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u, const double* noise, int mem)
 {
     if (!p || !meas || !u) {
@@ -371,16 +452,19 @@ extern "C" int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u,
     if ((rc = run_resample(p->stream, p->T, p->w_raw, p->N, p->N, d_u, 1, 1, p->wsum, p->parent, p->status,
                            nullptr, 1, 0, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE)))
         return rc;
+    p->rnd.epoch++; // epoch n = the n-th update (the degenerate branch's draws are keyed on it)
     if (p->d == 8)
         k_pf2d_resample_predict_v<8><<<grid_for(tot, 256), 256, 0, p->stream>>>(p->part[p->cur], p->part[p->cur ^ 1],
-                                                                                p->parent, p->status, d_noise, p->T, p->N);
+                                                                                p->parent, p->status, d_noise, p->T, p->N,
+                                                                                p->rnd);
     else if (p->d == 12)
         k_pf2d_resample_predict_v<12><<<grid_for(tot, 256), 256, 0, p->stream>>>(p->part[p->cur], p->part[p->cur ^ 1],
-                                                                                 p->parent, p->status, d_noise, p->T, p->N);
+                                                                                 p->parent, p->status, d_noise, p->T, p->N,
+                                                                                 p->rnd);
     else
         k_pf2d_resample_predict<<<grid_for(tot * p->d, 256), 256, 0, p->stream>>>(p->part[p->cur], p->part[p->cur ^ 1],
                                                                                   p->parent, p->status, d_noise, p->T,
-                                                                                  p->N, p->d);
+                                                                                  p->N, p->d, p->rnd);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     p->cur ^= 1;

@@ -292,6 +292,20 @@ class Pf2dBatch:
     def set_particles(self, p):
         L.check(L.lib.mkf_pf2d_set_particles(self._h, _addr(p)[0], _addr(p)[1]))
 
+    def set_random(self, seed, track0=0, side=None, im_w=640, im_h=480):
+        """parameters of the constructor / degenerate-branch randomisation (src/pf2D.cpp:44-71,232-250);
+        side: T flags (uint8) or None"""
+        sp = None
+        if side is not None:
+            side = _h(side, np.uint8)
+            assert side.size == self.T
+            sp = side.ctypes.data
+        L.check(L.lib.mkf_pf2d_set_random(self._h, int(seed), int(track0), sp, int(im_w), int(im_h)))
+
+    def randomise(self):
+        """the constructor's draw (src/pf2D.cpp:44-71): particles across the image, weights 1/N"""
+        L.check(L.lib.mkf_pf2d_randomise(self._h))
+
     def update(self, meas, u, noise=None):
         mem = _same_mem(meas, u, noise)
         L.check(L.lib.mkf_pf2d_update(self._h, _addr(meas)[0], _addr(u)[0], _addr(noise)[0], mem))

@@ -31,6 +31,7 @@
 #endif
 
 #include "../include/mkf_synth.h"
+#include "../include/mkf_expf.h"
 
 namespace {
 
@@ -820,7 +821,32 @@ struct orc_pf2d {
     int N, d, K;
     std::vector<double> mean, sigma_i, det_s, weight; // gmm
     std::vector<double> particles, weights;           // N x d, N
+    // randomisation of the constructor / degenerate branch (src/pf2D.cpp:58-70,232-250) from the counter generator
+    uint64_t seed = 0, track = 0, epoch = 0;
+    int side = 0, im_w = 640, im_h = 480;
 };
+static void pf2d_randomise(orc_pf2d* p)
+{
+    for (int c = 0; c < p->d; c++)      // `for i < d: cv::randu(particles.col(i), lo, hi)`
+        for (int i = 0; i < p->N; i++)
+            p->particles[(size_t)i * p->d + c] =
+                mkf_synth_pf2d_uniform(p->seed, p->track, p->epoch, i, c, p->side, p->im_w, p->im_h);
+}
+extern "C" void orc_pf2d_set_random(orc_pf2d* p, uint64_t seed, uint64_t track, int side, int im_w, int im_h)
+{
+    p->seed = seed;
+    p->track = track;
+    p->side = side;
+    p->im_w = im_w;
+    p->im_h = im_h;
+}
+// ParticleFilter(numParticles, numDims, side1) (src/pf2D.cpp:44-71): uniform weights, particles across the image
+extern "C" void orc_pf2d_randomise(orc_pf2d* p)
+{
+    p->epoch = 0;
+    p->weights.assign(p->N, 1.0 / (double)p->N);
+    pf2d_randomise(p);
+}
 
 // cv::invert(DECOMP_CHOLESKY) and cv::determinant restated with plain LU / Cholesky solves:
 // sigma_i = inv(s), det_s = 1/(pow(2 pi, d/2) * sqrt(det(s)))   (src/pf2D.cpp:28-37)
@@ -921,7 +947,7 @@ extern "C" int orc_pf2d_update(orc_pf2d* p, const double* meas, double u, const 
             }
             double q;
             gemm_nt(t.data(), 1, d, xu.data(), 1, 1.0, nullptr, 0.0, &q); // (..)*x_u.t()
-            double e = (double)expf((float)q);
+            double e = (double)mkf_expf((float)q); // glibc's expf, restated in include/mkf_expf.h (shared with the device)
             prior = prior + p->weight[j] * p->det_s[j] * e;
         }
         // likelihood = eyemvnpdf(p[6:8] - meas.row(0), 15) * eyemvnpdf(p[0:2] - meas.row(1), 15)
@@ -937,10 +963,12 @@ extern "C" int orc_pf2d_update(orc_pf2d* p, const double* meas, double u, const 
         if (p->weights[i] > mw) mw = p->weights[i];
     int status = 0;
     std::vector<double> old(p->particles);
+    p->epoch++; // epoch n = the n-th update
     if (mw == 0) {
-        // the reference re-randomises the particles over the image with cv::randu; no parity is
-        // defined for that branch (uses the global cv::theRNG()).  Reported, particles kept.
+        // src/pf2D.cpp:232-250: every particle re-randomised over the image (cv::randu there, the counter generator
+        // here: cv::theRNG() cannot be seeded through the class), weights back to 1/N
         status = 1;
+        pf2d_randomise(p);
         for (int i = 0; i < N; i++) {
             p->weights[i] = 1.0 / (double)N;
             if (parents) parents[i] = i;
@@ -1036,6 +1064,25 @@ extern "C" void orc_propose(const orc_filter* armL, const orc_filter* armR, int 
             if (cand_L) cand_L[(size_t)h * C + c] = mkf_likelihood_lookup(like, rows, cols, x, y);
         }
     }
+}
+
+extern "C" float orc_expf(float x) { return mkf_expf(x); }
+extern "C" float orc_libm_expf(float x) { return expf(x); }
+extern "C" uint64_t orc_expf_compare(const uint32_t* bits, uint64_t n)
+{
+    uint64_t bad = 0;
+#pragma omp parallel for reduction(+ : bad)
+    for (uint64_t i = 0; i < n; i++) {
+        float x, a, b;
+        std::memcpy(&x, &bits[i], 4);
+        a = expf(x);
+        b = mkf_expf(x);
+        uint32_t ua, ub;
+        std::memcpy(&ua, &a, 4);
+        std::memcpy(&ub, &b, 4);
+        if (ua != ub && !(a != a && b != b)) bad++;
+    }
+    return bad;
 }
 
 // expose the shared synthetic generator so numpy-free tests can pin it

@@ -110,6 +110,14 @@ typedef struct orc_pf2d orc_pf2d;
 orc_pf2d* orc_pf2d_create(int N, int d, int K, const double* means, const double* covs, const double* weights);
 void orc_pf2d_destroy(orc_pf2d* p);
 void orc_pf2d_set_particles(orc_pf2d* p, const double* particles /* N x d */);
+/* constructor / degenerate-branch randomisation (src/pf2D.cpp:44-71,232-250) from the counter generator of mkf_synth.h */
+void orc_pf2d_set_random(orc_pf2d* p, uint64_t seed, uint64_t track, int side, int im_w, int im_h);
+void orc_pf2d_randomise(orc_pf2d* p);
+/* include/mkf_expf.h (glibc's expf restated) and the host libm's expf, for tests/test_expf.py */
+float orc_expf(float x);
+float orc_libm_expf(float x);
+/* n arguments given as float bit patterns; returns the number of bit-level mismatches between the two */
+uint64_t orc_expf_compare(const uint32_t* bits, uint64_t n);
 void orc_pf2d_get_particles(const orc_pf2d* p, double* particles, double* weights);
 /* ParticleFilter::getEstimator (src/pf2D.cpp:79-88): est[d] = sum_i weights[i] * particles.row(i), index order */
 void orc_pf2d_estimate(const orc_pf2d* p, double* est);

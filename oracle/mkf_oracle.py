@@ -86,6 +86,16 @@ def lib():
     L.orc_pf2d_create.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     L.orc_pf2d_destroy.argtypes = [C.c_void_p]
     L.orc_pf2d_set_particles.argtypes = [C.c_void_p, _dp]
+    L.orc_pf2d_set_random.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+    L.orc_pf2d_set_random.restype = None
+    L.orc_pf2d_randomise.argtypes = [C.c_void_p]
+    L.orc_pf2d_randomise.restype = None
+    L.orc_expf.argtypes = [C.c_float]
+    L.orc_expf.restype = C.c_float
+    L.orc_libm_expf.argtypes = [C.c_float]
+    L.orc_libm_expf.restype = C.c_float
+    L.orc_expf_compare.argtypes = [C.c_void_p, C.c_uint64]
+    L.orc_expf_compare.restype = C.c_uint64
     L.orc_pf2d_get_particles.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_pf2d_get_gmm.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_pf2d_estimate.argtypes = [C.c_void_p, _dp]
@@ -286,6 +296,14 @@ class Pf2d:
         assert p.shape == (self.N, self.d)
         lib().orc_pf2d_set_particles(self.h, _ptr(p, _dp))
 
+    def set_random(self, seed, track=0, side=0, im_w=640, im_h=480):
+        """parameters of the constructor / degenerate-branch randomisation (src/pf2D.cpp:44-71,232-250)"""
+        lib().orc_pf2d_set_random(self.h, int(seed), int(track), int(side), int(im_w), int(im_h))
+
+    def randomise(self):
+        """the constructor's draw: particles across the image, weights 1/N"""
+        lib().orc_pf2d_randomise(self.h)
+
     def get(self):
         p = np.zeros((self.N, self.d))
         w = np.zeros(self.N)
@@ -376,3 +394,18 @@ def propose(armL: Filter, armR: Filter, Cn, roi, tracking, like, seed, track, fr
     lib().orc_propose(armL.h, armR.h, Cn, _ptr(roi, _dp), int(tracking), _ptr(like_c, _bp), rows, cols, int(seed),
                       int(track), int(frame), _ptr(xy, _dp), _ptr(Lv, _bp))
     return xy, Lv
+
+
+def expf(x):
+    """include/mkf_expf.h: glibc's expf restated (what the oracle and the device use for src/pf2D.cpp:108)"""
+    return float(lib().orc_expf(float(np.float32(x))))
+
+
+def libm_expf(x):
+    return float(lib().orc_libm_expf(float(np.float32(x))))
+
+
+def expf_compare(bits):
+    """bit-level mismatches between mkf_expf and the host libm's expf over float bit patterns `bits` (uint32)"""
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    return int(lib().orc_expf_compare(bits.ctypes.data, bits.size))

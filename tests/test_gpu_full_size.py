@@ -162,7 +162,5 @@ def test_legacy_pf2d_full_size():
     o = orc.Pf2d(N, means, covs, wts)
     o.set_particles(parts[t])
     r = o.update(meas[t], u[t], noise[t])
-    assert rel_err_weights(w[t], r["w_norm"]) <= 1e-6    # float expf inside (quirk B12)
-    ref_par, _ = orc.resample(w[t], N, u[t])            # the reference's loop on the device's weights: bit-exact
-    assert np.array_equal(par[t], ref_par)
-    assert (par[t] != r["parents"]).mean() <= 0.01
+    assert rel_err_weights(w[t], r["w_norm"]) <= 1e-9    # float expf inside (quirk B12): include/mkf_expf.h on both sides
+    assert np.array_equal(par[t], r["parents"])          # 65 536 resampled indices, bit-exact against the oracle

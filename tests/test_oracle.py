@@ -367,6 +367,46 @@ def test_pf2d_matches_numpy(rng):
     assert np.allclose(fresh.estimate(), parts.mean(0), rtol=1e-13)  # constructor weights 1/N (:52-55)
 
 
+def test_pf2d_constructor_and_degenerate_branch(rng):
+    """src/pf2D.cpp:44-71 (constructor) and :232-250 (max weight 0: re-randomise, weights 1/N), driven by the counter
+    generator of include/mkf_synth.h: ranges, determinism, one fresh draw per epoch"""
+    N, d, K = 200, 8, 4
+    means = rng.uniform(100, 400, (K, d))
+    covs = np.stack([spd(rng, d, 40.0) for _ in range(K)])
+    wts = rng.dirichlet(np.ones(K))
+    pfs = []
+    for side in (0, 1):
+        pf = orc.Pf2d(N, means, covs, wts)
+        pf.set_random(77, 5, side)
+        pf.randomise()
+        p, w = pf.get()
+        assert np.all(w == 1.0 / N)
+        assert p[:, 0::2].min() >= 1 and p[:, 0::2].max() < 640 and p[:, 1::2].min() >= 1 and p[:, 1::2].max() < 480
+        lo, hi = (321, 640) if side else (1, 320)
+        assert p[:, 6].min() >= lo and p[:, 6].max() < hi
+        assert abs(p[:, 0].mean() - 320.5) < 45 and abs(p[:, 1].mean() - 240.5) < 35
+        pfs.append(pf)
+    twin = orc.Pf2d(N, means, covs, wts)
+    twin.set_random(77, 5, 0)
+    twin.randomise()
+    assert np.array_equal(twin.get()[0], pfs[0].get()[0])
+    assert np.array_equal(pfs[0].get()[0][:, :6], pfs[1].get()[0][:, :6])   # same key: `side` only moves column 6
+    pf = pfs[0]
+    p0 = pf.get()[0]
+    far = np.array([[1e5, 1e5], [1e5, 1e5]])
+    r = pf.update(far, 0.3, None)          # all likelihoods underflow: 0/0 weights, max weight stays 0
+    assert r["status"] == 1 and np.isnan(r["w_norm"]).all() and np.array_equal(r["parents"], np.arange(N))
+    p1, w1 = pf.get()
+    assert np.all(w1 == 1.0 / N) and not np.array_equal(p1, p0)      # epoch 1: a fresh draw
+    assert p1[:, 6].max() < 320 and p1.min() >= 1
+    r = pf.update(far, 0.3, np.ones((N, d)))
+    p2, _ = pf.get()
+    assert r["status"] == 1 and not np.array_equal(p2, p1 + 5.0)     # epoch 2 differs from epoch 1 ...
+    twin.update(far, 0.9, None)
+    twin.update(far, 0.1, np.ones((N, d)))
+    assert np.array_equal(twin.get()[0], p2)                          # ... and is reproducible; predict() follows it
+
+
 # ---------------- synthetic generator ----------------
 def test_synth_generator_pinned():
     """pins include/mkf_synth.h (shared by oracle, host and device code) to fixed values"""
