@@ -126,7 +126,8 @@ int mkf_model_get(const mkf_model* m, double* means, double* covs, double* weigh
 
 /* ---- batch of tracks ---- */
 /* replaces `new ParticleFilter(numParticles)` x T (src/pfPose.cpp:57-59).  stream: a cudaStream_t
- * to enqueue on (e.g. torch's current stream) or NULL for a private stream. */
+ * to enqueue on (e.g. torch's current stream) or NULL for a private stream.  T * N <= 2^31 - 1 (32-bit slot
+ * indices on the device).  The batch keeps a pointer to `m`: destroy the model after every batch made from it. */
 int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, int N, int device, void* stream);
 void mkf_batch_destroy(mkf_batch* b);
 int mkf_batch_sync(mkf_batch* b);

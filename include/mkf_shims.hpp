@@ -161,12 +161,16 @@ inline std::function<void(const cv::Mat&)>& sample_hook()
     return h;
 }
 // parameters given to every my_gmm constructed afterwards (drivers such as PFTracker construct their
-// ParticleFilter objects themselves, src/pfPose.cpp:58-59)
+// ParticleFilter objects themselves, src/pfPose.cpp:58-59).  The class shims are the DROP-IN tier, so their default
+// alias mode is what the reference binary computes: MKF_ALIAS_CV_SHALLOW_LITERAL (quirk B3, src/pf2DRao.cpp:153-156:
+// slots that drew the same parent share its cv::Mat and are filtered sequentially in place).  The batch C ABI keeps
+// MKF_ALIAS_INDEPENDENT as its default (mkf_params_default); set default_params().alias_mode to it to opt in here.
 inline mkf_params& default_params()
 {
     static mkf_params p = [] {
         mkf_params q;
         mkf_params_default(&q);
+        q.alias_mode = MKF_ALIAS_CV_SHALLOW_LITERAL;
         return q;
     }();
     return p;

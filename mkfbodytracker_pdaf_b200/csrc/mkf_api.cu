@@ -180,6 +180,7 @@ struct mkf_batch {
     bool dedup_ok = true; // MKF_DEDUP=0 in the environment turns the sharing off (A/B measurements)
     const int32_t* gather_index() const { return shared ? src : parent; }
     int32_t* bounds = nullptr;
+    uint8_t* ind_tail = nullptr; // T x N: per-slot components behind a wrapped indicator draw (SlotArgs::ind_tail)
     double* w_raw = nullptr;
     double* wsum = nullptr;
     uint32_t* status = nullptr;
@@ -288,7 +289,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->rep, b->src, b->hd16, b->head_count, b->w_rec, b->bounds, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -310,8 +311,10 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
         return MKF_E_INVALID;
     }
     *out = nullptr;
-    if ((long long)T * N > (1ll << 40)) {
-        mkf_set_error("mkf_batch_create: T*N too large");
+    // slot, record and head-list indices are 32-bit on the device (src / rep / parent arrays, head entries)
+    if ((long long)T > 0x7fffffffll / N) {
+        mkf_set_error("mkf_batch_create: T*N = %lld exceeds 2^31 - 1 slots per batch (split the tracks over batches)",
+                      (long long)T * N);
         return MKF_E_INVALID;
     }
     int ndev = mkf_device_count();
@@ -377,6 +380,7 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
         if (cudaMemset(b->head_count, 0, 2 * sizeof(int)) != cudaSuccess) return fail(MKF_E_CUDA);
     }
     if ((rc = dmalloc((void**)&b->bounds, (size_t)T * (m->K + 2) * sizeof(int32_t)))) return fail(rc);
+    if (m->K <= 256 && (rc = dmalloc((void**)&b->ind_tail, (size_t)b->total))) return fail(rc);
     if ((rc = dmalloc((void**)&b->w_raw, (size_t)b->total * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->wsum, (size_t)T * sizeof(double)))) return fail(rc);
     if ((rc = dmalloc((void**)&b->status, (size_t)T * sizeof(uint32_t)))) return fail(rc);
@@ -481,7 +485,7 @@ static int launch_bounds_kernel(mkf_batch* b, const double* d_u, int clear_statu
 #define LAUNCH_BOUNDS(G)                                                                                       \
     mkf_launch(k_indicator_bounds<G>, grid_for(b->T * G, 128), 128, 0, b->stream, d_u, b->T, b->N, m->K, b->d_cw_hi,       \
                                                                            b->d_cw_lo, b->d_wprior, m->prior_wmax, \
-                                                                           b->bounds, b->status, clear_status)
+                                                                           b->bounds, b->status, clear_status, b->ind_tail)
     if (m->K <= 16)
         LAUNCH_BOUNDS(16);
     else
@@ -510,10 +514,10 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     b->pose_valid = false;
     if (b->m->d == 12)
         k_reset<12><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
-                                                                    b->total, b->N, b->m->K);
+                                                                    b->total, b->N, b->m->K, b->ind_tail);
     else
         k_reset<10><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
-                                                                    b->total, b->N, b->m->K);
+                                                                    b->total, b->N, b->m->K, b->ind_tail);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     return MKF_OK;
@@ -617,6 +621,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     a.head_count = b->head_count ? b->head_count + b->head_flip : nullptr;
     a.w_rec = b->w_rec;
     a.bounds = b->bounds;
+    a.ind_tail = b->ind_tail;
     a.meas = d_meas;
     a.comp_const = b->d_comp;
     a.w_raw = b->w_raw;
@@ -971,7 +976,7 @@ extern "C" int mkf_batch_download(mkf_batch* b, double* x, double* P, double* w_
     }
     if (w_norm || indicators) {
         k_aux_outputs<<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->w_raw, b->wsum, b->bounds, b->total, b->N,
-                                                                       m->K, own.devp, oi.devp);
+                                                                       m->K, own.devp, oi.devp, b->ind_tail);
         MKF_LAUNCHED();
         if (cudaGetLastError() != cudaSuccess) {
             mkf_set_error("k_aux_outputs launch failed");

@@ -312,7 +312,7 @@ extern "C" int mkf_batch_assoc_results(mkf_batch* b, uint8_t* gate, double* weig
         if ((rc = ow.init(b, weights, nc, mem, tmp))) return rc;
         k_aux_outputs<<<grid_for((long long)nc, 256), 256, 0, b->stream>>>((const double*)b->as_w.p,
                                                                           (const double*)b->as_wsum.p, nullptr,
-                                                                          (long long)nc, b->as_C, 0, ow.devp, nullptr);
+                                                                          (long long)nc, b->as_C, 0, ow.devp, nullptr, nullptr);
         MKF_LAUNCHED();
         if (cudaGetLastError() != cudaSuccess) {
             tmp.release();

@@ -69,7 +69,9 @@ struct SlotArgs {
     int* __restrict__ head_count;
     double* __restrict__ w_rec;
     int split; // 1: this frame runs k_share_keys -> k_slot_update_heads_direct (weights per record in w_rec)
-    const int32_t* __restrict__ bounds; // T x (K+2): e_0..e_{K-1}, wrap_from, wrap_k
+    const int32_t* __restrict__ bounds; // T x (K+2): e_0..e_{K-1}, wrap_from, wrap_k (-1: read ind_tail)
+    const uint8_t* __restrict__ ind_tail; // T x N: component of the slots at or after wrap_from (written by the
+                                          // literal loop of k_indicator_bounds when the draw wrapped past component K-1)
     const double* __restrict__ meas;
     const double* __restrict__ comp_const; // K x CS (global; staged to shared memory by TMA)
     double* __restrict__ w_raw;
@@ -349,12 +351,18 @@ __device__ __forceinline__ bool slot_math(double (&v)[SlotLay<D>::NE], const dou
     return ok;
 }
 
-// component of local slot j from the run boundaries written by k_indicator_bounds
-__device__ __forceinline__ int mkf_component_of(const int32_t* __restrict__ bt, int K, int j)
+// component of local slot j from the run boundaries written by k_indicator_bounds.  tail: the track's row of
+// ind_tail -- after a draw that wrapped past the last component (prior weights summing to less than the thresholds
+// reach, src/pf2DRao.cpp:198-207 with idx = (idx+1) % L) the components are no longer monotone in j and are read per slot
+__device__ __forceinline__ int mkf_component_of(const int32_t* __restrict__ bt, int K, int j,
+                                                const uint8_t* __restrict__ tail)
 {
     int k = 0;
     for (int q = 0; q < K - 1; q++) k += (j >= __ldg(bt + q)) ? 1 : 0;
-    if (j >= __ldg(bt + K)) k = __ldg(bt + K + 1);
+    if (j >= __ldg(bt + K)) {
+        const int wk = __ldg(bt + K + 1);
+        k = (wk >= 0 || !tail) ? max(wk, 0) : (int)tail[j];
+    }
     return k;
 }
 
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
             }
             mkf_load_meas(a, t, j, zc);
             bt = a.bounds + t * (a.K + 2);
-            k = mkf_component_of(bt, a.K, j);
+            k = mkf_component_of(bt, a.K, j, a.ind_tail ? a.ind_tail + t * a.N : nullptr);
         }
     }
     mkf_mbar_wait(&mbar, 0);
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
             a.w_raw[so] = w;
             if (++i >= len) break;
             mkf_load_meas(a, t, j + i, zc);
-            k = mkf_component_of(bt, a.K, j + i);
+            k = mkf_component_of(bt, a.K, j + i, a.ind_tail ? a.ind_tail + t * a.N : nullptr);
         }
     }
 }
@@ -560,7 +568,8 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_shared(const SlotArgs a)
         for (int g = 0; g < G; g++) {
             if (s0 + g < a.total) {
                 tl[g] = t_run;
-                kk[g] = mkf_component_of(a.bounds + (long long)t_run * (a.K + 2), a.K, j_run);
+                kk[g] = mkf_component_of(a.bounds + (long long)t_run * (a.K + 2), a.K, j_run,
+                                         a.ind_tail ? a.ind_tail + (long long)t_run * a.N : nullptr);
                 if (++j_run == a.N) {
                     j_run = 0;
                     t_run++;
@@ -759,7 +768,8 @@ __global__ void __launch_bounds__(256) k_share_keys(const SlotArgs a)
                     }
                 }
                 tl[g] = t_run;
-                kk[g] = (j_run >= wf) ? wk : k_lin;
+                kk[g] = (j_run >= wf) ? ((wk >= 0 || !a.ind_tail) ? max(wk, 0) : (int)a.ind_tail[(long long)t_run * a.N + j_run])
+                                      : k_lin;
                 // slots of a track that drew the same candidate see the same measurement column
                 if (WITH_BIN) kk[g] |= __ldg(a.bins + ((long long)t_run * 2 + a.hand) * a.N + j_run) << 8;
                 if (++j_run == a.N) {
@@ -940,7 +950,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
                 }
                 double zc[MKF_M], w;
                 mkf_load_meas(a, t, j, zc);
-                const int k = mkf_component_of(bt, a.K, j);
+                const int k = mkf_component_of(bt, a.K, j, a.ind_tail ? a.ind_tail + t * a.N : nullptr);
                 slot_math<D, true>(v, a.comp_const + (long long)k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
                 double2* dst = a.st_out + (s >> 5) * (long long)L::TILE2 + (s & 31) * L::H;
                 for (int p = 0; p < L::NP; p++) {
@@ -969,7 +979,7 @@ template <int GROUP>
 __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, int N, int K,
                                    const double* __restrict__ cw_hi, const double* __restrict__ cw_lo,
                                    const double* __restrict__ wprior, double wmax, int32_t* __restrict__ bounds,
-                                   uint32_t* __restrict__ status, int clear_status)
+                                   uint32_t* __restrict__ status, int clear_status, uint8_t* __restrict__ ind_tail)
 {
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
@@ -1033,12 +1043,21 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
         beta = __dadd_rn(beta, step);
         if (wraps == 0) {
             bt[idx] = i + 1; // last output index + 1 holding component idx (made cumulative below)
-        } else if (wrap_from == N) {
-            wrap_from = i;
-            wrap_k = idx;
-            st |= MKF_ST_IND_WRAP;
+        } else {
+            // past the last component the loop starts over at component 0 and keeps walking: from here on the
+            // components are stored per slot (one value when they all agree, which is what a prior that sums to
+            // 1 - 3e-14 produces for its last output; a tail row otherwise)
+            if (wrap_from == N) {
+                wrap_from = i;
+                wrap_k = idx;
+                st |= MKF_ST_IND_WRAP;
+            } else if (idx != wrap_k) {
+                wrap_k = -1;
+            }
+            if (ind_tail) ind_tail[t * N + i] = (uint8_t)idx;
         }
     }
+    if (wrap_k < 0 && !ind_tail) wrap_k = 0; // (no tail storage: never the case for a batch)
     int run = 0;
     for (int q = 0; q < K; q++) {
         if (bt[q] > run) run = bt[q];
@@ -1660,14 +1679,15 @@ __global__ void __launch_bounds__(128) k_estimate_small(const double2* __restric
 // resetTracker (src/my_gmm.cpp:30-42): slot j <- (mu_k, Sigma_k) of its drawn component
 template <int D>
 __global__ void k_reset(double2* __restrict__ st, int32_t* __restrict__ parent, const int32_t* __restrict__ bounds,
-                        const double* __restrict__ init_const, long long total, int N, int K)
+                        const double* __restrict__ init_const, long long total, int N, int K,
+                        const uint8_t* __restrict__ ind_tail)
 {
     using L = SlotLay<D>;
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= total) return;
     const long long t = s / N;
     const int j = (int)(s - t * N);
-    const int k = mkf_component_of(bounds + t * (K + 2), K, j);
+    const int k = mkf_component_of(bounds + t * (K + 2), K, j, ind_tail ? ind_tail + t * N : nullptr);
     const double* __restrict__ ic = init_const + (long long)k * L::NE;
     double2* __restrict__ dst = st + (s >> 5) * (long long)L::TILE2 + (s & 31) * L::H;
     for (int p = 0; p < L::NP; p++) {
@@ -1781,13 +1801,15 @@ __global__ void k_download(const double2* __restrict__ st, const int32_t* __rest
 // w_norm = w_raw / wsum (src/pf2DRao.cpp:145-148) and the per-slot component indicators
 __global__ void k_aux_outputs(const double* __restrict__ w_raw, const double* __restrict__ wsum,
                               const int32_t* __restrict__ bounds, long long total, int N, int K,
-                              double* __restrict__ w_norm, int32_t* __restrict__ indicators)
+                              double* __restrict__ w_norm, int32_t* __restrict__ indicators,
+                              const uint8_t* __restrict__ ind_tail)
 {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= total) return;
     const long long t = s / N;
     if (w_norm) w_norm[s] = __ddiv_rn(w_raw[s], wsum[t]);
-    if (indicators) indicators[s] = mkf_component_of(bounds + t * (K + 2), K, (int)(s - t * N));
+    if (indicators)
+        indicators[s] = mkf_component_of(bounds + t * (K + 2), K, (int)(s - t * N), ind_tail ? ind_tail + t * N : nullptr);
 }
 
 // synthetic workload of include/mkf_synth.h generated in place (bench / large-batch tests)

@@ -492,7 +492,7 @@ extern "C" int mkf_pf2d_get(mkf_pf2d* p, double* particles, double* w_norm, int3
             dst = (double*)tmp.p;
         }
         k_aux_outputs<<<grid_for((long long)tot, 256), 256, 0, p->stream>>>(p->w_raw, p->wsum, nullptr, (long long)tot,
-                                                                           p->N, 0, dst, nullptr);
+                                                                           p->N, 0, dst, nullptr, nullptr);
         MKF_LAUNCHED();
         if (host) cudaMemcpyAsync(w_norm, dst, tot * 8, cudaMemcpyDeviceToHost, p->stream);
     }

@@ -7,6 +7,7 @@ import pytest
 import mkf_oracle as orc
 import mkfbodytracker_pdaf_b200 as mk
 from helpers import RTOL, rel_err, rel_err_weights, synth_frame, synth_u_init
+from mkfbodytracker_pdaf_b200 import _lib as L_
 
 pytestmark = pytest.mark.gpu
 
@@ -130,6 +131,75 @@ def test_config3_full_size_gate_and_bins(left_arm, right_arm):
         want = orc.associate(fL, fR, cand[t], Lv[t], roi[t], u_c[t])
         assert np.array_equal(res["gate"][t], want["gate"]) and np.array_equal(bins[t], want["bins"])
         assert rel_err_weights(w[t], want["weights"]) <= RTOL
+
+
+def test_config3_full_size_associate_and_update(left_arm, right_arm):
+    """BASELINE config 3 at its real size: 16 384 persons x 500 slots per arm x 17 candidates per hand (1 detection +
+    16 clutter), association FOLLOWED by both arm updates (src/pfPose.cpp:238-326), three free-running frames.
+    Gate decisions are checked for every person and frame; six persons are replayed through the oracle from reset:
+    candidate bins, resampled indices of both arms bit-exact, weights and estimates within 1e-4."""
+    torch = pytest.importorskip("torch")
+    T, N, Cn, frames = 16384, 500, 17, 3
+    dev = torch.device("cuda:0")
+    s = torch.cuda.Stream()
+    spots = (0, 50, 75, 8191, 12345, T - 1)
+    with torch.cuda.stream(s):
+        b0 = mk.TrackBatch(left_arm.mk, T, N, stream=s.cuda_stream)
+        b1 = mk.TrackBatch(right_arm.mk, T, N, stream=s.cuda_stream)
+        rng = np.random.default_rng(33)
+        u0 = rng.random(T)
+        b0.reset(u0)
+        b1.reset(u0)
+        fl = {t: orc.Filter(left_arm.orc, N) for t in spots}
+        fr_ = {t: orc.Filter(right_arm.orc, N) for t in spots}
+        for t in spots:
+            fl[t].reset(u=u0[t])
+            fr_[t].reset(u=u0[t])
+        roi = np.tile(np.array([300.0, 51.0, 47.0, 47.0]), (T, 1))
+        par = [torch.empty((T, N), dtype=torch.int32, device=dev) for _ in range(2)]
+        wn = [torch.empty((T, N), dtype=torch.float64, device=dev) for _ in range(2)]
+        for frame in range(frames):
+            cand = np.zeros((T, 2, 2, Cn))
+            cand[:, :, 0] = rng.uniform(-32, 672, (T, 2, Cn))
+            cand[:, :, 1] = rng.uniform(-24, 504, (T, 2, Cn))
+            hx = 388.0 + 60.0 * np.sin(2 * np.pi * (frame / 75.0 + rng.random(T)))  # the detection: near the hand
+            hy = 250.0 + 70.0 * np.sin(2 * np.pi * (frame / 50.0 + rng.random(T)))
+            cand[:, 0, 0, 0], cand[:, 0, 1, 0] = hx + 3 * rng.standard_normal(T), hy + 3 * rng.standard_normal(T)
+            cand[:, 1, 0, 0], cand[:, 1, 1, 0] = hx - 140 + 3 * rng.standard_normal(T), hy + 3 * rng.standard_normal(T)
+            cand[::50, :, 0, 1] = 0.0     # exactly on the image border: the gate is strict (src/pfPose.cpp:251)
+            cand[::75, :, 1, 2] = 480.0
+            Lv = np.where(rng.random((T, 2, Cn)) < 0.5, 0, rng.integers(1, 129, (T, 2, Cn))).astype(np.uint8)
+            Lv[:, :, 0] = rng.integers(200, 256, (T, 2))
+            u_c, u_i, u_p = rng.random((T, 2)), rng.random((T, 2)), rng.random((T, 2))
+            mk.associate(b0, b1, cand, Lv, roi, u_c, u_i, u_p, do_update=True)
+            res = mk.assoc_results(b0, Cn)
+            x, y = cand[:, :, 0], cand[:, :, 1]
+            gate = (y > 0) & (y < 480) & (x > 0) & (x < 640) & (Lv != 0)
+            assert np.array_equal(res["gate"].astype(bool), gate), "gate decisions must be bit-exact at full size"
+            w = res["weights"]
+            assert np.all(w[~gate] == 0) and np.allclose(w.sum(2), 1.0, rtol=0, atol=1e-12)
+            bins = res["bins"]
+            assert np.all(np.diff(bins, axis=2) >= 0) and bins.min() >= 0 and bins.max() < Cn
+            assert np.all(np.take_along_axis(gate, bins.astype(np.int64), axis=2)), "only gated candidates are drawn"
+            for arm, b in enumerate((b0, b1)):
+                mk._lib.check(mk._lib.lib.mkf_batch_download(b._h, None, None, None, wn[arm].data_ptr(), None,
+                                                             par[arm].data_ptr(), None, None, mk.MEM_DEVICE))
+            est = [b.estimate() for b in (b0, b1)]
+            st = b0.status() | b1.status()
+            assert not (st & (L_.ST_POST_DEGENERATE | L_.ST_CHOL_FAIL | L_.ST_CAND_DEGENERATE)).any()
+            for arm in range(2):
+                p = par[arm].cpu().numpy()
+                assert p.min() >= 0 and p.max() < N and np.all(np.diff(p, axis=1) >= 0)
+            for t in spots:
+                want = orc.associate(fl[t], fr_[t], cand[t], Lv[t], roi[t], u_c[t])
+                assert np.array_equal(res["gate"][t], want["gate"]) and np.array_equal(bins[t], want["bins"]), (frame, t)
+                assert rel_err_weights(w[t], want["weights"]) <= RTOL
+                for arm, f in enumerate((fl[t], fr_[t])):
+                    r = f.update(want["meas"][arm], u_i[t, arm], u_p[t, arm])
+                    assert np.array_equal(par[arm][t].cpu().numpy(), r["parents"]), (frame, t, arm)
+                    assert rel_err_weights(wn[arm][t].cpu().numpy(), r["w_norm"]) <= RTOL
+                    xo, po = f.estimate()
+                    assert rel_err(est[arm][0][t], xo) <= RTOL and rel_err(est[arm][1][t], po) <= RTOL
 
 
 def test_legacy_pf2d_full_size():

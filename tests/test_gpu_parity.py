@@ -527,6 +527,44 @@ def test_indicator_bounds_all_shapes_and_edge_draws(left_arm):
                 assert np.array_equal(ind[t], want), (K, N, t)
 
 
+@pytest.mark.parametrize("N", [10, 500, 130])
+def test_indicator_draw_with_unnormalised_prior_wraps_like_the_loop(left_arm, N):
+    """Prior weights that do not sum to 1 (my_gmm::loadGaussian takes any w, src/my_gmm.cpp:45-52): the literal loop of
+    src/pf2DRao.cpp:198-207 walks past the last component and starts over at component 0 -- possibly several times --
+    so the indicators are no longer monotone in the slot index.  ADVICE r1: w = [.2, .2, .1], N = 10, u = .5 must give
+    0,0,1,1,2,0,0,1,1,2.  Checked through reset() and through full frame updates (shared column -> record sharing,
+    per-slot columns -> k_slot_update) against the oracle."""
+    rng = np.random.default_rng(17)
+    a = left_arm.arrays
+    for wts in (np.array([0.2, 0.2, 0.1]), np.array([0.05, 0.3, 0.02, 0.11]), np.array([0.7, 0.2999])):
+        K = len(wts)
+        means = a["means"][:K]
+        covs = a["covs"][:K]
+        gam = a["gamma"][:K]
+        m = mk.Model.from_arrays(means, covs, wts, gam, a["pca_proj"], a["pca_mean"])
+        om = orc.Model(means, covs, wts, gam, a["pca_proj"], a["pca_mean"])
+        u = np.concatenate([[0.5, 0.0, 1.0 - 2.0**-53], rng.random(5)])
+        T = len(u)
+        b = mk.TrackBatch(m, T, N)
+        b.reset(u)
+        ind = b.download(state=False, cov=False)["indicators"]
+        for t in range(T):
+            want, _ = orc.resample(wts, N, u[t])
+            assert np.array_equal(ind[t], want), (wts, N, t)
+        if K == 3 and N == 10:
+            assert list(ind[0]) == [0, 0, 1, 1, 2, 0, 0, 1, 1, 2]
+        fs = [orc.Filter(om, N) for _ in range(T)]
+        for f, uu in zip(fs, u):
+            f.reset(u=uu)
+        for fr in range(4):
+            meas, ui, up = synth_frame(0x5EED0002, list(range(T)), fr, N if fr % 2 else None)
+            res = [f.update(meas[t], ui[t], up[t]) for t, f in enumerate(fs)]
+            b.update(meas, ui, up)
+            stats, d = compare_frame(b, fs, res)
+            assert_parity(stats)
+        assert (b.status() & L.ST_IND_WRAP).any()
+
+
 def test_host_async_pipeline_matches_synchronous_calls(left_arm):
     """MKF_MEM_HOST_ASYNC (inputs copied on the library's copy stream, results returned on its output stream, no
     synchronisation until mkf_batch_sync) gives bit-identical poses to the synchronous host path, frame by frame,

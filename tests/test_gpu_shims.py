@@ -62,8 +62,9 @@ def test_shim_driver_against_oracle(left_arm):
     xu, Pu = left_arm.orc.kf_update(3, z, xo, Po)
     got = np.array(lines["KFUPD"], float)
     assert np.allclose(got[:12], xu, rtol=1e-9, atol=1e-8) and abs(got[12] - Pu[0, 0]) <= 1e-9 * np.abs(Pu).max()
-    # the frame loop with the shim's own draws
-    f = orc.Filter(left_arm.orc, N)
+    # the frame loop with the shim's own draws; the class shims default to the reference binary's shallow-copy
+    # aliasing (quirk B3), the mode its own sources compute
+    f = orc.Filter(left_arm.orc, N, alias_mode=orc.ALIAS_CV_SHALLOW_LITERAL)
     f.reset(u=float(lines["INIT_U"][0]))
     for fr, ui, up, xbar in frames_out:
         meas, _, _ = synth_frame(0x5EED0001, [0], fr, N, jitter=0)
