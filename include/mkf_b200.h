@@ -248,6 +248,33 @@ int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u, const doub
 int mkf_pf2d_estimate(mkf_pf2d* p, double* est, int mem);
 int mkf_pf2d_sync(mkf_pf2d* p);
 
+/* ---- multi-GPU: tracks shard over the GPUs of one box, one final gather of per-track summaries ----
+ * The reference is one single-threaded process (src/pfPoseTracker.cpp:5-14) tracking one person; independent persons /
+ * tracks have no coupling, so a batch per GPU needs no per-frame exchange.  The only collective is the
+ * gather below: every rank contributes one row {pose[D], wsum, (double)status} per track and receives all ranks' rows
+ * (ncclAllGather over NVLink / NVSwitch, enqueued on the batch's stream).  NCCL is bound at run time (dlopen of
+ * libnccl.so.2 -- a copy already loaded into the process, e.g. torch's, is shared); without it these calls return
+ * MKF_E_UNSUPPORTED and everything else works. */
+typedef struct mkf_comm mkf_comm;
+#define MKF_COMM_ID_BYTES 128
+/* contiguous block partition of `total` tracks: rank r filters tracks [first, first + count) */
+int mkf_shard_tracks(int64_t total, int world, int rank, int64_t* first, int64_t* count);
+/* rank 0 makes an id (ncclGetUniqueId) and hands its 128 bytes to the other ranks by any host channel; every rank then
+ * creates its communicator (ncclCommInitRank) for the device its batch lives on.  mkf_comm_wrap adopts an existing
+ * ncclComm_t instead (not destroyed by mkf_comm_destroy). */
+int mkf_comm_unique_id(void* id128);
+int mkf_comm_create(mkf_comm** out, int nranks, int rank, const void* id128, int device);
+int mkf_comm_wrap(mkf_comm** out, void* nccl_comm, int device);
+void mkf_comm_destroy(mkf_comm* c);
+int mkf_comm_info(const mkf_comm* c, int* nranks, int* rank, int* nccl_version);
+/* this rank's summary rows: rows x (D + 2) doubles, rows >= T (rows beyond T are zero: padding for ragged shards).
+ * Runs the estimator (src/pf2DRao.cpp:23-31, src/pfPose.cpp:347-348) for the pose columns. */
+int mkf_batch_summaries(mkf_batch* b, int64_t rows, double* out, int mem);
+/* the gather: out = nranks x rows_per_rank x (D + 2) doubles in rank order on every rank (rows_per_rank = the largest
+ * shard; 0 = this batch's T when all shards are equal).  Device `out`: asynchronous on the batch's stream, packed and
+ * gathered in place.  Host `out`: complete on return. */
+int mkf_batch_gather_summaries(mkf_batch* b, mkf_comm* c, int64_t rows_per_rank, double* out, int mem);
+
 /* ---- synthetic workload (include/mkf_synth.h), generated on the device ---- */
 /* fills meas (device, layout per meas_layout) and u_ind/u_post (device, T each) for `frame` */
 int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint64_t frame, int jitter, int meas_layout,

@@ -1125,3 +1125,4 @@ extern "C" int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint6
 #include "mkf_assoc.cuh"
 #include "mkf_extra.cuh"
 #include "mkf_pf2d.cuh"
+#include "mkf_comm.cuh"

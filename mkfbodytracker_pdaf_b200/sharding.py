@@ -2,9 +2,77 @@
 block-partitioned over the ranks of one node with NO data-path collective; the only
 communication is one final all_gather of the per-track summaries {pose[D], wsum, status}.
 
-torch.distributed is used for the plumbing only (NCCL over NVLink on the GPU box, gloo in the
-CPU tests)."""
+Two routes to that gather:
+  * `Comm` + `gather_summaries_native`: the C ABI's own collective (mkf_batch_gather_summaries: rows packed on the device
+    and gathered in place with ncclAllGather on the batch's stream) -- what a C++ host uses; torch.distributed only
+    carries the 128-byte NCCL id from rank 0 to the others;
+  * `pack_summary` + `gather_summaries`: the same rows through torch.distributed (gloo in the CPU tests)."""
 from __future__ import annotations
+
+import ctypes as C
+
+
+class Comm:
+    """one NCCL communicator per rank, created through the C ABI (mkf_comm_create)"""
+
+    def __init__(self, world: int, rank: int, device: int, id_bytes: bytes):
+        from . import _lib as L
+        self._L = L
+        h = C.c_void_p()
+        buf = C.create_string_buffer(id_bytes, L.COMM_ID_BYTES)
+        L.check(L.lib.mkf_comm_create(C.byref(h), world, rank, C.cast(buf, C.c_void_p), device))
+        self._h = h
+        self.world, self.rank, self.device = world, rank, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        from . import _lib as L
+        buf = C.create_string_buffer(L.COMM_ID_BYTES)
+        L.check(L.lib.mkf_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int):
+        """rank 0 draws the NCCL id; the initialised torch.distributed group (any backend) broadcasts its 128 bytes"""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(world, rank, device, box[0])
+
+    def nccl_version(self) -> int:
+        v = C.c_int(0)
+        self._L.check(self._L.lib.mkf_comm_info(self._h, None, None, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self._h:
+            self._L.lib.mkf_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gather_summaries_native(batch, comm: Comm, out, rows_per_rank: int = 0):
+    """mkf_batch_gather_summaries: `out` (world * rows_per_rank, D + 2) float64, device tensor (asynchronous on the
+    batch's stream) or host array (complete on return)"""
+    from . import _lib as L
+    from .tracker import _addr
+    addr, mem = _addr(out)
+    L.check(L.lib.mkf_batch_gather_summaries(batch._h, comm._h, int(rows_per_rank), addr, mem))
+    return out
+
+
+def shard_tracks_native(total_tracks: int, world: int, rank: int):
+    """mkf_shard_tracks (the C ABI's copy of shard_tracks)"""
+    from . import _lib as L
+    first, n = C.c_int64(0), C.c_int64(0)
+    L.check(L.lib.mkf_shard_tracks(total_tracks, world, rank, C.byref(first), C.byref(n)))
+    return first.value, n.value
 
 
 def shard_tracks(total_tracks: int, world: int, rank: int):

@@ -23,6 +23,47 @@ def test_shard_tracks_partitions_exactly():
         shard_tracks(10, 2, 2)
 
 
+def test_c_abi_shard_tracks_matches_python():
+    """mkf_shard_tracks (what a C++ host calls) is the same partition"""
+    from mkfbodytracker_pdaf_b200.sharding import shard_tracks_native
+    import mkfbodytracker_pdaf_b200 as mk
+    for total in (0, 1, 7, 4096, 1048576, 1000003):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                assert shard_tracks_native(total, world, r) == shard_tracks(total, world, r)
+    with pytest.raises(mk.MkfError):
+        shard_tracks_native(10, 2, 2)
+
+
+@pytest.mark.gpu
+def test_native_gather_single_rank(left_arm):
+    """mkf_comm_create / mkf_batch_gather_summaries with one rank (the -m gpu box has one GPU; bench.py --gpus N runs
+    the same call over N ranks and cross-checks rows between ranks): rows = {pose, wsum, status}, padding rows zero,
+    device and host destinations agree"""
+    import mkfbodytracker_pdaf_b200 as mk
+    from helpers import synth_frame, synth_u_init
+    from mkfbodytracker_pdaf_b200.sharding import Comm, gather_summaries_native
+    T, N, seed = 37, 120, 0x5EED0005
+    b = mk.TrackBatch(left_arm.mk, T, N)
+    b.reset(synth_u_init(seed, range(T)))
+    for fr in range(2):
+        b.update(*synth_frame(seed, list(range(T)), fr))
+    comm = Comm(1, 0, 0, Comm.unique_id())
+    assert comm.nccl_version() >= 20000
+    D = left_arm.mk.D
+    host = np.full((T + 3, D + 2), -1.0)
+    gather_summaries_native(b, comm, host, rows_per_rank=T + 3)
+    _, pose = b.estimate()
+    d = b.download(state=False, cov=False)
+    assert np.array_equal(host[:T, :D], pose) and np.array_equal(host[:T, D], d["wsum"])
+    assert np.array_equal(host[:T, D + 1], d["status"].astype(np.float64)) and not host[T:].any()
+    dev = torch.full((T, D + 2), -1.0, dtype=torch.float64, device="cuda:0")
+    gather_summaries_native(b, comm, dev)
+    b.sync()
+    assert np.array_equal(dev.cpu().numpy(), host[:T])
+    comm.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
