@@ -247,6 +247,10 @@ int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u, const doub
  * Device outputs are ordered on the filter's stream; host outputs are complete on return. */
 int mkf_pf2d_estimate(mkf_pf2d* p, double* est, int mem);
 int mkf_pf2d_sync(mkf_pf2d* p);
+/* per-kernel device timing of mkf_pf2d_update (CUDA events on the filter's stream): arm for up to max_updates updates
+ * (0 disables); read returns the summed milliseconds of ms[3] = {weights, normalise + resample, gather + predict} */
+int mkf_pf2d_profile(mkf_pf2d* p, int max_updates);
+int mkf_pf2d_profile_read(mkf_pf2d* p, double* ms, int* n_updates);
 
 /* ---- multi-GPU: tracks shard over the GPUs of one box, one final gather of per-track summaries ----
  * The reference is one single-threaded process (src/pfPoseTracker.cpp:5-14) tracking one person; independent persons /

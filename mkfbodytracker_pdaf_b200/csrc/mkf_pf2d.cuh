@@ -33,6 +33,10 @@ struct mkf_pf2d {
     // epoch n = the n-th update
     PfRand rnd;
     uint8_t* d_side = nullptr;
+    // optional per-kernel timing (mkf_pf2d_profile): start | weights | normalise + resample | gather + predict
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_n = 0, prof_cap = 0;
 };
 
 template <int D>
@@ -193,6 +197,7 @@ extern "C" void mkf_pf2d_destroy(mkf_pf2d* p)
     p->in_u.release();
     p->in_noise.release();
     p->in_part.release();
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -428,6 +433,8 @@ extern "C" int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u,
     if ((rc = pf_in_ptr(p, u, (size_t)p->T, mem, p->in_u, &d_u))) return rc;
     if ((rc = pf_in_ptr(p, noise, (size_t)tot * p->d, mem, p->in_noise, &d_noise))) return rc;
     CK(cudaMemsetAsync(p->status, 0, (size_t)p->T * 4, p->stream));
+    cudaEvent_t* pe = (p->prof_on && p->prof_n < p->prof_cap) ? &p->prof_ev[(size_t)p->prof_n * 4] : nullptr;
+    if (pe) cudaEventRecord(pe[0], p->stream);
     const size_t smem = (size_t)p->K * p->gstride * sizeof(double);
     if (smem > 200 * 1024) {
         mkf_set_error("mkf_pf2d_update: GMM too large for shared memory");
@@ -449,9 +456,11 @@ extern "C" int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u,
 #undef LAUNCH_W
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    if (pe) cudaEventRecord(pe[1], p->stream);
     if ((rc = run_resample(p->stream, p->T, p->w_raw, p->N, p->N, d_u, 1, 1, p->wsum, p->parent, p->status,
                            nullptr, 1, 0, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE)))
         return rc;
+    if (pe) cudaEventRecord(pe[2], p->stream);
     p->rnd.epoch++; // epoch n = the n-th update (the degenerate branch's draws are keyed on it)
     if (p->d == 8)
         k_pf2d_resample_predict_v<8><<<grid_for(tot, 256), 256, 0, p->stream>>>(p->part[p->cur], p->part[p->cur ^ 1],
@@ -467,7 +476,53 @@ extern "C" int mkf_pf2d_update(mkf_pf2d* p, const double* meas, const double* u,
                                                                                   p->N, p->d, p->rnd);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    if (pe) {
+        cudaEventRecord(pe[3], p->stream);
+        p->prof_n++;
+    }
     p->cur ^= 1;
+    return MKF_OK;
+}
+
+// per-kernel device timing of mkf_pf2d_update (CUDA events on the filter's stream; bench.py)
+extern "C" int mkf_pf2d_profile(mkf_pf2d* p, int max_updates)
+{
+    if (!p || max_updates < 0) {
+        mkf_set_error("mkf_pf2d_profile: invalid argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+    p->prof_ev.clear();
+    p->prof_n = 0;
+    p->prof_cap = max_updates;
+    p->prof_on = max_updates > 0;
+    for (int i = 0; i < max_updates * 4; i++) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        p->prof_ev.push_back(e);
+    }
+    return MKF_OK;
+}
+extern "C" int mkf_pf2d_profile_read(mkf_pf2d* p, double* ms /* 3: weights, normalise+resample, gather+predict */,
+                                     int* n_updates)
+{
+    if (!p || !ms) {
+        mkf_set_error("mkf_pf2d_profile_read: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    ms[0] = ms[1] = ms[2] = 0.0;
+    for (int i = 0; i < p->prof_n; i++)
+        for (int k = 0; k < 3; k++) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, p->prof_ev[(size_t)i * 4 + k], p->prof_ev[(size_t)i * 4 + k + 1]));
+            ms[k] += t;
+        }
+    if (n_updates) *n_updates = p->prof_n;
+    p->prof_n = 0;
     return MKF_OK;
 }
 

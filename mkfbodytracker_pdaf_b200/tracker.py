@@ -306,6 +306,15 @@ class Pf2dBatch:
         """the constructor's draw (src/pf2D.cpp:44-71): particles across the image, weights 1/N"""
         L.check(L.lib.mkf_pf2d_randomise(self._h))
 
+    def profile(self, max_updates):
+        L.check(L.lib.mkf_pf2d_profile(self._h, int(max_updates)))
+
+    def profile_read(self):
+        ms = (C.c_double * 3)()
+        n = C.c_int(0)
+        L.check(L.lib.mkf_pf2d_profile_read(self._h, ms, C.byref(n)))
+        return dict(ms_weights=ms[0], ms_resample=ms[1], ms_predict=ms[2], n=n.value)
+
     def update(self, meas, u, noise=None):
         mem = _same_mem(meas, u, noise)
         L.check(L.lib.mkf_pf2d_update(self._h, _addr(meas)[0], _addr(u)[0], _addr(noise)[0], mem))

@@ -147,3 +147,22 @@ def test_candidate_proposal_front_end(left_arm, right_arm):
                 assert np.array_equal(d["parents"][t], r["parents"])
                 xo, _ = f.get_state()
                 assert rel_err(d["x"][t], xo) <= RTOL
+
+
+def test_bench_reference_arm_reads_models_without_the_product():
+    """bench.py's CPU legs parse the model YAMLs themselves (the reference arm must not map libmkf_b200.so); the
+    arrays equal what the product's loader (cv::FileStorage semantics, src/pfPose.cpp:34-55) returns"""
+    import importlib.util
+    import os
+    import mkfbodytracker_pdaf_b200 as mk
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    got = bench.model_arrays(bench.LEFT_YML, bench.RIGHT_YML)
+    want = mk.Model.load(mk.LEFT_ARM_MODEL, mk.RIGHT_ARM_MODEL).arrays()
+    for k in ("means", "covs", "weights", "gamma", "pca_proj", "pca_mean"):
+        assert np.array_equal(np.asarray(got[k]).reshape(-1), np.asarray(want[k]).reshape(-1)), k
+    src = open(os.path.join(root, "bench.py")).read()
+    cpu_part = src[src.index("def read_opencv_yaml"):src.index("_JSON_FD = None")]
+    assert "mkfbodytracker_pdaf_b200 as" not in cpu_part and "import mkfbodytracker" not in cpu_part
