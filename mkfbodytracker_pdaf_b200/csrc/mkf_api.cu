@@ -14,6 +14,7 @@
 
 #include "mkf_internal.h"
 #include "mkf_kernels.cuh"
+#include "mkf_runs.cuh"
 #include "../../include/mkf_expf.h"
 
 // events per profiled update: start | bounds | share keys | slot kernel | repair | resample
@@ -177,6 +178,17 @@ struct mkf_batch {
     double* w_rec = nullptr;
     bool share_split = true; // MKF_SHARE_SPLIT=0 at creation: the single-launch variant k_slot_update_shared (A/B runs)
     bool shared = false; // the children of the last update share records (read state through src, not parent)
+    // run-length particle sets (mkf_runs.cuh): the current set as a list of (record of st[cur], multiplicity) per track,
+    // the head table of the last frame, and the draw / seed of its resample (for the on-demand per-slot replay)
+    int2* runs = nullptr;
+    int* nruns = nullptr;
+    int4* hmeta = nullptr;
+    int* nheads = nullptr;
+    double* u_keep = nullptr;
+    uint64_t* seed_keep = nullptr;
+    bool run_mode = false;    // `runs` describes the current particle set
+    bool slots_valid = true;  // parent / src / rep / w_raw describe it too (false after a run-level frame until
+                              // ensure_slots() replays the resample per slot)
     bool dedup_ok = true; // MKF_DEDUP=0 in the environment turns the sharing off (A/B measurements)
     const int32_t* gather_index() const { return shared ? src : parent; }
     int32_t* bounds = nullptr;
@@ -213,6 +225,8 @@ struct mkf_batch {
     int prof_n = 0, prof_every = 1;
     uint64_t prof_tick = 0;
 };
+
+static int ensure_slots(mkf_batch* b); // per-slot views of a run-level particle set (defined with update_device)
 
 static bool is_device_ptr(const void* p, int mem)
 {
@@ -289,7 +303,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->rep, b->src, b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -378,6 +392,17 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
             (rc = dmalloc((void**)&b->w_rec, (size_t)b->total * sizeof(double))))
             return fail(rc);
         if (cudaMemset(b->head_count, 0, 2 * sizeof(int)) != cudaSuccess) return fail(MKF_E_CUDA);
+        // run-length pipeline (MKF_RUNS=0 keeps the per-slot record-sharing kernels, for A/B runs and tests)
+        const char* e3 = getenv("MKF_RUNS");
+        if (!(e3 && e3[0] == '0') && b->share_split && N > 64 && N >= 4 * m->K) {
+            if ((rc = dmalloc((void**)&b->runs, (size_t)b->total * sizeof(int2))) ||
+                (rc = dmalloc((void**)&b->nruns, (size_t)T * sizeof(int))) ||
+                (rc = dmalloc((void**)&b->hmeta, (size_t)b->total * sizeof(int4))) ||
+                (rc = dmalloc((void**)&b->nheads, (size_t)T * sizeof(int))) ||
+                (rc = dmalloc((void**)&b->u_keep, (size_t)T * sizeof(double))) ||
+                (rc = dmalloc((void**)&b->seed_keep, (size_t)T * sizeof(uint64_t))))
+                return fail(rc);
+        }
     }
     if ((rc = dmalloc((void**)&b->bounds, (size_t)T * (m->K + 2) * sizeof(int32_t)))) return fail(rc);
     if (m->K <= 256 && (rc = dmalloc((void**)&b->ind_tail, (size_t)b->total))) return fail(rc);
@@ -444,6 +469,10 @@ extern "C" int mkf_batch_shared_records(mkf_batch* b, int64_t* records, int64_t*
     *slots = b->total;
     *records = b->total;
     if (!b->shared) return MKF_OK;
+    {
+        int rc0 = ensure_slots(b);
+        if (rc0) return rc0;
+    }
     unsigned long long* d = nullptr;
     CK(cudaMalloc((void**)&d, 8));
     CK(cudaMemsetAsync(d, 0, 8, b->stream));
@@ -511,6 +540,8 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     if ((rc = launch_bounds_kernel(b, d_u))) return rc;
     b->cur = 0;
     b->shared = false;
+    b->run_mode = false;
+    b->slots_valid = true;
     b->pose_valid = false;
     if (b->m->d == 12)
         k_reset<12><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
@@ -537,10 +568,10 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
                         int u_stride, int normalise, double* d_wsum, int32_t* d_out, uint32_t* d_status,
                         const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb, uint32_t bit_deg,
                         uint32_t* d_unsorted = nullptr, const int32_t* d_rep = nullptr, int32_t* d_src = nullptr,
-                        double* d_w_slot_out = nullptr)
+                        double* d_w_slot_out = nullptr, const double* d_wsum_in = nullptr)
 {
     if (L <= 64 && N <= 64) {
-        if (d_w_slot_out) {
+        if (d_w_slot_out || d_wsum_in) {
             mkf_set_error("internal: per-record weights are not supported by the small-track resampler");
             return MKF_E_INVALID;
         }
@@ -550,7 +581,7 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
             CK(cudaFuncSetAttribute(k_resample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         mkf_launch(k_resample_small, grid_for(nt, 128), 128, smem, stream, d_w, nt, L, N, d_u, u_stride, normalise, d_wsum,
                    d_out, d_status, 1, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src);
-    } else if (L <= 32 && !d_rep && !d_src && !d_w_slot_out) {
+    } else if (L <= 32 && !d_rep && !d_src && !d_w_slot_out && !d_wsum_in) {
         // few weights, many outputs (candidate resample): a warp per track
         mkf_launch(k_resample_warp, grid_for(nt, 4), 128, 0, stream, d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
                    d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted);
@@ -559,7 +590,8 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
         const int span = L > N ? L : N;
 #define MKF_RS_BLOCK(BT)                                                                                             \
     mkf_launch(k_resample_block<BT, 4>, (unsigned)nt, BT, 0, stream, d_w, L, N, d_u, u_stride, normalise, d_wsum, d_out, \
-               d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src, d_w_slot_out)
+               d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_rep, d_src, d_w_slot_out,     \
+               d_wsum_in)
         if (span <= 1024)
             MKF_RS_BLOCK(128);
         else if (span <= 8192)
@@ -573,50 +605,35 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
     return MKF_OK;
 }
 
-// the frame pipeline on device pointers
-static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, const double* d_uind,
-                         const double* d_upost, int u_stride, const uint64_t* d_seeds, int seed_stride, int seed_off)
+// per-slot views of a run-level particle set (mkf_runs.cuh): rep[] from the head table, then the exact per-slot resampler
+// replays the last resample from the same head weights, normaliser, draw and seed -> parent[], src[], w_raw[]
+static int ensure_slots(mkf_batch* b)
+{
+    if (!b->run_mode || b->slots_valid) return MKF_OK;
+    k_expand_rep<<<grid_for(b->T, 4), 128, 0, b->stream>>>(b->hmeta, b->nheads, b->T, b->N, b->rep);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    int rc = run_resample(b->stream, b->T, b->w_rec, b->N, b->N, b->u_keep, 1, 1, nullptr, b->parent, b->status,
+                          b->seed_keep, 1, 0, MKF_ST_POST_FALLBACK, MKF_ST_POST_DEGENERATE, b->unsorted, b->rep, b->src,
+                          b->w_raw, b->wsum);
+    if (rc) return rc;
+    b->slots_valid = true;
+    return MKF_OK;
+}
+
+static void fill_slot_args(mkf_batch* b, SlotArgs& a, const double* d_meas, int meas_layout)
 {
     const mkf_model* m = b->m;
-    int rc;
-    if (u_stride != 1) {
-        mkf_set_error("internal: strided u_ind unsupported");
-        return MKF_E_INVALID;
-    }
-    const bool prof = b->prof_on && (b->prof_tick++ % (uint64_t)b->prof_every) == 0 &&
-                      (size_t)(b->prof_n + 1) * MKF_PROF_EV <= b->prof_ev.size();
-    cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * MKF_PROF_EV] : nullptr;
-    b->pose_valid = false;
-    if (prof) cudaEventRecord(pe[0], b->stream);
-    if ((rc = launch_bounds_kernel(b, d_uind, b->clear_status_next ? 1 : 0))) return rc;
-    b->clear_status_next = false;
-    if (prof) cudaEventRecord(pe[1], b->stream);
-    SlotArgs a{};
     a.st_in = b->st[b->cur];
     a.st_out = b->st[b->cur ^ 1];
     a.parent = b->parent;
     a.src = b->gather_index();
-    // identical children exist only when the slots of a track see one measurement (and never in the literal alias
-    // mode, where duplicates are filtered one after the other)
-    // Worth it when a component owns several slots of a track (N >= 4 K); at N = K = 15 nearly every slot is its own
-    // (parent, component) pair and the bookkeeping costs more than it saves (measured: 3.65 -> 4.15 ms at 1 M x 15).
-    // ... or one of a few candidate columns (MKF_MEAS_CAND): the candidate bin is then part of the key, which only the
-    // two-launch path carries
-    const bool dedup = b->dedup_ok && b->stage == 3 && b->N >= 4 * m->K &&
-                       (meas_layout == MKF_MEAS_SHARED ||
-                        (meas_layout == MKF_MEAS_CAND && b->share_split && b->N > 64));
     a.cand = b->cm_cand;
     a.bins = b->cm_bins;
     a.roi = b->cm_roi;
     a.cand_C = b->cm_C;
     a.hand = b->cm_hand;
     a.neck = m->prm.neck_offset;
-    if (meas_layout == MKF_MEAS_CAND && (!a.cand || !a.bins || !a.roi)) {
-        mkf_set_error("internal: MKF_MEAS_CAND without a candidate source");
-        return MKF_E_INVALID;
-    }
-    a.dedup = dedup ? 1 : 0;
-    a.rep = dedup ? b->rep : nullptr;
     a.hd16 = b->hd16;
     a.head_count = b->head_count ? b->head_count + b->head_flip : nullptr;
     a.w_rec = b->w_rec;
@@ -636,8 +653,163 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     a.unsorted = b->unsorted;
     for (int r = 0; r < MKF_M; r++) a.bh[r] = m->BH[r];
     a.r = m->prm.meas_noise_var;
+}
+
+// CTAs of k_slot_update_heads_direct per SM: 2 are resident; with more, the later ones start as earlier ones finish and
+// the gather / arithmetic / store phases of the resident CTAs drift apart (measured at 4096 x 500: 77.7 us with 2, 74.5
+// with 4, 72.1 with 12-24).  The kernel strides over the list, so any grid is correct.  MKF_HEADS_CTAS_PER_SM overrides.
+static int heads_ctas_per_sm()
+{
+    static const int v = [] {
+        const char* e = getenv("MKF_HEADS_CTAS_PER_SM");
+        const int x = e ? atoi(e) : 12;
+        return (x >= 1 && x <= 64) ? x : 12;
+    }();
+    return v;
+}
+
+// one frame on a run-length particle set (mkf_runs.cuh): frame heads -> slot update of the heads -> repair -> resample
+static int update_device_runs(mkf_batch* b, const double* d_meas, const double* d_uind, const double* d_upost,
+                              const uint64_t* d_seeds, int seed_stride, int seed_off, cudaEvent_t* pe)
+{
+    const mkf_model* m = b->m;
+    if (!b->run_mode) { // entering from a per-slot set (reset, upload, a per-slot frame): its run list
+        mkf_launch(k_runs_from_slots, grid_for(b->T, 4), 128, 0, b->stream, b->gather_index(), b->T, b->N, b->runs,
+                   b->nruns);
+        MKF_LAUNCHED();
+        CK(cudaGetLastError());
+        b->run_mode = true; // (slots_valid keeps its value: the per-slot arrays still describe this set)
+    }
+    if (pe) {
+        cudaEventRecord(pe[0], b->stream);
+        cudaEventRecord(pe[1], b->stream); // no separate indicator kernel: the draw is part of k_frame_heads
+    }
+    FrameArgs f{};
+    f.u_ind = d_uind;
+    f.T = b->T;
+    f.N = b->N;
+    f.K = m->K;
+    f.cw_hi = b->d_cw_hi;
+    f.cw_lo = b->d_cw_lo;
+    f.wprior = b->d_wprior;
+    f.wmax = m->prior_wmax;
+    f.bounds = b->bounds;
+    f.status = b->status;
+    f.clear_status = b->clear_status_next ? 1 : 0;
+    f.ind_tail = b->ind_tail;
+    f.runs = b->runs;
+    f.nruns = b->nruns;
+    f.hmeta = b->hmeta;
+    f.nheads = b->nheads;
+    f.hd16 = b->hd16;
+    f.head_count = b->head_count + b->head_flip;
+    b->clear_status_next = false;
+    mkf_launch(k_frame_heads, grid_for(b->T, 4), 128, 0, b->stream, f);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if (pe) cudaEventRecord(pe[2], b->stream);
+    SlotArgs a{};
+    fill_slot_args(b, a, d_meas, MKF_MEAS_SHARED);
+    a.dedup = 1;
+    a.split = 1;
+    a.rep = nullptr;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
-    bool use_split = false;
+    {
+        static std::atomic<uint64_t> seen{0};
+        if (first_on_this_device(seen)) {
+            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        }
+    }
+    const unsigned hgrid = (unsigned)(heads_ctas_per_sm() * sm_count(b->device));
+    if (m->d == 12) {
+        mkf_launch(k_slot_update_heads_direct<12>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
+        MKF_LAUNCHED();
+        if (pe) cudaEventRecord(pe[3], b->stream);
+        mkf_launch(k_runs_repair<12>, grid_for(b->T, 128), 128, 0, b->stream, a, (const int4*)b->hmeta, (const int*)b->nheads);
+    } else {
+        mkf_launch(k_slot_update_heads_direct<10>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
+        MKF_LAUNCHED();
+        if (pe) cudaEventRecord(pe[3], b->stream);
+        mkf_launch(k_runs_repair<10>, grid_for(b->T, 128), 128, 0, b->stream, a, (const int4*)b->hmeta, (const int*)b->nheads);
+    }
+    b->head_flip ^= 1;
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if (pe) cudaEventRecord(pe[4], b->stream);
+    b->cur ^= 1;
+    ResampleRunsArgs ra{};
+    ra.T = b->T;
+    ra.N = b->N;
+    ra.hmeta = b->hmeta;
+    ra.nheads = b->nheads;
+    ra.w_rec = b->w_rec;
+    ra.u = d_upost;
+    ra.seeds = d_seeds;
+    ra.seed_stride = seed_stride;
+    ra.seed_off = seed_off;
+    ra.wsum_out = b->wsum;
+    ra.status = b->status;
+    ra.runs = b->runs;
+    ra.nruns = b->nruns;
+    ra.u_keep = b->u_keep;
+    ra.seed_keep = b->seed_keep;
+    mkf_launch(k_resample_runs, grid_for(b->T, 4), 128, 0, b->stream, ra);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if (pe) cudaEventRecord(pe[5], b->stream);
+    b->shared = true;
+    b->slots_valid = false;
+    return MKF_OK;
+}
+
+// the frame pipeline on device pointers
+static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, const double* d_uind,
+                         const double* d_upost, int u_stride, const uint64_t* d_seeds, int seed_stride, int seed_off)
+{
+    const mkf_model* m = b->m;
+    int rc;
+    if (u_stride != 1) {
+        mkf_set_error("internal: strided u_ind unsupported");
+        return MKF_E_INVALID;
+    }
+    const bool prof = b->prof_on && (b->prof_tick++ % (uint64_t)b->prof_every) == 0 &&
+                      (size_t)(b->prof_n + 1) * MKF_PROF_EV <= b->prof_ev.size();
+    cudaEvent_t* pe = prof ? &b->prof_ev[(size_t)b->prof_n * MKF_PROF_EV] : nullptr;
+    b->pose_valid = false;
+    // identical children exist only when the slots of a track see one measurement (and never in the literal alias
+    // mode, where duplicates are filtered one after the other)
+    // Worth it when a component owns several slots of a track (N >= 4 K); at N = K = 15 nearly every slot is its own
+    // (parent, component) pair and the bookkeeping costs more than it saves (measured: 3.65 -> 4.15 ms at 1 M x 15).
+    // ... or one of a few candidate columns (MKF_MEAS_CAND): the candidate bin is then part of the key, which only the
+    // two-launch path carries
+    const bool dedup = b->dedup_ok && b->stage == 3 && b->N >= 4 * m->K &&
+                       (meas_layout == MKF_MEAS_SHARED ||
+                        (meas_layout == MKF_MEAS_CAND && b->share_split && b->N > 64));
+    // (tracks of <= 64 slots go to k_resample_small, which reads per-slot weights)
+    const bool use_split = dedup && b->share_split && b->N > 64;
+    if (use_split && meas_layout == MKF_MEAS_SHARED && b->runs) {
+        rc = update_device_runs(b, d_meas, d_uind, d_upost, d_seeds, seed_stride, seed_off, pe);
+        if (prof && rc == MKF_OK) b->prof_n++;
+        return rc;
+    }
+    if (b->run_mode) { // leaving the run-level representation: this frame reads per-slot record indices
+        if ((rc = ensure_slots(b))) return rc;
+        b->run_mode = false;
+    }
+    if (prof) cudaEventRecord(pe[0], b->stream);
+    if ((rc = launch_bounds_kernel(b, d_uind, b->clear_status_next ? 1 : 0))) return rc;
+    b->clear_status_next = false;
+    if (prof) cudaEventRecord(pe[1], b->stream);
+    SlotArgs a{};
+    fill_slot_args(b, a, d_meas, meas_layout);
+    if (meas_layout == MKF_MEAS_CAND && (!a.cand || !a.bins || !a.roi)) {
+        mkf_set_error("internal: MKF_MEAS_CAND without a candidate source");
+        return MKF_E_INVALID;
+    }
+    a.dedup = dedup ? 1 : 0;
+    a.rep = dedup ? b->rep : nullptr;
+    const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
     {
         static std::atomic<uint64_t> seen{0};
         if (smem > 48 * 1024 && first_on_this_device(seen)) {
@@ -656,17 +828,6 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             const int v = e ? atoi(e) : 8;
             return (v == 4 || v == 8 || v == 16) ? v : 8;
         }();
-        // CTAs of k_slot_update_heads_direct per SM: 2 are resident; with more, the later ones start as earlier ones
-        // finish and the gather / arithmetic / store phases of the resident CTAs drift apart (measured at 4096 x 500:
-        // 77.7 us with 2, 74.5 with 4, 72.1 with 12-24).  The kernel strides over the list, so any grid is correct.
-        // MKF_HEADS_CTAS_PER_SM overrides for experiments.
-        static const int heads_ctas_per_sm = [] {
-            const char* e = getenv("MKF_HEADS_CTAS_PER_SM");
-            const int v = e ? atoi(e) : 12;
-            return (v >= 1 && v <= 64) ? v : 12;
-        }();
-        // (tracks of <= 64 slots go to k_resample_small, which reads per-slot weights)
-        use_split = dedup && b->share_split && b->N > 64;
         a.split = use_split ? 1 : 0;
         if (prof && !use_split) cudaEventRecord(pe[2], b->stream); // no k_share_keys in this frame: an empty interval
         const size_t smem_shared = smem + (size_t)128 * share_g * (8 + 4 * 4 + 1);
@@ -697,7 +858,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
                 mkf_launch(k_share_keys<false>, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);           \
             MKF_LAUNCHED();                                                            \
             if (prof) cudaEventRecord(pe[2], b->stream);                               \
-            mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(heads_ctas_per_sm * sm_count(b->device)), 128, smem, b->stream, a,   \
+            mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(heads_ctas_per_sm() * sm_count(b->device)), 128, smem, b->stream, a,   \
                        b->head_count + (b->head_flip ^ 1));                            \
             b->head_flip ^= 1;                                                         \
         } else if (dedup && share_g == 4)                                                \
@@ -862,6 +1023,11 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
     const double2* st = b->st[b->cur];
     double* d_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
     const size_t coef_bytes = (size_t)(m->D + DD) * DD * sizeof(double);
+    if (b->run_mode) { // the current set is a run list: sum of multiplicity x mean
+        mkf_launch(k_estimate_runs<DD>, grid_for(b->T, 4), 128, coef_bytes, b->stream, st, (const int2*)b->runs,
+                   (const int*)b->nruns, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose, d_pose2);
+        return;
+    }
     // tracks per CTA = TRIPS * 128 / GROUP: 8 trips amortise staging the reconstruction matrices once there are
     // enough tracks to fill the GPU several times over; small batches keep one trip so that they still spread out
 #define MKF_EST_SMALL(G, TR)                                                                                  \
@@ -947,6 +1113,10 @@ extern "C" int mkf_batch_download(mkf_batch* b, double* x, double* P, double* w_
     const mkf_model* m = b->m;
     const int d = m->d;
     const size_t tot = (size_t)b->total;
+    if (x || P || w_raw || w_norm || parents) { // a run-level particle set: replay the last resample per slot first
+        int rc0 = ensure_slots(b);
+        if (rc0) return rc0;
+    }
     DevBuf sx, sp, sw, si; // temporaries for host-bound outputs (freed on return)
     OutPtr<double> ox, op, own;
     OutPtr<int32_t> oi;
@@ -1019,6 +1189,8 @@ extern "C" int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, 
     if ((rc = in_ptr(b, P, (size_t)b->total * d * d, mem, b->in_p, &dP))) return rc;
     b->cur = 0;
     b->shared = false;
+    b->run_mode = false;
+    b->slots_valid = true;
     b->pose_valid = false;
     CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if (d == 12)

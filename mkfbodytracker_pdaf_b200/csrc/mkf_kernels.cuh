@@ -975,18 +975,17 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
 // against the double-double prefix sum of the prior weights; if any lane is ambiguous (or the thresholds
 // run past the total prior mass) lane 0 replays the literal loop.  bounds[t] = { e_0..e_{K-1}, wrap_from, wrap_k }
 // -----------------------------------------------------------------------------------------
+// (a device function so that k_frame_heads, whose warps are such groups, runs the same code; every lane of the calling
+// warp must enter it)
 template <int GROUP>
-__global__ void k_indicator_bounds(const double* __restrict__ u, long long T, int N, int K,
-                                   const double* __restrict__ cw_hi, const double* __restrict__ cw_lo,
-                                   const double* __restrict__ wprior, double wmax, int32_t* __restrict__ bounds,
-                                   uint32_t* __restrict__ status, int clear_status, uint8_t* __restrict__ ind_tail)
+__device__ __forceinline__ void mkf_indicator_bounds_group(const long long t, const int k, const bool live,
+                                                           const double* __restrict__ u, int N, int K,
+                                                           const double* __restrict__ cw_hi,
+                                                           const double* __restrict__ cw_lo,
+                                                           const double* __restrict__ wprior, double wmax,
+                                                           int32_t* __restrict__ bounds, uint32_t* __restrict__ status,
+                                                           int clear_status, uint8_t* __restrict__ ind_tail)
 {
-    mkf_pdl_launch_dependents();
-    mkf_pdl_wait();
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long t = gid / GROUP;
-    const int k = (int)(gid % GROUP);
-    const bool live = t < T;
     // first kernel of a frame update: the track's status word starts from zero (no memset node in front of the
     // chain); the only writer of status in this kernel is this same thread, below
     if (clear_status && live && k == 0) status[t] = 0u;
@@ -1071,6 +1070,20 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
     atomicOr(status + t, st);
 }
 
+template <int GROUP>
+__global__ void k_indicator_bounds(const double* __restrict__ u, long long T, int N, int K,
+                                   const double* __restrict__ cw_hi, const double* __restrict__ cw_lo,
+                                   const double* __restrict__ wprior, double wmax, int32_t* __restrict__ bounds,
+                                   uint32_t* __restrict__ status, int clear_status, uint8_t* __restrict__ ind_tail)
+{
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = gid / GROUP;
+    mkf_indicator_bounds_group<GROUP>(t, (int)(gid % GROUP), t < T, u, N, K, cw_hi, cw_lo, wprior, wmax, bounds, status,
+                                      clear_status, ind_tail);
+}
+
 // the prefix-sum / head-marker pass of k_resample_block carried in double-double throughout; kept out of line so that
 // its registers do not weigh on the common path.  Returns this thread's ambiguity flag.
 template <int BT, int ITEMS>
@@ -1138,15 +1151,17 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
                                                         int seed_off, uint32_t* __restrict__ unsorted,
                                                         const int32_t* __restrict__ rep_all,
                                                         int32_t* __restrict__ src_all,
-                                                        double* __restrict__ w_slot_out)
+                                                        double* __restrict__ w_slot_out,
+                                                        const double* __restrict__ wsum_in)
 {
+    // wsum_in: the normaliser is given (the per-slot replay of a run-level resample, mkf_runs.cuh) instead of summed here
     // rep_all / src_all (both or neither): besides the parent SLOT of every output, also write the RECORD that holds
     // that slot's state, src = rep[parent] (k_slot_update with dedup stores identical children once).
     // w_slot_out (with rep_all): w_all holds one weight per RECORD (k_slot_update_heads_direct), slot i's weight is
     // w[rep[i]]; pass 1 also writes the per-slot weights out (mkf_batch_download reads them)
     constexpr int CH = 512;
     __shared__ int sc_i[BT / 32];
-    __shared__ double sc_d[BT / 32], sc_d2[BT / 32], sc_d3[BT / 32];
+    __shared__ double sc_d[BT / 32], sc_d2[BT / 32], sc_d3[BT / 32], sc_d4[BT / 32];
     __shared__ double chunk[CH]; // weights staged for the literal loop (rare)
     __shared__ int sh_flag;
     mkf_pdl_launch_dependents();
@@ -1165,9 +1180,12 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
     // same value, so both paths see identical normalised weights.
     // A track that fits one tile (L <= BT * ITEMS) is read once: each thread keeps its ITEMS consecutive weights for
     // pass 2.
+    // The sum is accumulated in double-double and rounded once, so that its value does not depend on how the slots
+    // are spread over threads -- k_resample_runs (sum over runs of multiplicity x weight) arrives at the same double.
     const bool single = L <= BT * ITEMS;
     double xs[ITEMS];
-    double acc = 0.0, mx = 0.0, sq = 0.0;
+    dd accd = dd_make(0.0);
+    double mx = 0.0, sq = 0.0;
     if (single) {
 #pragma unroll
         for (int q = 0; q < ITEMS; q++) {
@@ -1180,7 +1198,7 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
                 } else {
                     x = w[i];
                 }
-                acc += x;
+                accd = dd_add_d(accd, x);
                 sq = fma(x, x, sq);
                 if (x > mx) mx = x;
             }
@@ -1195,34 +1213,42 @@ __global__ void __launch_bounds__(BT, 1024 / BT) k_resample_block(const double* 
             } else {
                 x = w[i];
             }
-            acc += x;
+            accd = dd_add_d(accd, x);
             sq = fma(x, x, sq);
             if (x > mx) mx = x;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        dd other;
+        other.hi = __shfl_xor_sync(0xffffffffu, accd.hi, o);
+        other.lo = __shfl_xor_sync(0xffffffffu, accd.lo, o);
+        accd = dd_add(accd, other);
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     if (lane == 0) {
-        sc_d[wid] = acc;
+        sc_d[wid] = accd.hi;
+        sc_d4[wid] = accd.lo;
         sc_d2[wid] = mx;
         sc_d3[wid] = sq;
     }
     if (tid == 0) sh_flag = 0;
     __syncthreads();
-    acc = 0.0;
+    accd = dd_make(0.0);
     mx = 0.0;
     sq = 0.0;
 #pragma unroll
     for (int q = 0; q < BT / 32; q++) {
-        acc += sc_d[q];
+        dd part;
+        part.hi = sc_d[q];
+        part.lo = sc_d4[q];
+        accd = dd_add(accd, part);
         mx = fmax(mx, sc_d2[q]);
         sq += sc_d3[q];
     }
     __syncthreads();
+    const double acc = wsum_in ? wsum_in[t] : accd.hi;
     const double wsum = normalise ? acc : 1.0;
     if (tid == 0 && wsum_out) wsum_out[t] = acc;
     const double wmax_n = normalise ? __ddiv_rn(mx, wsum) : mx;

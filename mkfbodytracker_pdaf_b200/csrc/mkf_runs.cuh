@@ -1,0 +1,493 @@
+// mkf_runs.cuh -- the frame pipeline on RUN-LENGTH particle sets (included by mkf_api.cu).
+//
+// With one measurement column per track (MKF_MEAS_SHARED) and independent slots (MKF_ALIAS_INDEPENDENT), children that
+// drew the same parent record and the same component are bit-identical Gaussians (mkf_kernels.cuh, record sharing), and
+// because systematic resampling returns sorted parents they are consecutive slots.  The particle set of a track is
+// therefore a short list of RUNS (record, multiplicity) -- ~50 for 500 slots in steady state -- and every step of
+// ParticleFilter::update (src/pf2DRao.cpp:125-158) has a run-level form that never touches a per-slot array:
+//
+//   k_frame_heads     K -> N indicator draw (src/pf2DRao.cpp:128) in closed form -> K-1 cut positions; the frame's
+//                     distinct Gaussians ("heads") are the runs cut at those positions.  One warp per track writes the
+//                     head table {source record, component, multiplicity, first slot} and appends the heads to the
+//                     batch-wide work list of k_slot_update_heads_direct (one atomicAdd per track).
+//   k_slot_update_heads_direct   (mkf_kernels.cuh) predict + likelihood + update of every head, weight per head.
+//   k_runs_repair     literal cv::Cholesky-failure semantics for flagged tracks (rare).
+//   k_resample_runs   src/pf2DRao.cpp:139-156 on runs: wsum = sum m_h w_h, normalised weights, prefix sums at run ends in
+//                     double-double, children per head from the closed-form count e(C) -> the next frame's run list.
+//                     A run of m equal weights is one super-parent of weight m * w: which of its slots a threshold
+//                     falls on does not change the child's Gaussian, so only the decisions AT run ends matter, and
+//                     those are taken exactly as k_resample_block takes them (same ambiguity band, literal loop of
+//                     src/pf2DRao.cpp:195-207 over the slots when undecidable, cv::RNG branch when max weight is 0).
+//   k_estimate_runs   getEstimator (src/pf2DRao.cpp:23-31) = sum_runs multiplicity * x' / N, + PCA reconstruction.
+//
+// Per-slot views (parents, per-slot weights, states: mkf_batch_download; a following per-slot-measurement or
+// association frame) are materialised on demand: k_expand_rep turns the head table into rep[] and the existing exact
+// per-slot resampler k_resample_block replays the SAME resample (same head weights, the stored wsum, u and seed), so
+// what it writes is what the run-level step decided.
+#ifndef MKF_RUNS_CUH
+#define MKF_RUNS_CUH
+
+// one warp per track: the run list of a per-slot particle set (gi = record of every slot, sorted or not)
+__global__ void __launch_bounds__(128) k_runs_from_slots(const int32_t* __restrict__ gi, long long T, int N,
+                                                         int2* __restrict__ runs, int* __restrict__ nruns)
+{
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int32_t* __restrict__ g = gi + t * N;
+    int2* __restrict__ rt = runs + t * N;
+    int nr = 0, last = -2;
+    for (int base = 0; base < N; base += 32) {
+        const int j = base + lane;
+        const int v = j < N ? g[j] : -1;
+        int prev = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) prev = last;
+        const bool start = j < N && v != prev;
+        const unsigned m = __ballot_sync(0xffffffffu, start);
+        if (start) rt[nr + __popc(m & ((1u << lane) - 1u))] = make_int2(v, j); // .y = first slot for now
+        nr += __popc(m);
+        last = __shfl_sync(0xffffffffu, v, 31);
+    }
+    __syncwarp();
+    for (int r0 = 0; r0 < nr; r0 += 32) { // first slots -> multiplicities
+        const int r = r0 + lane;
+        int a = 0, b = 0;
+        if (r < nr) {
+            a = rt[r].y;
+            b = r + 1 < nr ? rt[r + 1].y : N;
+        }
+        __syncwarp();
+        if (r < nr) rt[r].y = b - a;
+        __syncwarp();
+    }
+    if (lane == 0) nruns[t] = nr;
+}
+
+struct FrameArgs {
+    const double* __restrict__ u_ind;
+    long long T;
+    int N, K;
+    const double* __restrict__ cw_hi;
+    const double* __restrict__ cw_lo;
+    const double* __restrict__ wprior;
+    double wmax;
+    int32_t* __restrict__ bounds;
+    uint32_t* __restrict__ status;
+    int clear_status;
+    uint8_t* __restrict__ ind_tail;
+    const int2* __restrict__ runs;
+    const int* __restrict__ nruns;
+    int4* __restrict__ hmeta; // T x N: head i of track t = {source record, component, multiplicity, first slot}
+    int* __restrict__ nheads;
+    int4* __restrict__ hd16;
+    int* __restrict__ head_count;
+};
+
+__global__ void __launch_bounds__(128) k_frame_heads(const FrameArgs f)
+{
+    __shared__ int cuts_s[4][64];
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * 4 + wid;
+    if (t >= f.T) return;
+    const int N = f.N, K = f.K;
+    // the K -> N indicator draw: the lanes of this warp are the group of k_indicator_bounds<32>
+    mkf_indicator_bounds_group<32>(t, lane, true, f.u_ind, N, K, f.cw_hi, f.cw_lo, f.wprior, f.wmax, f.bounds, f.status,
+                                   f.clear_status, f.ind_tail);
+    __syncwarp();
+    const int32_t* bt = f.bounds + t * (K + 2);
+    int* cuts = cuts_s[wid];
+    const int nc = K - 1; // cut q = first slot whose component exceeds q
+    for (int q = lane; q < nc; q += 32) cuts[q] = bt[q];
+    const int wrap_from = bt[K];
+    __syncwarp();
+    const int2* __restrict__ rt = f.runs + t * N;
+    int4* __restrict__ hm = f.hmeta + t * N;
+    const int nr = f.nruns[t];
+    int nh = 0;
+    if (wrap_from >= N) {
+        int pos_carry = 0;
+        for (int r0 = 0; r0 < nr; r0 += 32) {
+            const int r = r0 + lane;
+            const int2 rn = r < nr ? rt[r] : make_int2(0, 0);
+            int inc = rn.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
+            int k0 = 0, np = 0;
+            if (r < nr) {
+                while (k0 < nc && cuts[k0] <= a) k0++; // component of slot a
+                int k = k0;
+                for (;;) {
+                    np++;
+                    const int c = k < nc ? cuts[k] : N;
+                    if (c >= b) break;
+                    while (k < nc && cuts[k] <= c) k++;
+                }
+            }
+            int pinc = np;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, pinc, o);
+                if (lane >= o) pinc += n;
+            }
+            if (r < nr) {
+                int h = nh + pinc - np, k = k0, pos = a;
+                for (;;) {
+                    const int c = k < nc ? cuts[k] : N;
+                    const int end = c < b ? c : b;
+                    hm[h++] = make_int4(rn.x, k, end - pos, pos);
+                    if (c >= b) break;
+                    pos = c;
+                    while (k < nc && cuts[k] <= c) k++;
+                }
+            }
+            nh += __shfl_sync(0xffffffffu, pinc, 31);
+            pos_carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    } else {
+        // the draw wrapped past the last component (prior mass short of the thresholds): components are read per slot
+        if (lane == 0) {
+            const uint8_t* tail = f.ind_tail ? f.ind_tail + t * N : nullptr;
+            int pos = 0;
+            for (int r = 0; r < nr; r++) {
+                const int2 rn = rt[r];
+                int j = pos;
+                const int b = pos + rn.y;
+                while (j < b) {
+                    const int k = mkf_component_of(bt, K, j, tail);
+                    int j2 = j + 1;
+                    while (j2 < b && mkf_component_of(bt, K, j2, tail) == k) j2++;
+                    hm[nh++] = make_int4(rn.x, k, j2 - j, j);
+                    j = j2;
+                }
+                pos = b;
+            }
+        }
+        nh = __shfl_sync(0xffffffffu, nh, 0);
+    }
+    __syncwarp();
+    int lb = 0;
+    if (lane == 0) {
+        f.nheads[t] = nh;
+        lb = atomicAdd(f.head_count, nh); // this track's stretch of the batch-wide work list (order immaterial)
+    }
+    lb = __shfl_sync(0xffffffffu, lb, 0);
+    const int tN = (int)(t * N);
+    for (int i = lane; i < nh; i += 32) {
+        const int4 m = hm[i];
+        f.hd16[lb + i] = make_int4(tN + m.x, tN + i, (int)t, m.y);
+    }
+}
+
+// literal cv::Cholesky-failure semantics for flagged tracks, head by head (see k_slot_update_repair)
+template <int D>
+__global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const int4* __restrict__ hmeta,
+                                                        const int* __restrict__ nheads)
+{
+    using L = SlotLay<D>;
+    __shared__ uint32_t flags[128];
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const long long T = a.total / a.N;
+    const long long base = (long long)blockIdx.x * 128;
+    {
+        const long long t = base + threadIdx.x;
+        uint32_t fl = 0;
+        if (t < T) fl = (a.status[t] & MKF_ST_CHOL_FAIL) ? 1u : 0u;
+        flags[threadIdx.x] = fl;
+        if (!__syncthreads_or((int)fl)) return;
+    }
+    for (int q = 0; q < 128; q++) {
+        if (!flags[q]) continue;
+        const long long t = base + q;
+        const int nh = nheads[t];
+        for (int i = threadIdx.x; i < nh; i += 128) {
+            const int4 m = hmeta[t * a.N + i];
+            const long long sp = t * a.N + m.x, so = t * a.N + i;
+            const double2* src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+            double v[L::NE];
+            for (int p = 0; p < L::NP; p++) {
+                const double2 qq = src[L::po(p)];
+                v[2 * p] = qq.x;
+                if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
+            }
+            double zc[MKF_M], w;
+            mkf_load_meas(a, t, 0, zc);
+            slot_math<D, true>(v, a.comp_const + (long long)(m.y & 0xff) * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+            double2* dst = a.st_out + (so >> 5) * (long long)L::TILE2 + (so & 31) * L::H;
+            for (int p = 0; p < L::NP; p++) {
+                double2 qq;
+                qq.x = v[2 * p];
+                qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                dst[L::po(p)] = qq;
+            }
+            a.w_rec[so] = w;
+        }
+    }
+}
+
+__device__ __forceinline__ dd dd_shfl_xor(dd v, int o)
+{
+    dd r;
+    r.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
+    r.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
+    return r;
+}
+__device__ __forceinline__ dd dd_shfl_up(dd v, int o)
+{
+    dd r;
+    r.hi = __shfl_up_sync(0xffffffffu, v.hi, o);
+    r.lo = __shfl_up_sync(0xffffffffu, v.lo, o);
+    return r;
+}
+// m * w exactly (m an integer count) as a double-double
+__device__ __forceinline__ dd dd_mul_exact(double m, double w)
+{
+    const double p = __dmul_rn(m, w);
+    const double e = __fma_rn(m, w, -p);
+    return dd_fast_two_sum(p, e);
+}
+
+struct ResampleRunsArgs {
+    long long T;
+    int N;
+    const int4* __restrict__ hmeta;
+    const int* __restrict__ nheads;
+    const double* __restrict__ w_rec; // weight of head i of track t at t*N + i
+    const double* __restrict__ u;
+    const uint64_t* __restrict__ seeds;
+    int seed_stride, seed_off;
+    double* __restrict__ wsum_out;
+    uint32_t* __restrict__ status;
+    int2* __restrict__ runs; // out: the new particle set, {head index = record, children}
+    int* __restrict__ nruns;
+    double* __restrict__ u_keep;   // copies of the draw / seed of this resample, for the on-demand per-slot replay
+    uint64_t* __restrict__ seed_keep;
+};
+
+__global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
+{
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= a.T) return;
+    const int N = a.N;
+    const int nh = a.nheads[t];
+    const int4* __restrict__ hm = a.hmeta + t * N;
+    const double* __restrict__ wr = a.w_rec + t * N;
+    int2* __restrict__ rt = a.runs + t * N;
+
+    // pass 1: wsum = sum over slots (src/pf2DRao.cpp:139) = sum_h m_h w_h, accumulated in double-double and rounded once;
+    // NaN-ignoring max (src/pf2DRao.cpp:161-172)
+    dd acc = dd_make(0.0);
+    double mx = 0.0, sq = 0.0;
+    for (int i = lane; i < nh; i += 32) {
+        const double w = wr[i], md = (double)hm[i].z;
+        acc = dd_add(acc, dd_mul_exact(md, w));
+        if (w > mx) mx = w;
+        sq = fma(__dmul_rn(md, w), w, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc = dd_add(acc, dd_shfl_xor(acc, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const double wsum = acc.hi;
+    const double uu = a.u[t];
+    const uint64_t seed = a.seeds ? a.seeds[t * a.seed_stride + a.seed_off] : 1ull;
+    if (lane == 0) {
+        a.wsum_out[t] = wsum;
+        a.u_keep[t] = uu;
+        a.seed_keep[t] = seed;
+    }
+    const double wmax_n = __ddiv_rn(mx, wsum);
+    if (!(wmax_n > 0.0)) { // max weight 0 / NaN -> N random parents from cv::RNG (src/pf2DRao.cpp:184-192)
+        if (lane == 0) {
+            atomicOr(a.status + t, MKF_ST_POST_DEGENERATE);
+            mkf_cvrng rng(seed);
+            (void)rng.uniform_int(0, N); // `int idx = rng.uniform(0, L);` drawn and discarded
+            int nr = 0, cur = -1, cnt = 0;
+            for (int i = 0; i < N; i++) {
+                const int idx = rng.uniform_int(0, N); // a SLOT; its record is the head whose range holds it
+                int lo = 0, hi = nh - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (hm[mid].w <= idx)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                if (lo == cur) {
+                    cnt++;
+                } else {
+                    if (cnt) rt[nr++] = make_int2(cur, cnt);
+                    cur = lo;
+                    cnt = 1;
+                }
+            }
+            if (cnt) rt[nr++] = make_int2(cur, cnt);
+            a.nruns[t] = nr;
+        }
+        return;
+    }
+    const double step = __ddiv_rn(1.0, (double)N);
+    const double beta0 = __dmul_rn(uu, step);
+    // the band in which the literal loop's accumulated rounding could change a decision (mkf_resample_tol*), plus the
+    // rounding of mkf_count_le's remainder and of the double-double prefix sums (as k_resample_block's second opinion)
+    const double s2 = __ddiv_rn(sq, __dmul_rn(wsum, wsum)) * (1.0 + 1e-9);
+    const double tol_loop = fmin(mkf_resample_tol(N, N, wmax_n, step), mkf_resample_tol_s2(N, N, s2, 1.0));
+    const double tol2 = tol_loop + 8.0 * 1.1102230246251565e-16 * step + 8.0e-28 * 2.0;
+
+    // pass 2: prefix sums at run ends -> children per head -> the new run list
+    dd carry = dd_make(0.0);
+    int e_carry = 0, nr = 0;
+    bool amb = false;
+    for (int i0 = 0; i0 < nh; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < nh;
+        const double wn = valid ? __ddiv_rn(wr[i], wsum) : 0.0; // the normalised weight of each of the head's slots
+        dd inc = dd_mul_exact(valid ? (double)hm[i].z : 0.0, wn);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const dd n = dd_shfl_up(inc, o);
+            if (lane >= o) inc = dd_add(n, inc);
+        }
+        const dd C = dd_add(carry, inc);
+        int eh = N;
+        if (valid) {
+            eh = mkf_count_le(C, beta0, step, N, tol2, amb);
+            if (i == nh - 1 && eh < N) amb = true; // the literal loop would wrap past the last slot
+        }
+        int eprev = __shfl_up_sync(0xffffffffu, eh, 1);
+        if (lane == 0) eprev = e_carry;
+        const int c = valid ? eh - eprev : 0;
+        const unsigned msk = __ballot_sync(0xffffffffu, c > 0);
+        if (c > 0) rt[nr + __popc(msk & ((1u << lane) - 1u))] = make_int2(i, c);
+        nr += __popc(msk);
+        const int lastl = (nh - i0 >= 32) ? 31 : (nh - i0 - 1);
+        e_carry = __shfl_sync(0xffffffffu, eh, lastl);
+        carry.hi = __shfl_sync(0xffffffffu, C.hi, 31); // lane 31's inclusive prefix (lanes beyond nh add zero)
+        carry.lo = __shfl_sync(0xffffffffu, C.lo, 31);
+    }
+    if (__any_sync(0xffffffffu, amb)) {
+        // undecidable in closed form: the reference's loop itself (src/pf2DRao.cpp:195-207), slot by slot
+        if (lane == 0) {
+            atomicOr(a.status + t, MKF_ST_POST_FALLBACK);
+            int h = 0, left = hm[0].z;
+            double wi = __ddiv_rn(wr[0], wsum);
+            double beta = beta0;
+            int cur = -1, cnt = 0;
+            nr = 0;
+            for (int i = 0; i < N; i++) {
+                while (beta > wi) {
+                    beta = __dsub_rn(beta, wi);
+                    if (--left == 0) { // idx = (idx + 1) % L moved on to the next head's first slot
+                        h = (h + 1 == nh) ? 0 : h + 1;
+                        left = hm[h].z;
+                        wi = __ddiv_rn(wr[h], wsum);
+                    }
+                }
+                beta = __dadd_rn(beta, step);
+                if (h == cur) {
+                    cnt++;
+                } else {
+                    if (cnt) rt[nr++] = make_int2(cur, cnt);
+                    cur = h;
+                    cnt = 1;
+                }
+            }
+            if (cnt) rt[nr++] = make_int2(cur, cnt);
+        }
+        nr = __shfl_sync(0xffffffffu, nr, 0);
+    }
+    if (lane == 0) a.nruns[t] = nr;
+}
+
+// getEstimator + reconstruction from the run list: 4 tracks per CTA, one warp each
+template <int D>
+__global__ void __launch_bounds__(128) k_estimate_runs(const double2* __restrict__ st, const int2* __restrict__ runs,
+                                                       const int* __restrict__ nruns, long long T, int N, int Dpose,
+                                                       const double* __restrict__ recon, const double* __restrict__ pmean,
+                                                       const double* __restrict__ tinv, double* __restrict__ xbar_out,
+                                                       double* __restrict__ pose_out, double* __restrict__ pose_out2)
+{
+    using L = SlotLay<D>;
+    extern __shared__ double coef[]; // [c][r], r < Dpose + D: rows of recon (pose) then rows of tinv (xbar)
+    mkf_pdl_launch_dependents();
+    const int R = Dpose + D;
+    for (int i = threadIdx.x; i < R * D; i += 128) { // model constants: safe before the dependency wait
+        const int r = i / D, c = i - r * D;
+        coef[c * R + r] = r < Dpose ? recon[r * D + c] : tinv[(r - Dpose) * D + c];
+    }
+    mkf_pdl_wait();
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int nr = nruns[t];
+    const int2* __restrict__ rt = runs + t * N;
+    double acc[D];
+#pragma unroll
+    for (int e = 0; e < D; e++) acc[e] = 0.0;
+    for (int r = lane; r < nr; r += 32) {
+        const int2 rn = rt[r];
+        const long long sp = t * N + rn.x;
+        const double2* __restrict__ src = st + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+        const double m = (double)rn.y;
+#pragma unroll
+        for (int p = 0; p < D / 2; p++) {
+            const double2 q = __ldg(src + L::po(p));
+            acc[2 * p] = fma(m, q.x, acc[2 * p]);
+            acc[2 * p + 1] = fma(m, q.y, acc[2 * p + 1]);
+        }
+    }
+    const double inv_n = 1.0 / (double)N;
+#pragma unroll
+    for (int e = 0; e < D; e++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+        acc[e] *= inv_n;
+    }
+    for (int r = lane; r < R; r += 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; c++) s = fma(coef[c * R + r], acc[c], s);
+        if (r < Dpose) {
+            if (pose_out) pose_out[t * Dpose + r] = s + pmean[r];
+            if (pose_out2) pose_out2[t * Dpose + r] = s + pmean[r];
+        } else if (xbar_out) {
+            xbar_out[t * D + (r - Dpose)] = s;
+        }
+    }
+}
+
+// head table -> rep[] (the record of st[cur] that holds every slot of the LAST frame), for the per-slot replay
+__global__ void __launch_bounds__(128) k_expand_rep(const int4* __restrict__ hmeta, const int* __restrict__ nheads,
+                                                    long long T, int N, int32_t* __restrict__ rep)
+{
+    const int lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int nh = nheads[t];
+    for (int i0 = 0; i0 < nh; i0 += 32) {
+        // the lanes of a warp walk the slots of 32 consecutive heads together: a head of m slots costs ceil(m / 32) trips
+        for (int q = 0; q < 32 && i0 + q < nh; q++) {
+            const int4 m = hmeta[t * N + i0 + q];
+            for (int j = lane; j < m.z; j += 32) rep[t * N + m.w + j] = i0 + q;
+        }
+    }
+}
+
+// run list -> src[] (the record of st[cur] that holds every slot of the CURRENT set) when no per-slot replay is
+// possible (entry into run mode without an update: not needed, the per-slot arrays are still valid then)
+
+#endif

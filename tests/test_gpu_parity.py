@@ -636,19 +636,22 @@ def test_record_sharing_is_invisible(left_arm):
     assert rel_err(d2["x"], d["x"]) <= 1e-12 and rel_err(d2["P"], d["P"]) <= 1e-12
 
 
-@pytest.mark.parametrize("T,N", [(7, 333), (3, 1025), (70, 65), (2, 4099), (1, 61)])
+@pytest.mark.parametrize("T,N", [(7, 333), (3, 1025), (70, 65), (2, 4099), (1, 61), (130, 500)])
 def test_record_sharing_variants_agree(left_arm, T, N, monkeypatch):
-    """the three slot-update paths of a shared-measurement frame -- every slot computed (MKF_DEDUP=0), the single-launch
-    record-sharing kernel (MKF_SHARE_SPLIT=0) and the default two-launch one (k_share_keys + k_slot_update_heads_direct,
-    weights per record read by the resampler) -- run the same arithmetic on the same Gaussians: every download agrees
-    bit for bit over free-running frames, on shapes that leave ragged tails (slots not a multiple of 4 / 1024, tracks
-    straddling chunks, a chunk with more than 128 heads, N <= 64 falling back to the per-slot resampler)."""
+    """the slot-update paths of a shared-measurement frame -- every slot computed (MKF_DEDUP=0), the single-launch
+    record-sharing kernel (MKF_SHARE_SPLIT=0), the two-launch per-slot one (MKF_RUNS=0: k_share_keys +
+    k_slot_update_heads_direct, weights per record read by the resampler) and the default run-length pipeline
+    (mkf_runs.cuh: k_frame_heads + k_slot_update_heads_direct + k_resample_runs, per-slot views replayed on demand) --
+    run the same arithmetic on the same Gaussians: every download agrees bit for bit over free-running frames, on shapes
+    that leave ragged tails (slots not a multiple of 4 / 1024, tracks straddling chunks, a chunk with more than 128
+    heads, N <= 64 falling back to the per-slot resampler).  Estimates: bit-identical among the per-slot paths; the
+    run-length path sums multiplicity x mean (one rounding instead of m), so it agrees to 1e-13."""
     seed = 0x5EED0007
     tracks = list(range(T))
     u0 = synth_u_init(seed, tracks)
 
     def make(env):
-        for k in ("MKF_DEDUP", "MKF_SHARE_SPLIT"):
+        for k in ("MKF_DEDUP", "MKF_SHARE_SPLIT", "MKF_RUNS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -656,7 +659,17 @@ def test_record_sharing_variants_agree(left_arm, T, N, monkeypatch):
         b.reset(u0)
         return b
 
-    variants = [make({"MKF_DEDUP": "0"}), make({"MKF_SHARE_SPLIT": "0"}), make({})]
+    variants = [make({"MKF_DEDUP": "0"}), make({"MKF_SHARE_SPLIT": "0"}), make({"MKF_RUNS": "0"}), make({})]
+    keys = ("parents", "indicators", "x", "P", "w_raw", "w_norm", "wsum", "status")
+
+    def check_estimates():
+        e0 = variants[0].estimate()
+        for b in variants[1:3]:
+            e = b.estimate()
+            assert np.array_equal(e0[0], e[0]) and np.array_equal(e0[1], e[1])
+        e = variants[3].estimate()
+        assert rel_err(e[0], e0[0]) <= 1e-13 and rel_err(e[1], e0[1]) <= 1e-13
+
     for fr in range(6):
         m, ui, up = synth_frame(seed, tracks, fr)
         ds = []
@@ -664,15 +677,32 @@ def test_record_sharing_variants_agree(left_arm, T, N, monkeypatch):
             b.update(m, ui, up)
             ds.append(b.download())
         for d in ds[1:]:
-            for key in ("parents", "indicators", "x", "P", "w_raw", "w_norm", "wsum", "status"):
+            for key in keys:
                 assert np.array_equal(ds[0][key], d[key]), (fr, key)
-        if fr >= 2:  # sharing is real on the two sharing variants, absent on the first
+        if fr >= 2:  # sharing is real on the sharing variants, absent on the first
             assert variants[0].shared_records()[0] == T * N
-            assert variants[1].shared_records() == variants[2].shared_records()
+            assert variants[1].shared_records() == variants[2].shared_records() == variants[3].shared_records()
             if N >= 4 * 15:
-                assert variants[2].shared_records()[0] < T * N
-        # estimates read the state through the record indices
-        e0 = variants[0].estimate()
-        for b in variants[1:]:
-            e = b.estimate()
-            assert np.array_equal(e0[0], e[0]) and np.array_equal(e0[1], e[1])
+                assert variants[3].shared_records()[0] < T * N
+        # estimates read the state through the record indices / the run list
+        check_estimates()
+    # frames with nothing read back in between: the run-length path never materialises a per-slot array here
+    for fr in range(6, 14):
+        m, ui, up = synth_frame(seed, tracks, fr)
+        for b in variants:
+            b.update(m, ui, up)
+        check_estimates()
+    ds = [b.download() for b in variants]
+    for d in ds[1:]:
+        for key in keys:
+            assert np.array_equal(ds[0][key], d[key]), ("after 8 unobserved frames", key)
+    # a per-slot-measurement frame on top (the run-length path hands its set over to the per-slot kernels), then back
+    mm = np.repeat(m[:, :, None], N, axis=2) + np.random.default_rng(3).normal(0, 2.0, (T, 6, N))
+    for fr, meas in ((14, mm), (15, None), (16, None)):
+        m, ui, up = synth_frame(seed, tracks, fr)
+        for b in variants:
+            b.update(m if meas is None else meas, ui, up)
+    ds = [b.download() for b in variants]
+    for d in ds[1:]:
+        for key in keys:
+            assert np.array_equal(ds[0][key], d[key]), ("after the per-slot frame", key)
