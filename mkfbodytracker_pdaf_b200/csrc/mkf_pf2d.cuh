@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) k_pf2d_weight(const double* __restrict__ 
 }
 
 __global__ void k_pf2d_resample_predict(const double* __restrict__ old_p, double* __restrict__ new_p,
-                                        const int32_t* __restrict__ parent, const uint32_t* __restrict__ status,
+                                        int32_t* __restrict__ parent, const uint32_t* __restrict__ status,
                                         const double* __restrict__ noise, long long T, int N, int d, const PfRand rnd)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,6 +116,8 @@ __global__ void k_pf2d_resample_predict(const double* __restrict__ old_p, double
         // max weight 0: every particle is re-randomised across the image (src/pf2D.cpp:232-244)
         v = mkf_synth_pf2d_uniform(rnd.seed, (uint64_t)(rnd.track0 + t), rnd.epoch, (int)(s - t * N), c,
                                    rnd.side ? (int)rnd.side[t] : 0, rnd.im_w, rnd.im_h);
+        if (c == d - 1) parent[s] = (int)(s - t * N); // no parent in this branch: reported as the particle itself
+                                                      // (the resampler's cv::RNG draw belongs to pf2DRao, not to pf2D)
     } else {
         const long long sp = t * N + parent[s];
         v = __dadd_rn(0.0, old_p[sp * d + c]); // particles.row(i) = zeros + old_particles.row(idx)
@@ -129,7 +131,7 @@ __global__ void k_pf2d_resample_predict(const double* __restrict__ old_p, double
 template <int D>
 __global__ void __launch_bounds__(256) k_pf2d_resample_predict_v(const double* __restrict__ old_p,
                                                                   double* __restrict__ new_p,
-                                                                  const int32_t* __restrict__ parent,
+                                                                  int32_t* __restrict__ parent,
                                                                   const uint32_t* __restrict__ status,
                                                                   const double* __restrict__ noise, long long T, int N,
                                                                   const PfRand rnd)
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) k_pf2d_resample_predict_v(const double* _
     if (__ldg(status + t) & MKF_ST_POST_DEGENERATE) {
         // max weight 0: every particle is re-randomised across the image (src/pf2D.cpp:232-244)
         const int side = rnd.side ? (int)rnd.side[t] : 0, j = (int)(s - t * N);
+        parent[s] = j; // no parent in this branch: reported as the particle itself
 #pragma unroll
         for (int p = 0; p < D / 2; p++) {
             // "- 0.0": the common tail below adds 0.0 to what it takes for a gathered row (x + 0.0 == x here)

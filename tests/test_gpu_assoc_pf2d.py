@@ -225,12 +225,13 @@ def test_pf2d_constructor_and_degenerate_branch():
         lo, hi = (321, 640) if side[t] else (1, 320)
         assert p0[t][:, 6].min() >= lo and p0[t][:, 6].max() < hi
         assert np.max(np.abs(pb.estimate()[t] - ofs[t].estimate()) / np.abs(ofs[t].estimate())) <= 1e-12
-    # particles drawn across the whole image sit far outside the prior (most filters go degenerate on the first update,
-    # as the reference's would after its constructor); afterwards the filters are put near the components and knocked
-    # out again on two frames
+    # particles drawn across the whole image sit far outside the prior: their weights live in the subnormal range, where
+    # one ulp of libm's / CUDA's double exp decides between "tiny" and "exactly 0" -- not a regime with a parity
+    # contract.  The filters are put near the components, then knocked out on two frames (every likelihood exactly 0)
+    # and re-seeded.
     n_dead = 0
     for frame in range(8):
-        if frame in (1, 5):
+        if frame in (0, 5):
             near = means[rng.integers(0, K, (T, N))] + rng.standard_normal((T, N, d)) * 6
             pb.set_particles(near)
             for t in range(T):
@@ -248,7 +249,7 @@ def test_pf2d_constructor_and_degenerate_branch():
             r = ofs[t].update(meas[t], u[t], noise[t])
             if frame in (3, 6) and t in (1, 2):
                 assert r["status"] == 1
-            if frame in (1, 2, 5):
+            if frame in (0, 1, 2, 5):
                 assert r["status"] == 0
             n_dead += r["status"]
             assert np.array_equal(par[t], r["parents"]), (frame, t)
