@@ -186,6 +186,13 @@ struct mkf_batch {
     int* nheads = nullptr;
     double* u_keep = nullptr;
     uint64_t* seed_keep = nullptr;
+    // the estimate of the current set as k_resample_runs left it: est[slot] = [xbar T x d | pose T x D]; two slots so that
+    // a device->host copy of frame f (MKF_MEM_HOST_ASYNC) may still be in flight while frame f+1 is computed
+    double* est[2] = {nullptr, nullptr};
+    int est_slot = 0;
+    bool est_valid = false;
+    cudaEvent_t est_ready = nullptr, est_done[2] = {nullptr, nullptr};
+    bool est_used[2] = {false, false};
     bool run_mode = false;    // `runs` describes the current particle set
     bool slots_valid = true;  // parent / src / rep / w_raw describe it too (false after a run-level frame until
                               // ensure_slots() replays the resample per slot)
@@ -303,7 +310,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -313,6 +320,9 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
                       &b->as_ui,   &b->as_up};
     for (DevBuf* d : bufs) d->release();
     b->aio.release();
+    if (b->est_ready) cudaEventDestroy(b->est_ready);
+    for (int i = 0; i < 2; i++)
+        if (b->est_done[i]) cudaEventDestroy(b->est_done[i]);
     for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -400,8 +410,16 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
                 (rc = dmalloc((void**)&b->hmeta, (size_t)b->total * sizeof(int4))) ||
                 (rc = dmalloc((void**)&b->nheads, (size_t)T * sizeof(int))) ||
                 (rc = dmalloc((void**)&b->u_keep, (size_t)T * sizeof(double))) ||
-                (rc = dmalloc((void**)&b->seed_keep, (size_t)T * sizeof(uint64_t))))
+                (rc = dmalloc((void**)&b->seed_keep, (size_t)T * sizeof(uint64_t))) ||
+                (rc = dmalloc((void**)&b->est[0], (size_t)T * (m->d + m->D) * sizeof(double))) ||
+                (rc = dmalloc((void**)&b->est[1], (size_t)T * (m->d + m->D) * sizeof(double))))
                 return fail(rc);
+            if (cudaEventCreateWithFlags(&b->est_ready, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b->est_done[0], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b->est_done[1], cudaEventDisableTiming) != cudaSuccess) {
+                mkf_set_error("cudaEventCreate failed");
+                return fail(MKF_E_CUDA);
+            }
         }
     }
     if ((rc = dmalloc((void**)&b->bounds, (size_t)T * (m->K + 2) * sizeof(int32_t)))) return fail(rc);
@@ -502,6 +520,7 @@ extern "C" int mkf_batch_join(mkf_batch* b)
     for (int i = 0; i < 2; i++) {
         if (io.in_used[i]) CK(cudaStreamWaitEvent(b->stream, io.in_done[i], 0));
         if (io.out_used[i]) CK(cudaStreamWaitEvent(b->stream, io.out_done[i], 0));
+        if (b->est_used[i]) CK(cudaStreamWaitEvent(b->stream, b->est_done[i], 0));
     }
     return MKF_OK;
 }
@@ -542,6 +561,7 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     b->shared = false;
     b->run_mode = false;
     b->slots_valid = true;
+    b->est_valid = false;
     b->pose_valid = false;
     if (b->m->d == 12)
         k_reset<12><<<grid_for(b->total, 256), 256, 0, b->stream>>>(b->st[0], b->parent, b->bounds, b->d_init,
@@ -754,12 +774,28 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, const double* 
     ra.nruns = b->nruns;
     ra.u_keep = b->u_keep;
     ra.seed_keep = b->seed_keep;
-    mkf_launch(k_resample_runs, grid_for(b->T, 4), 128, 0, b->stream, ra);
+    // the estimate of the new set goes to the other slot (a host copy of the previous one may be in flight)
+    b->est_slot ^= 1;
+    if (b->est_used[b->est_slot]) CK(cudaStreamWaitEvent(b->stream, b->est_done[b->est_slot], 0));
+    ra.st_new = b->st[b->cur];
+    ra.Dpose = m->D;
+    ra.recon = b->d_recon;
+    ra.pmean = b->d_pmean;
+    ra.tinv = b->d_tinv;
+    ra.est_xbar = b->est[b->est_slot];
+    ra.est_pose = b->est[b->est_slot] + (size_t)b->T * m->d;
+    ra.est_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
+    if (m->d == 12)
+        mkf_launch(k_resample_runs<12>, grid_for(b->T, 4), 128, 0, b->stream, ra);
+    else
+        mkf_launch(k_resample_runs<10>, grid_for(b->T, 4), 128, 0, b->stream, ra);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (pe) cudaEventRecord(pe[5], b->stream);
     b->shared = true;
     b->slots_valid = false;
+    b->est_valid = true;
+    if (b->pose_cache_on) b->pose_valid = true;
     return MKF_OK;
 }
 
@@ -797,6 +833,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         if ((rc = ensure_slots(b))) return rc;
         b->run_mode = false;
     }
+    b->est_valid = false;
     if (prof) cudaEventRecord(pe[0], b->stream);
     if ((rc = launch_bounds_kernel(b, d_uind, b->clear_status_next ? 1 : 0))) return rc;
     b->clear_status_next = false;
@@ -1017,16 +1054,25 @@ extern "C" int mkf_batch_update(mkf_batch* b, const double* meas, int meas_layou
 
 // getEstimator + reconstruction of every track of the batch (device pointers; either output may be null)
 template <int DD>
-static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
+static bool launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose) // false: served by copies, no kernel
 {
     const mkf_model* m = b->m;
     const double2* st = b->st[b->cur];
     double* d_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
     const size_t coef_bytes = (size_t)(m->D + DD) * DD * sizeof(double);
+    if (b->run_mode && b->est_valid) { // k_resample_runs left the estimate of this set in the batch: copies only
+        const double* ex = b->est[b->est_slot];
+        const double* ep = ex + (size_t)b->T * DD;
+        if (d_xbar) cudaMemcpyAsync(d_xbar, ex, (size_t)b->T * DD * 8, cudaMemcpyDeviceToDevice, b->stream);
+        if (d_pose) cudaMemcpyAsync(d_pose, ep, (size_t)b->T * m->D * 8, cudaMemcpyDeviceToDevice, b->stream);
+        if (d_pose2 && !b->pose_valid)
+            cudaMemcpyAsync(d_pose2, ep, (size_t)b->T * m->D * 8, cudaMemcpyDeviceToDevice, b->stream);
+        return false;
+    }
     if (b->run_mode) { // the current set is a run list: sum of multiplicity x mean
         mkf_launch(k_estimate_runs<DD>, grid_for(b->T, 4), 128, coef_bytes, b->stream, st, (const int2*)b->runs,
                    (const int*)b->nruns, b->T, b->N, m->D, b->d_recon, b->d_pmean, b->d_tinv, d_xbar, d_pose, d_pose2);
-        return;
+        return true;
     }
     // tracks per CTA = TRIPS * 128 / GROUP: 8 trips amortise staging the reconstruction matrices once there are
     // enough tracks to fill the GPU several times over; small batches keep one trip so that they still spread out
@@ -1051,14 +1097,12 @@ static void launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose)
     else // long tracks: more loads in flight per track (BT = 512 is slower at N = 500: 64 vs 41 us at 4096 tracks)
         mkf_launch(k_estimate<DD, 512>, (unsigned)b->T, 512, 0, b->stream, st, b->gather_index(), b->N, m->D, b->d_recon, b->d_pmean,
                                                                    b->d_tinv, d_xbar, d_pose, d_pose2);
+    return true;
 }
 static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
 {
-    if (b->m->d == 12)
-        launch_estimate_d<12>(b, d_xbar, d_pose);
-    else
-        launch_estimate_d<10>(b, d_xbar, d_pose);
-    MKF_LAUNCHED();
+    const bool kernel = (b->m->d == 12) ? launch_estimate_d<12>(b, d_xbar, d_pose) : launch_estimate_d<10>(b, d_xbar, d_pose);
+    if (kernel) MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (b->pose_cache_on) b->pose_valid = true;
     return MKF_OK;
@@ -1074,6 +1118,39 @@ extern "C" int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int 
     const mkf_model* m = b->m;
     OutPtr<double> ox, op;
     int rc;
+    if (b->run_mode && b->est_valid) {
+        // run-length pipeline: k_resample_runs already left xbar / pose of the current set in the batch -- copies only
+        const int sl = b->est_slot;
+        const double* ex = b->est[sl];
+        const double* ep = ex + (size_t)b->T * m->d;
+        const size_t nx = (size_t)b->T * m->d * 8, np = (size_t)b->T * m->D * 8;
+        if (mem == MKF_MEM_HOST_ASYNC) {
+            AsyncIo& io = b->aio;
+            if ((rc = io.init())) return rc;
+            CK(cudaEventRecord(b->est_ready, b->stream));
+            CK(cudaStreamWaitEvent(io.s_out, b->est_ready, 0));
+            if (xbar) CK(cudaMemcpyAsync(xbar, ex, nx, cudaMemcpyDeviceToHost, io.s_out));
+            if (pose) CK(cudaMemcpyAsync(pose, ep, np, cudaMemcpyDeviceToHost, io.s_out));
+            CK(cudaEventRecord(b->est_done[sl], io.s_out));
+            b->est_used[sl] = true;
+            return MKF_OK;
+        }
+        bool any_host = false;
+        auto put = [&](double* dst, const double* src, size_t bytes) -> int {
+            if (!dst) return MKF_OK;
+            const bool dev = is_device_ptr(dst, mem);
+            any_host |= !dev;
+            CK(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, b->stream));
+            return MKF_OK;
+        };
+        if ((rc = put(xbar, ex, nx)) || (rc = put(pose, ep, np))) return rc;
+        if (b->pose_cache_on && !b->pose_valid) {
+            CK(cudaMemcpyAsync(b->pose_cache.p, ep, np, cudaMemcpyDeviceToDevice, b->stream));
+            b->pose_valid = true;
+        }
+        if (any_host) CK(cudaStreamSynchronize(b->stream));
+        return MKF_OK;
+    }
     if (mem == MKF_MEM_HOST_ASYNC) {
         // the kernel writes this call's staging slot; the copy to the host runs on the output stream
         AsyncIo& io = b->aio;
@@ -1191,6 +1268,7 @@ extern "C" int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, 
     b->shared = false;
     b->run_mode = false;
     b->slots_valid = true;
+    b->est_valid = false;
     b->pose_valid = false;
     CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if (d == 12)

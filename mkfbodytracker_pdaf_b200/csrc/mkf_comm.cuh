@@ -215,12 +215,17 @@ extern "C" int mkf_batch_summaries(mkf_batch* b, int64_t rows, double* out, int 
     CK(cudaSetDevice(b->device));
     const int D = b->m->D, W = D + 2;
     int rc;
-    if ((rc = b->out_b.ensure((size_t)b->T * D * 8))) return rc;
-    if ((rc = launch_estimate(b, nullptr, (double*)b->out_b.p))) return rc;
+    const double* d_pose;
+    if (b->run_mode && b->est_valid) { // the pose k_resample_runs left in the batch
+        d_pose = b->est[b->est_slot] + (size_t)b->T * b->m->d;
+    } else {
+        if ((rc = b->out_b.ensure((size_t)b->T * D * 8))) return rc;
+        if ((rc = launch_estimate(b, nullptr, (double*)b->out_b.p))) return rc;
+        d_pose = (const double*)b->out_b.p;
+    }
     OutPtr<double> o;
     if ((rc = o.init(b, out, (size_t)rows * W, mem, b->out_a))) return rc;
-    k_pack_summary<<<grid_for(rows * W, 256), 256, 0, b->stream>>>((const double*)b->out_b.p, b->wsum, b->status, b->T,
-                                                                   rows, D, o.devp);
+    k_pack_summary<<<grid_for(rows * W, 256), 256, 0, b->stream>>>(d_pose, b->wsum, b->status, b->T, rows, D, o.devp);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if ((rc = o.finish(b))) return rc;

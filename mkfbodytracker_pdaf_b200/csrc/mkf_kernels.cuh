@@ -977,14 +977,16 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
 // -----------------------------------------------------------------------------------------
 // (a device function so that k_frame_heads, whose warps are such groups, runs the same code; every lane of the calling
 // warp must enter it)
+// Returns true when the closed form decided (then e_lo / e_hi hold this lane's e_k and e_{k+GROUP}, no wrap).
 template <int GROUP>
-__device__ __forceinline__ void mkf_indicator_bounds_group(const long long t, const int k, const bool live,
+__device__ __forceinline__ bool mkf_indicator_bounds_group(const long long t, const int k, const bool live,
                                                            const double* __restrict__ u, int N, int K,
                                                            const double* __restrict__ cw_hi,
                                                            const double* __restrict__ cw_lo,
                                                            const double* __restrict__ wprior, double wmax,
                                                            int32_t* __restrict__ bounds, uint32_t* __restrict__ status,
-                                                           int clear_status, uint8_t* __restrict__ ind_tail)
+                                                           int clear_status, uint8_t* __restrict__ ind_tail, int& e_lo,
+                                                           int& e_hi)
 {
     // first kernel of a frame update: the track's status word starts from zero (no memset node in front of the
     // chain); the only writer of status in this kernel is this same thread, below
@@ -1011,7 +1013,9 @@ __device__ __forceinline__ void mkf_indicator_bounds_group(const long long t, co
     const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(unsigned)(GROUP - 1)));
     const unsigned votes = __ballot_sync(0xffffffffu, amb);
     const bool any_amb = (votes & gmask) != 0u;
-    if (!live) return;
+    e_lo = e[0];
+    e_hi = e[1];
+    if (!live) return false;
     int32_t* bt = bounds + t * (K + 2);
     if (!any_amb) {
         if (k < K) bt[k] = e[0];
@@ -1020,9 +1024,9 @@ __device__ __forceinline__ void mkf_indicator_bounds_group(const long long t, co
             bt[K] = N;
             bt[K + 1] = 0;
         }
-        return;
+        return true;
     }
-    if (k != 0) return;
+    if (k != 0) return false;
     // literal loop (src/pf2DRao.cpp:195-207) -> counts per component
     uint32_t st = MKF_ST_IND_FALLBACK;
     for (int q = 0; q < K; q++) bt[q] = 0;
@@ -1068,6 +1072,7 @@ __device__ __forceinline__ void mkf_indicator_bounds_group(const long long t, co
     bt[K] = wrap_from;
     bt[K + 1] = wrap_k;
     atomicOr(status + t, st);
+    return false;
 }
 
 template <int GROUP>
@@ -1080,8 +1085,9 @@ __global__ void k_indicator_bounds(const double* __restrict__ u, long long T, in
     mkf_pdl_wait();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long t = gid / GROUP;
+    int e_lo, e_hi;
     mkf_indicator_bounds_group<GROUP>(t, (int)(gid % GROUP), t < T, u, N, K, cw_hi, cw_lo, wprior, wmax, bounds, status,
-                                      clear_status, ind_tail);
+                                      clear_status, ind_tail, e_lo, e_hi);
 }
 
 // the prefix-sum / head-marker pass of k_resample_block carried in double-double throughout; kept out of line so that

@@ -85,6 +85,16 @@ struct FrameArgs {
     int* __restrict__ head_count;
 };
 
+// component of slot j = number of cuts <= j (cuts sorted, nc <= 63): branch-free binary search
+__device__ __forceinline__ int mkf_cuts_le(const int* cuts, int nc, int j)
+{
+    int lo = 0; // invariant: cuts[0..lo) <= j
+#pragma unroll
+    for (int s = 32; s > 0; s >>= 1)
+        if (lo + s <= nc && cuts[lo + s - 1] <= j) lo += s;
+    return lo;
+}
+
 __global__ void __launch_bounds__(128) k_frame_heads(const FrameArgs f)
 {
     __shared__ int cuts_s[4][64];
@@ -94,20 +104,100 @@ __global__ void __launch_bounds__(128) k_frame_heads(const FrameArgs f)
     const long long t = (long long)blockIdx.x * 4 + wid;
     if (t >= f.T) return;
     const int N = f.N, K = f.K;
-    // the K -> N indicator draw: the lanes of this warp are the group of k_indicator_bounds<32>
-    mkf_indicator_bounds_group<32>(t, lane, true, f.u_ind, N, K, f.cw_hi, f.cw_lo, f.wprior, f.wmax, f.bounds, f.status,
-                                   f.clear_status, f.ind_tail);
-    __syncwarp();
-    const int32_t* bt = f.bounds + t * (K + 2);
-    int* cuts = cuts_s[wid];
-    const int nc = K - 1; // cut q = first slot whose component exceeds q
-    for (int q = lane; q < nc; q += 32) cuts[q] = bt[q];
-    const int wrap_from = bt[K];
-    __syncwarp();
     const int2* __restrict__ rt = f.runs + t * N;
     int4* __restrict__ hm = f.hmeta + t * N;
     const int nr = f.nruns[t];
+    int2 rn0 = make_int2(0, 0), rn1 = make_int2(0, 0); // (loads in flight during the indicator draw)
+    if (lane < nr) rn0 = rt[lane];
+    if (32 + lane < nr) rn1 = rt[32 + lane];
+    // the K -> N indicator draw: the lanes of this warp are the group of k_indicator_bounds<32>
+    int e_lo, e_hi;
+    const bool closed = mkf_indicator_bounds_group<32>(t, lane, true, f.u_ind, N, K, f.cw_hi, f.cw_lo, f.wprior, f.wmax,
+                                                       f.bounds, f.status, f.clear_status, f.ind_tail, e_lo, e_hi);
+    const bool fast = __all_sync(0xffffffffu, closed);
+    const int32_t* bt = f.bounds + t * (K + 2);
+    int* cuts = cuts_s[wid];
+    const int nc = K - 1; // cut q = first slot whose component exceeds q
+    int wrap_from = N;
+    if (fast) { // the boundaries are still in registers
+        if (lane < nc) cuts[lane] = e_lo;
+        if (32 + lane < nc) cuts[32 + lane] = e_hi;
+    } else {    // the literal loop wrote them (lane 0)
+        __syncwarp();
+        for (int q = lane; q < nc; q += 32) cuts[q] = __ldcg(bt + q);
+        wrap_from = __ldcg(bt + K);
+    }
+    __syncwarp();
     int nh = 0;
+    const int tN = (int)(t * N);
+    if (wrap_from >= N && nr <= 64) {
+        // the common case: the track's runs fit two per lane; count the pieces, reserve the track's stretch of the
+        // batch-wide work list with one atomicAdd, then write head table and work list in one walk
+        int a_[2], b_[2], k0_[2], h0_[2];
+        int pos_carry = 0;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int2 rn = c ? rn1 : rn0;
+            const bool live = c * 32 + lane < nr;
+            int inc = rn.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
+            int k0 = 0, np = 0;
+            if (live) {
+                k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
+                // one more piece per component change inside the run; empty components (equal cuts) change nothing:
+                // count the distinct cut positions in (a, b)
+                int k = k0, cnt = 0;
+                while (k < nc && cuts[k] < b) {
+                    const int cpos = cuts[k];
+                    cnt++;
+                    while (k < nc && cuts[k] == cpos) k++;
+                }
+                np = 1 + cnt;
+            }
+            int pinc = np;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, pinc, o);
+                if (lane >= o) pinc += n;
+            }
+            a_[c] = a;
+            b_[c] = b;
+            k0_[c] = k0;
+            h0_[c] = nh + pinc - np;
+            nh += __shfl_sync(0xffffffffu, pinc, 31);
+            pos_carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        int lb = 0;
+        if (lane == 0) {
+            f.nheads[t] = nh;
+            lb = atomicAdd(f.head_count, nh); // this track's stretch of the batch-wide work list (order immaterial)
+        }
+        lb = __shfl_sync(0xffffffffu, lb, 0);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (c * 32 + lane < nr) {
+                const int rec = c ? rn1.x : rn0.x;
+                const int b = b_[c];
+                int h = h0_[c], k = k0_[c], pos = a_[c];
+                for (;;) {
+                    const int cpos = k < nc ? cuts[k] : N;
+                    const int end = cpos < b ? cpos : b;
+                    hm[h] = make_int4(rec, k, end - pos, pos);
+                    f.hd16[lb + h] = make_int4(tN + rec, tN + h, (int)t, k);
+                    h++;
+                    if (cpos >= b) break;
+                    pos = cpos;
+                    while (k < nc && cuts[k] <= cpos) k++;
+                }
+            }
+        }
+        return;
+    }
     if (wrap_from >= N) {
         int pos_carry = 0;
         for (int r0 = 0; r0 < nr; r0 += 32) {
@@ -122,7 +212,7 @@ __global__ void __launch_bounds__(128) k_frame_heads(const FrameArgs f)
             const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
             int k0 = 0, np = 0;
             if (r < nr) {
-                while (k0 < nc && cuts[k0] <= a) k0++; // component of slot a
+                k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
                 int k = k0;
                 for (;;) {
                     np++;
@@ -179,9 +269,8 @@ __global__ void __launch_bounds__(128) k_frame_heads(const FrameArgs f)
         lb = atomicAdd(f.head_count, nh); // this track's stretch of the batch-wide work list (order immaterial)
     }
     lb = __shfl_sync(0xffffffffu, lb, 0);
-    const int tN = (int)(t * N);
     for (int i = lane; i < nh; i += 32) {
-        const int4 m = hm[i];
+        const int4 m = __ldcg(hm + i);
         f.hd16[lb + i] = make_int4(tN + m.x, tN + i, (int)t, m.y);
     }
 }
@@ -270,10 +359,22 @@ struct ResampleRunsArgs {
     int* __restrict__ nruns;
     double* __restrict__ u_keep;   // copies of the draw / seed of this resample, for the on-demand per-slot replay
     uint64_t* __restrict__ seed_keep;
+    // getEstimator + reconstruction of the new set (src/pf2DRao.cpp:23-31, src/pfPose.cpp:347-348), left in the batch:
+    // mkf_batch_estimate then only copies
+    const double2* __restrict__ st_new; // the records the heads kernel just wrote
+    int Dpose;
+    const double* __restrict__ recon;
+    const double* __restrict__ pmean;
+    const double* __restrict__ tinv;
+    double* __restrict__ est_xbar;  // T x d
+    double* __restrict__ est_pose;  // T x Dpose
+    double* __restrict__ est_pose2; // the association step's copy of the pose (or null)
 };
 
+template <int D>
 __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
 {
+    using L = SlotLay<D>;
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -283,7 +384,7 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
     const int nh = a.nheads[t];
     const int4* __restrict__ hm = a.hmeta + t * N;
     const double* __restrict__ wr = a.w_rec + t * N;
-    int2* __restrict__ rt = a.runs + t * N;
+    int2* rt = a.runs + t * N;
 
     // pass 1: wsum = sum over slots (src/pf2DRao.cpp:139) = sum_h m_h w_h, accumulated in double-double and rounded once;
     // NaN-ignoring max (src/pf2DRao.cpp:161-172)
@@ -310,12 +411,13 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
         a.seed_keep[t] = seed;
     }
     const double wmax_n = __ddiv_rn(mx, wsum);
+    int nr = 0;
     if (!(wmax_n > 0.0)) { // max weight 0 / NaN -> N random parents from cv::RNG (src/pf2DRao.cpp:184-192)
         if (lane == 0) {
             atomicOr(a.status + t, MKF_ST_POST_DEGENERATE);
             mkf_cvrng rng(seed);
             (void)rng.uniform_int(0, N); // `int idx = rng.uniform(0, L);` drawn and discarded
-            int nr = 0, cur = -1, cnt = 0;
+            int cur = -1, cnt = 0;
             for (int i = 0; i < N; i++) {
                 const int idx = rng.uniform_int(0, N); // a SLOT; its record is the head whose range holds it
                 int lo = 0, hi = nh - 1;
@@ -335,81 +437,121 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
                 }
             }
             if (cnt) rt[nr++] = make_int2(cur, cnt);
-            a.nruns[t] = nr;
-        }
-        return;
-    }
-    const double step = __ddiv_rn(1.0, (double)N);
-    const double beta0 = __dmul_rn(uu, step);
-    // the band in which the literal loop's accumulated rounding could change a decision (mkf_resample_tol*), plus the
-    // rounding of mkf_count_le's remainder and of the double-double prefix sums (as k_resample_block's second opinion)
-    const double s2 = __ddiv_rn(sq, __dmul_rn(wsum, wsum)) * (1.0 + 1e-9);
-    const double tol_loop = fmin(mkf_resample_tol(N, N, wmax_n, step), mkf_resample_tol_s2(N, N, s2, 1.0));
-    const double tol2 = tol_loop + 8.0 * 1.1102230246251565e-16 * step + 8.0e-28 * 2.0;
-
-    // pass 2: prefix sums at run ends -> children per head -> the new run list
-    dd carry = dd_make(0.0);
-    int e_carry = 0, nr = 0;
-    bool amb = false;
-    for (int i0 = 0; i0 < nh; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < nh;
-        const double wn = valid ? __ddiv_rn(wr[i], wsum) : 0.0; // the normalised weight of each of the head's slots
-        dd inc = dd_mul_exact(valid ? (double)hm[i].z : 0.0, wn);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const dd n = dd_shfl_up(inc, o);
-            if (lane >= o) inc = dd_add(n, inc);
-        }
-        const dd C = dd_add(carry, inc);
-        int eh = N;
-        if (valid) {
-            eh = mkf_count_le(C, beta0, step, N, tol2, amb);
-            if (i == nh - 1 && eh < N) amb = true; // the literal loop would wrap past the last slot
-        }
-        int eprev = __shfl_up_sync(0xffffffffu, eh, 1);
-        if (lane == 0) eprev = e_carry;
-        const int c = valid ? eh - eprev : 0;
-        const unsigned msk = __ballot_sync(0xffffffffu, c > 0);
-        if (c > 0) rt[nr + __popc(msk & ((1u << lane) - 1u))] = make_int2(i, c);
-        nr += __popc(msk);
-        const int lastl = (nh - i0 >= 32) ? 31 : (nh - i0 - 1);
-        e_carry = __shfl_sync(0xffffffffu, eh, lastl);
-        carry.hi = __shfl_sync(0xffffffffu, C.hi, 31); // lane 31's inclusive prefix (lanes beyond nh add zero)
-        carry.lo = __shfl_sync(0xffffffffu, C.lo, 31);
-    }
-    if (__any_sync(0xffffffffu, amb)) {
-        // undecidable in closed form: the reference's loop itself (src/pf2DRao.cpp:195-207), slot by slot
-        if (lane == 0) {
-            atomicOr(a.status + t, MKF_ST_POST_FALLBACK);
-            int h = 0, left = hm[0].z;
-            double wi = __ddiv_rn(wr[0], wsum);
-            double beta = beta0;
-            int cur = -1, cnt = 0;
-            nr = 0;
-            for (int i = 0; i < N; i++) {
-                while (beta > wi) {
-                    beta = __dsub_rn(beta, wi);
-                    if (--left == 0) { // idx = (idx + 1) % L moved on to the next head's first slot
-                        h = (h + 1 == nh) ? 0 : h + 1;
-                        left = hm[h].z;
-                        wi = __ddiv_rn(wr[h], wsum);
-                    }
-                }
-                beta = __dadd_rn(beta, step);
-                if (h == cur) {
-                    cnt++;
-                } else {
-                    if (cnt) rt[nr++] = make_int2(cur, cnt);
-                    cur = h;
-                    cnt = 1;
-                }
-            }
-            if (cnt) rt[nr++] = make_int2(cur, cnt);
         }
         nr = __shfl_sync(0xffffffffu, nr, 0);
+    } else {
+        const double step = __ddiv_rn(1.0, (double)N);
+        const double beta0 = __dmul_rn(uu, step);
+        // the band in which the literal loop's accumulated rounding could change a decision (mkf_resample_tol*), plus
+        // the rounding of mkf_count_le's remainder and of the double-double prefix sums (as k_resample_block's second
+        // opinion)
+        const double s2 = __ddiv_rn(sq, __dmul_rn(wsum, wsum)) * (1.0 + 1e-9);
+        const double tol_loop = fmin(mkf_resample_tol(N, N, wmax_n, step), mkf_resample_tol_s2(N, N, s2, 1.0));
+        const double tol2 = tol_loop + 8.0 * 1.1102230246251565e-16 * step + 8.0e-28 * 2.0;
+
+        // pass 2: prefix sums at run ends -> children per head -> the new run list
+        dd carry = dd_make(0.0);
+        int e_carry = 0;
+        bool amb = false;
+        for (int i0 = 0; i0 < nh; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < nh;
+            const double wn = valid ? __ddiv_rn(wr[i], wsum) : 0.0; // the normalised weight of each of the head's slots
+            dd inc = dd_mul_exact(valid ? (double)hm[i].z : 0.0, wn);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const dd n = dd_shfl_up(inc, o);
+                if (lane >= o) inc = dd_add(n, inc);
+            }
+            const dd C = dd_add(carry, inc);
+            int eh = N;
+            if (valid) {
+                eh = mkf_count_le(C, beta0, step, N, tol2, amb);
+                if (i == nh - 1 && eh < N) amb = true; // the literal loop would wrap past the last slot
+            }
+            int eprev = __shfl_up_sync(0xffffffffu, eh, 1);
+            if (lane == 0) eprev = e_carry;
+            const int c = valid ? eh - eprev : 0;
+            const unsigned msk = __ballot_sync(0xffffffffu, c > 0);
+            if (c > 0) rt[nr + __popc(msk & ((1u << lane) - 1u))] = make_int2(i, c);
+            nr += __popc(msk);
+            const int lastl = (nh - i0 >= 32) ? 31 : (nh - i0 - 1);
+            e_carry = __shfl_sync(0xffffffffu, eh, lastl);
+            carry.hi = __shfl_sync(0xffffffffu, C.hi, 31); // lane 31's inclusive prefix (lanes beyond nh add zero)
+            carry.lo = __shfl_sync(0xffffffffu, C.lo, 31);
+        }
+        if (__any_sync(0xffffffffu, amb)) {
+            // undecidable in closed form: the reference's loop itself (src/pf2DRao.cpp:195-207), slot by slot
+            if (lane == 0) {
+                atomicOr(a.status + t, MKF_ST_POST_FALLBACK);
+                int h = 0, left = hm[0].z;
+                double wi = __ddiv_rn(wr[0], wsum);
+                double beta = beta0;
+                int cur = -1, cnt = 0;
+                nr = 0;
+                for (int i = 0; i < N; i++) {
+                    while (beta > wi) {
+                        beta = __dsub_rn(beta, wi);
+                        if (--left == 0) { // idx = (idx + 1) % L moved on to the next head's first slot
+                            h = (h + 1 == nh) ? 0 : h + 1;
+                            left = hm[h].z;
+                            wi = __ddiv_rn(wr[h], wsum);
+                        }
+                    }
+                    beta = __dadd_rn(beta, step);
+                    if (h == cur) {
+                        cnt++;
+                    } else {
+                        if (cnt) rt[nr++] = make_int2(cur, cnt);
+                        cur = h;
+                        cnt = 1;
+                    }
+                }
+                if (cnt) rt[nr++] = make_int2(cur, cnt);
+            }
+            nr = __shfl_sync(0xffffffffu, nr, 0);
+        }
     }
     if (lane == 0) a.nruns[t] = nr;
+    __syncwarp();
+
+    // estimator of the new set: sum over its runs of children x mean, / N; then the PCA reconstruction
+    double xs[D];
+#pragma unroll
+    for (int e = 0; e < D; e++) xs[e] = 0.0;
+    for (int r = lane; r < nr; r += 32) {
+        const int2 rn = __ldcg(rt + r); // written by this warp just above
+        const long long sp = t * N + rn.x;
+        const double2* __restrict__ src = a.st_new + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+        const double m = (double)rn.y;
+#pragma unroll
+        for (int p = 0; p < D / 2; p++) {
+            const double2 q = __ldg(src + L::po(p));
+            xs[2 * p] = fma(m, q.x, xs[2 * p]);
+            xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
+        }
+    }
+    const double inv_n = 1.0 / (double)N;
+#pragma unroll
+    for (int e = 0; e < D; e++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) xs[e] += __shfl_xor_sync(0xffffffffu, xs[e], o);
+        xs[e] *= inv_n;
+    }
+    const int R = a.Dpose + D;
+    for (int r = lane; r < R; r += 32) {
+        const double* __restrict__ row = r < a.Dpose ? a.recon + r * D : a.tinv + (r - a.Dpose) * D;
+        double sacc = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; c++) sacc = fma(__ldg(row + c), xs[c], sacc);
+        if (r < a.Dpose) {
+            const double v = sacc + __ldg(a.pmean + r);
+            a.est_pose[t * a.Dpose + r] = v;
+            if (a.est_pose2) a.est_pose2[t * a.Dpose + r] = v;
+        } else {
+            a.est_xbar[t * D + (r - a.Dpose)] = sacc;
+        }
+    }
 }
 
 // getEstimator + reconstruction from the run list: 4 tracks per CTA, one warp each
