@@ -724,7 +724,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, const double* 
     f.hd16 = b->hd16;
     f.head_count = b->head_count + b->head_flip;
     b->clear_status_next = false;
-    mkf_launch(k_frame_heads, grid_for(b->T, 4), 128, 0, b->stream, f);
+    mkf_launch(k_frame_heads, grid_for(b->T, MKF_FH_WARPS), 32 * MKF_FH_WARPS, 0, b->stream, f);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (pe) cudaEventRecord(pe[2], b->stream);
@@ -785,10 +785,11 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, const double* 
     ra.est_xbar = b->est[b->est_slot];
     ra.est_pose = b->est[b->est_slot] + (size_t)b->T * m->d;
     ra.est_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
+    const size_t coef_bytes = (size_t)(m->D + m->d) * m->d * sizeof(double);
     if (m->d == 12)
-        mkf_launch(k_resample_runs<12>, grid_for(b->T, 4), 128, 0, b->stream, ra);
+        mkf_launch(k_resample_runs<12>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
     else
-        mkf_launch(k_resample_runs<10>, grid_for(b->T, 4), 128, 0, b->stream, ra);
+        mkf_launch(k_resample_runs<10>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (pe) cudaEventRecord(pe[5], b->stream);

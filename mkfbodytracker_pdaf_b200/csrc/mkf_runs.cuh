@@ -95,89 +95,173 @@ __device__ __forceinline__ int mkf_cuts_le(const int* cuts, int nc, int j)
     return lo;
 }
 
-__global__ void __launch_bounds__(128) k_frame_heads(const FrameArgs f)
+constexpr int MKF_FH_WARPS = 8; // tracks per CTA of k_frame_heads
+
+__global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameArgs f)
 {
-    __shared__ int cuts_s[4][64];
+    __shared__ int cuts_s[MKF_FH_WARPS][64];
+    __shared__ int nh_s[MKF_FH_WARPS];
+    __shared__ int base_s;
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long t = (long long)blockIdx.x * 4 + wid;
-    if (t >= f.T) return;
+    const long long t = (long long)blockIdx.x * MKF_FH_WARPS + wid;
+    const bool live_t = t < f.T; // (a warp without a track still meets the CTA's barriers below)
     const int N = f.N, K = f.K;
-    const int2* __restrict__ rt = f.runs + t * N;
-    int4* __restrict__ hm = f.hmeta + t * N;
-    const int nr = f.nruns[t];
+    const int2* __restrict__ rt = f.runs + (live_t ? t : 0) * N;
+    int4* __restrict__ hm = f.hmeta + (live_t ? t : 0) * N;
+    const int nr = live_t ? f.nruns[t] : 0;
     int2 rn0 = make_int2(0, 0), rn1 = make_int2(0, 0); // (loads in flight during the indicator draw)
     if (lane < nr) rn0 = rt[lane];
     if (32 + lane < nr) rn1 = rt[32 + lane];
-    // the K -> N indicator draw: the lanes of this warp are the group of k_indicator_bounds<32>
-    int e_lo, e_hi;
-    const bool closed = mkf_indicator_bounds_group<32>(t, lane, true, f.u_ind, N, K, f.cw_hi, f.cw_lo, f.wprior, f.wmax,
-                                                       f.bounds, f.status, f.clear_status, f.ind_tail, e_lo, e_hi);
-    const bool fast = __all_sync(0xffffffffu, closed);
-    const int32_t* bt = f.bounds + t * (K + 2);
+    int nh = 0;
+    int mode = 0; // 1: fast path (pieces still to be written, in one walk with the work list), 2: head table written
+    int a_[2] = {0, 0}, b_[2] = {0, 0}, k0_[2] = {0, 0}, h0_[2] = {0, 0};
     int* cuts = cuts_s[wid];
     const int nc = K - 1; // cut q = first slot whose component exceeds q
-    int wrap_from = N;
-    if (fast) { // the boundaries are still in registers
-        if (lane < nc) cuts[lane] = e_lo;
-        if (32 + lane < nc) cuts[32 + lane] = e_hi;
-    } else {    // the literal loop wrote them (lane 0)
+    const int tN = (int)((live_t ? t : 0) * N);
+    if (live_t) {
+        // the K -> N indicator draw: the lanes of this warp are the group of k_indicator_bounds<32>
+        int e_lo, e_hi;
+        const bool closed = mkf_indicator_bounds_group<32>(t, lane, true, f.u_ind, N, K, f.cw_hi, f.cw_lo, f.wprior, f.wmax,
+                                                           f.bounds, f.status, f.clear_status, f.ind_tail, e_lo, e_hi);
+        const bool fast = __all_sync(0xffffffffu, closed);
+        const int32_t* bt = f.bounds + t * (K + 2);
+        int wrap_from = N;
+        if (fast) { // the boundaries are still in registers
+            if (lane < nc) cuts[lane] = e_lo;
+            if (32 + lane < nc) cuts[32 + lane] = e_hi;
+        } else {    // the literal loop wrote them (lane 0)
+            __syncwarp();
+            for (int q = lane; q < nc; q += 32) cuts[q] = __ldcg(bt + q);
+            wrap_from = __ldcg(bt + K);
+        }
         __syncwarp();
-        for (int q = lane; q < nc; q += 32) cuts[q] = __ldcg(bt + q);
-        wrap_from = __ldcg(bt + K);
-    }
-    __syncwarp();
-    int nh = 0;
-    const int tN = (int)(t * N);
-    if (wrap_from >= N && nr <= 64) {
-        // the common case: the track's runs fit two per lane; count the pieces, reserve the track's stretch of the
-        // batch-wide work list with one atomicAdd, then write head table and work list in one walk
-        int a_[2], b_[2], k0_[2], h0_[2];
-        int pos_carry = 0;
+        if (wrap_from >= N && nr <= 64) {
+            // the common case: the track's runs fit two per lane; count the pieces first
+            mode = 1;
+            int pos_carry = 0;
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int2 rn = c ? rn1 : rn0;
-            const bool live = c * 32 + lane < nr;
-            int inc = rn.y;
+            for (int c = 0; c < 2; c++) {
+                const int2 rn = c ? rn1 : rn0;
+                const bool live = c * 32 + lane < nr;
+                int inc = rn.y;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += n;
-            }
-            const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
-            int k0 = 0, np = 0;
-            if (live) {
-                k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
-                // one more piece per component change inside the run; empty components (equal cuts) change nothing:
-                // count the distinct cut positions in (a, b)
-                int k = k0, cnt = 0;
-                while (k < nc && cuts[k] < b) {
-                    const int cpos = cuts[k];
-                    cnt++;
-                    while (k < nc && cuts[k] == cpos) k++;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += n;
                 }
-                np = 1 + cnt;
-            }
-            int pinc = np;
+                const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
+                int k0 = 0, np = 0;
+                if (live) {
+                    k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
+                    // one more piece per component change inside the run; empty components (equal cuts) change
+                    // nothing: count the distinct cut positions in (a, b)
+                    int k = k0, cnt = 0;
+                    while (k < nc && cuts[k] < b) {
+                        const int cpos = cuts[k];
+                        cnt++;
+                        while (k < nc && cuts[k] == cpos) k++;
+                    }
+                    np = 1 + cnt;
+                }
+                int pinc = np;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, pinc, o);
-                if (lane >= o) pinc += n;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, pinc, o);
+                    if (lane >= o) pinc += n;
+                }
+                a_[c] = a;
+                b_[c] = b;
+                k0_[c] = k0;
+                h0_[c] = nh + pinc - np;
+                nh += __shfl_sync(0xffffffffu, pinc, 31);
+                pos_carry += __shfl_sync(0xffffffffu, inc, 31);
             }
-            a_[c] = a;
-            b_[c] = b;
-            k0_[c] = k0;
-            h0_[c] = nh + pinc - np;
-            nh += __shfl_sync(0xffffffffu, pinc, 31);
-            pos_carry += __shfl_sync(0xffffffffu, inc, 31);
+        } else if (wrap_from >= N) {
+            mode = 2;
+            int pos_carry = 0;
+            for (int r0 = 0; r0 < nr; r0 += 32) {
+                const int r = r0 + lane;
+                const int2 rn = r < nr ? rt[r] : make_int2(0, 0);
+                int inc = rn.y;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += n;
+                }
+                const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
+                int k0 = 0, np = 0;
+                if (r < nr) {
+                    k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
+                    int k = k0;
+                    for (;;) {
+                        np++;
+                        const int c = k < nc ? cuts[k] : N;
+                        if (c >= b) break;
+                        while (k < nc && cuts[k] <= c) k++;
+                    }
+                }
+                int pinc = np;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, pinc, o);
+                    if (lane >= o) pinc += n;
+                }
+                if (r < nr) {
+                    int h = nh + pinc - np, k = k0, pos = a;
+                    for (;;) {
+                        const int c = k < nc ? cuts[k] : N;
+                        const int end = c < b ? c : b;
+                        hm[h++] = make_int4(rn.x, k, end - pos, pos);
+                        if (c >= b) break;
+                        pos = c;
+                        while (k < nc && cuts[k] <= c) k++;
+                    }
+                }
+                nh += __shfl_sync(0xffffffffu, pinc, 31);
+                pos_carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        } else {
+            // the draw wrapped past the last component (prior mass short of the thresholds): components per slot
+            mode = 2;
+            if (lane == 0) {
+                const uint8_t* tail = f.ind_tail ? f.ind_tail + t * N : nullptr;
+                int pos = 0;
+                for (int r = 0; r < nr; r++) {
+                    const int2 rn = rt[r];
+                    int j = pos;
+                    const int b = pos + rn.y;
+                    while (j < b) {
+                        const int k = mkf_component_of(bt, K, j, tail);
+                        int j2 = j + 1;
+                        while (j2 < b && mkf_component_of(bt, K, j2, tail) == k) j2++;
+                        hm[nh++] = make_int4(rn.x, k, j2 - j, j);
+                        j = j2;
+                    }
+                    pos = b;
+                }
+            }
+            nh = __shfl_sync(0xffffffffu, nh, 0);
         }
-        int lb = 0;
-        if (lane == 0) {
-            f.nheads[t] = nh;
-            lb = atomicAdd(f.head_count, nh); // this track's stretch of the batch-wide work list (order immaterial)
-        }
-        lb = __shfl_sync(0xffffffffu, lb, 0);
+    }
+    // one atomicAdd per CTA reserves its tracks' stretch of the batch-wide work list (order immaterial); 4096
+    // same-address atomics, one per track, were what the kernel waited for
+    if (lane == 0) {
+        nh_s[wid] = nh;
+        if (live_t) f.nheads[t] = nh;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < MKF_FH_WARPS; w++) tot += nh_s[w];
+        base_s = atomicAdd(f.head_count, tot);
+    }
+    __syncthreads();
+    int lb = base_s;
+    for (int w = 0; w < wid; w++) lb += nh_s[w];
+    if (mode == 1) { // head table and work list in one walk
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             if (c * 32 + lane < nr) {
@@ -196,82 +280,12 @@ __global__ void __launch_bounds__(128) k_frame_heads(const FrameArgs f)
                 }
             }
         }
-        return;
-    }
-    if (wrap_from >= N) {
-        int pos_carry = 0;
-        for (int r0 = 0; r0 < nr; r0 += 32) {
-            const int r = r0 + lane;
-            const int2 rn = r < nr ? rt[r] : make_int2(0, 0);
-            int inc = rn.y;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += n;
-            }
-            const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
-            int k0 = 0, np = 0;
-            if (r < nr) {
-                k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
-                int k = k0;
-                for (;;) {
-                    np++;
-                    const int c = k < nc ? cuts[k] : N;
-                    if (c >= b) break;
-                    while (k < nc && cuts[k] <= c) k++;
-                }
-            }
-            int pinc = np;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, pinc, o);
-                if (lane >= o) pinc += n;
-            }
-            if (r < nr) {
-                int h = nh + pinc - np, k = k0, pos = a;
-                for (;;) {
-                    const int c = k < nc ? cuts[k] : N;
-                    const int end = c < b ? c : b;
-                    hm[h++] = make_int4(rn.x, k, end - pos, pos);
-                    if (c >= b) break;
-                    pos = c;
-                    while (k < nc && cuts[k] <= c) k++;
-                }
-            }
-            nh += __shfl_sync(0xffffffffu, pinc, 31);
-            pos_carry += __shfl_sync(0xffffffffu, inc, 31);
+    } else if (mode == 2) {
+        __syncwarp();
+        for (int i = lane; i < nh; i += 32) {
+            const int4 m = __ldcg(hm + i);
+            f.hd16[lb + i] = make_int4(tN + m.x, tN + i, (int)t, m.y);
         }
-    } else {
-        // the draw wrapped past the last component (prior mass short of the thresholds): components are read per slot
-        if (lane == 0) {
-            const uint8_t* tail = f.ind_tail ? f.ind_tail + t * N : nullptr;
-            int pos = 0;
-            for (int r = 0; r < nr; r++) {
-                const int2 rn = rt[r];
-                int j = pos;
-                const int b = pos + rn.y;
-                while (j < b) {
-                    const int k = mkf_component_of(bt, K, j, tail);
-                    int j2 = j + 1;
-                    while (j2 < b && mkf_component_of(bt, K, j2, tail) == k) j2++;
-                    hm[nh++] = make_int4(rn.x, k, j2 - j, j);
-                    j = j2;
-                }
-                pos = b;
-            }
-        }
-        nh = __shfl_sync(0xffffffffu, nh, 0);
-    }
-    __syncwarp();
-    int lb = 0;
-    if (lane == 0) {
-        f.nheads[t] = nh;
-        lb = atomicAdd(f.head_count, nh); // this track's stretch of the batch-wide work list (order immaterial)
-    }
-    lb = __shfl_sync(0xffffffffu, lb, 0);
-    for (int i = lane; i < nh; i += 32) {
-        const int4 m = __ldcg(hm + i);
-        f.hd16[lb + i] = make_int4(tN + m.x, tN + i, (int)t, m.y);
     }
 }
 
@@ -336,6 +350,14 @@ __device__ __forceinline__ dd dd_shfl_up(dd v, int o)
     r.lo = __shfl_up_sync(0xffffffffu, v.lo, o);
     return r;
 }
+// a + b for operands of the same sign (the weight sums): the error term of the low words is not re-split, error
+// <= 2^-104 relative -- 11 operations instead of dd_add's 20
+__device__ __forceinline__ dd dd_add_pos(dd a, dd b)
+{
+    dd s = dd_two_sum(a.hi, b.hi);
+    s.lo = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
+    return dd_fast_two_sum(s.hi, s.lo);
+}
 // m * w exactly (m an integer count) as a double-double
 __device__ __forceinline__ dd dd_mul_exact(double m, double w)
 {
@@ -372,11 +394,18 @@ struct ResampleRunsArgs {
 };
 
 template <int D>
-__global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
+__global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs a)
 {
     using L = SlotLay<D>;
+    extern __shared__ double coef[]; // [c][r], r < Dpose + D: rows of recon (pose) then rows of tinv (xbar)
     mkf_pdl_launch_dependents();
+    const int R = a.Dpose + D;
+    for (int i = threadIdx.x; i < R * D; i += 128) { // model constants: safe before the dependency wait
+        const int r = i / D, c = i - r * D;
+        coef[c * R + r] = r < a.Dpose ? a.recon[r * D + c] : a.tinv[(r - a.Dpose) * D + c];
+    }
     mkf_pdl_wait();
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= a.T) return;
@@ -385,6 +414,9 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
     const int4* __restrict__ hm = a.hmeta + t * N;
     const double* __restrict__ wr = a.w_rec + t * N;
     int2* rt = a.runs + t * N;
+    // estimator of the new set (sum over its runs of children x mean): gathered as soon as a head's children are known
+    double xs[D];
+    bool xs_done = false;
 
     // pass 1: wsum = sum over slots (src/pf2DRao.cpp:139) = sum_h m_h w_h, accumulated in double-double and rounded once;
     // NaN-ignoring max (src/pf2DRao.cpp:161-172)
@@ -392,13 +424,13 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
     double mx = 0.0, sq = 0.0;
     for (int i = lane; i < nh; i += 32) {
         const double w = wr[i], md = (double)hm[i].z;
-        acc = dd_add(acc, dd_mul_exact(md, w));
+        acc = dd_add_pos(acc, dd_mul_exact(md, w));
         if (w > mx) mx = w;
         sq = fma(__dmul_rn(md, w), w, sq);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        acc = dd_add(acc, dd_shfl_xor(acc, o));
+        acc = dd_add_pos(acc, dd_shfl_xor(acc, o));
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
@@ -448,39 +480,74 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
         const double s2 = __ddiv_rn(sq, __dmul_rn(wsum, wsum)) * (1.0 + 1e-9);
         const double tol_loop = fmin(mkf_resample_tol(N, N, wmax_n, step), mkf_resample_tol_s2(N, N, s2, 1.0));
         const double tol2 = tol_loop + 8.0 * 1.1102230246251565e-16 * step + 8.0e-28 * 2.0;
-
-        // pass 2: prefix sums at run ends -> children per head -> the new run list
-        dd carry = dd_make(0.0);
-        int e_carry = 0;
+        // pass 2: prefix sums at run ends -> children per head -> the new run list.  First with the prefix sums in plain
+        // double (<= 8 roundings of partial sums <= 1 on the way to any run end: the same 16 x 2^-53 x (1 + mass) term
+        // as k_resample_block adds to the band); a track with a threshold inside the band gets a second opinion with
+        // the prefix sums in double-double (only the loop's own bound left), and then the literal loop.
         bool amb = false;
-        for (int i0 = 0; i0 < nh; i0 += 32) {
-            const int i = i0 + lane;
-            const bool valid = i < nh;
-            const double wn = valid ? __ddiv_rn(wr[i], wsum) : 0.0; // the normalised weight of each of the head's slots
-            dd inc = dd_mul_exact(valid ? (double)hm[i].z : 0.0, wn);
+        for (int pass = 0; pass < 2; pass++) {
+            const double tol = pass == 0 ? tol_loop + 16.0 * 1.1102230246251565e-16 * 2.0 : tol2;
+            dd carry = dd_make(0.0);
+            int e_carry = 0;
+            amb = false;
+            nr = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const dd n = dd_shfl_up(inc, o);
-                if (lane >= o) inc = dd_add(n, inc);
+            for (int e = 0; e < D; e++) xs[e] = 0.0;
+            for (int i0 = 0; i0 < nh; i0 += 32) {
+                const int i = i0 + lane;
+                const bool valid = i < nh;
+                const double wn = valid ? __ddiv_rn(wr[i], wsum) : 0.0; // the normalised weight of each of the head's slots
+                const double md = valid ? (double)hm[i].z : 0.0;
+                dd C;
+                if (pass == 0) {
+                    double inc = __dmul_rn(md, wn);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double n = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += n;
+                    }
+                    C = dd_make(carry.hi + inc);
+                } else {
+                    dd inc = dd_mul_exact(md, wn);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const dd n = dd_shfl_up(inc, o);
+                        if (lane >= o) inc = dd_add(n, inc);
+                    }
+                    C = dd_add(carry, inc);
+                }
+                int eh = N;
+                if (valid) {
+                    eh = mkf_count_le(C, beta0, step, N, tol, amb);
+                    if (i == nh - 1 && eh < N) amb = true; // the literal loop would wrap past the last slot
+                }
+                int eprev = __shfl_up_sync(0xffffffffu, eh, 1);
+                if (lane == 0) eprev = e_carry;
+                const int c = valid ? eh - eprev : 0;
+                const unsigned msk = __ballot_sync(0xffffffffu, c > 0);
+                if (c > 0) {
+                    rt[nr + __popc(msk & ((1u << lane) - 1u))] = make_int2(i, c);
+                    const long long sp = t * N + i; // head i's record, just written by the slot kernel
+                    const double2* __restrict__ src = a.st_new + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+                    const double m = (double)c;
+#pragma unroll
+                    for (int p = 0; p < D / 2; p++) {
+                        const double2 q = __ldg(src + L::po(p));
+                        xs[2 * p] = fma(m, q.x, xs[2 * p]);
+                        xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
+                    }
+                }
+                nr += __popc(msk);
+                const int lastl = (nh - i0 >= 32) ? 31 : (nh - i0 - 1);
+                e_carry = __shfl_sync(0xffffffffu, eh, lastl);
+                carry.hi = __shfl_sync(0xffffffffu, C.hi, 31); // lane 31's inclusive prefix (lanes beyond nh add zero)
+                carry.lo = __shfl_sync(0xffffffffu, C.lo, 31);
             }
-            const dd C = dd_add(carry, inc);
-            int eh = N;
-            if (valid) {
-                eh = mkf_count_le(C, beta0, step, N, tol2, amb);
-                if (i == nh - 1 && eh < N) amb = true; // the literal loop would wrap past the last slot
-            }
-            int eprev = __shfl_up_sync(0xffffffffu, eh, 1);
-            if (lane == 0) eprev = e_carry;
-            const int c = valid ? eh - eprev : 0;
-            const unsigned msk = __ballot_sync(0xffffffffu, c > 0);
-            if (c > 0) rt[nr + __popc(msk & ((1u << lane) - 1u))] = make_int2(i, c);
-            nr += __popc(msk);
-            const int lastl = (nh - i0 >= 32) ? 31 : (nh - i0 - 1);
-            e_carry = __shfl_sync(0xffffffffu, eh, lastl);
-            carry.hi = __shfl_sync(0xffffffffu, C.hi, 31); // lane 31's inclusive prefix (lanes beyond nh add zero)
-            carry.lo = __shfl_sync(0xffffffffu, C.lo, 31);
+            amb = __any_sync(0xffffffffu, amb);
+            if (!amb) break;
         }
-        if (__any_sync(0xffffffffu, amb)) {
+        xs_done = !amb;
+        if (amb) {
             // undecidable in closed form: the reference's loop itself (src/pf2DRao.cpp:195-207), slot by slot
             if (lane == 0) {
                 atomicOr(a.status + t, MKF_ST_POST_FALLBACK);
@@ -515,20 +582,20 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
     if (lane == 0) a.nruns[t] = nr;
     __syncwarp();
 
-    // estimator of the new set: sum over its runs of children x mean, / N; then the PCA reconstruction
-    double xs[D];
+    if (!xs_done) { // the rare branches (literal loop, cv::RNG indices) left only the run list: gather from it
 #pragma unroll
-    for (int e = 0; e < D; e++) xs[e] = 0.0;
-    for (int r = lane; r < nr; r += 32) {
-        const int2 rn = __ldcg(rt + r); // written by this warp just above
-        const long long sp = t * N + rn.x;
-        const double2* __restrict__ src = a.st_new + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
-        const double m = (double)rn.y;
+        for (int e = 0; e < D; e++) xs[e] = 0.0;
+        for (int r = lane; r < nr; r += 32) {
+            const int2 rn = __ldcg(rt + r); // written by lane 0 just above
+            const long long sp = t * N + rn.x;
+            const double2* __restrict__ src = a.st_new + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+            const double m = (double)rn.y;
 #pragma unroll
-        for (int p = 0; p < D / 2; p++) {
-            const double2 q = __ldg(src + L::po(p));
-            xs[2 * p] = fma(m, q.x, xs[2 * p]);
-            xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
+            for (int p = 0; p < D / 2; p++) {
+                const double2 q = __ldg(src + L::po(p));
+                xs[2 * p] = fma(m, q.x, xs[2 * p]);
+                xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
+            }
         }
     }
     const double inv_n = 1.0 / (double)N;
@@ -538,12 +605,10 @@ __global__ void __launch_bounds__(128) k_resample_runs(const ResampleRunsArgs a)
         for (int o = 16; o > 0; o >>= 1) xs[e] += __shfl_xor_sync(0xffffffffu, xs[e], o);
         xs[e] *= inv_n;
     }
-    const int R = a.Dpose + D;
     for (int r = lane; r < R; r += 32) {
-        const double* __restrict__ row = r < a.Dpose ? a.recon + r * D : a.tinv + (r - a.Dpose) * D;
         double sacc = 0.0;
 #pragma unroll
-        for (int c = 0; c < D; c++) sacc = fma(__ldg(row + c), xs[c], sacc);
+        for (int c = 0; c < D; c++) sacc = fma(coef[c * R + r], xs[c], sacc);
         if (r < a.Dpose) {
             const double v = sacc + __ldg(a.pmean + r);
             a.est_pose[t * a.Dpose + r] = v;
