@@ -70,6 +70,10 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            for _ in range(150):  # the first sample takes nvidia-smi about a second
+                if self.rows:
+                    break
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -87,6 +91,19 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.proc = None
+
+    def defer(self, t0, t1):
+        """a window to be summarised once sampling has stopped (resolve() replaces it in the result object)"""
+        return ("__clock_window__", t0, t1)
+
+    def resolve(self, obj):
+        if isinstance(obj, tuple) and len(obj) == 3 and obj[0] == "__clock_window__":
+            return self.window(obj[1], obj[2])
+        if isinstance(obj, dict):
+            return {k: self.resolve(v) for k, v in obj.items()}
+        if isinstance(obj, list):
+            return [self.resolve(v) for v in obj]
+        return obj
 
     def window(self, t0, t1):
         if not self.rows:
@@ -306,15 +323,17 @@ class Ctx:
     pass
 
 
-def timed_region(cx, fn, steps, warmup, tail=None):
+def timed_region(cx, fn, steps, warmup, tail=None, collective=True):
     """W untimed + K timed calls of fn(i), CUDA events on the launching stream, barrier + synchronize on both sides,
-    MAX over ranks.  `tail` runs once inside the timed region after the last step.  Returns (ms_total, t0, t1)."""
+    MAX over ranks.  `tail` runs once inside the timed region after the last step.  collective=False: a leg that only
+    rank 0 runs (no barrier, no reduction).  Returns (ms_total, t0, t1)."""
     torch, dist = cx.torch, cx.dist
+    sync = cx.barrier if collective else torch.cuda.synchronize
     for i in range(warmup):
         fn(i)
     if tail:
         tail()
-    cx.barrier()
+    sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
@@ -323,10 +342,10 @@ def timed_region(cx, fn, steps, warmup, tail=None):
     if tail:
         tail()
     e1.record()
-    cx.barrier()
+    sync()
     t1 = time.perf_counter()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=cx.dev)
-    if cx.world > 1:
+    if cx.world > 1 and collective:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item()), t0, t1
 
@@ -392,7 +411,7 @@ def leg_config2(cx, args):
     launches = mk.launch_count() - launches0
     prof = batch.profile_read_stages()
     batch.profile(0)
-    clocks = cx.clk.window(t0, t1) if rank == 0 else None
+    clocks = cx.clk.defer(t0, t1) if rank == 0 else None
     # repeat the timed region (same frames, fresh reset) and keep the median: K = 20 steps last ~3 ms
     reps = [ms]
     for _ in range(args.repeats - 1):
@@ -476,7 +495,7 @@ def leg_config2(cx, args):
         return {"steps": K2, "ms_per_step": ms2, "value": T * 1e3 / ms2, "unit": UNIT,
                 "slot_updates_per_s": T * N * 1e3 / ms2, "stage_ms": sm, "status_flagged_tracks": bad,
                 "roofline": roofline_of(cx, label_kernel, T * N, sm["slot_kernel"], sm["samples"]),
-                "clocks": cx.clk.window(ta, tb)}
+                "clocks": cx.clk.defer(ta, tb)}
 
     every_slot = literal = None
     if rank == 0 and not args.headline_only:
@@ -544,9 +563,9 @@ def leg_config3(cx, steps=12, warmup=3):
 
     for i in range(warmup):
         frame(i)
-    ms_a, _, _ = timed_region(cx, assoc_only, steps, 1)
+    ms_a, _, _ = timed_region(cx, assoc_only, steps, 1, collective=False)
     b0.profile((steps + 1) // 2, 2)
-    ms_f, t0, t1 = timed_region(cx, lambda i: frame(warmup + i), steps, 0)
+    ms_f, t0, t1 = timed_region(cx, lambda i: frame(warmup + i), steps, 0, collective=False)
     p0 = b0.profile_read_stages()
     b0.profile(0)
     rec, nslots = b0.shared_records()
@@ -568,7 +587,7 @@ def leg_config3(cx, steps=12, warmup=3):
             "roofline": roofline_of(cx, "k_slot_update_heads_direct<12> (left arm)" if sharing else "k_slot_update<12, 0>",
                                     rec if sharing else nslots, sm["slot_kernel"], sm["samples"],
                                     traffic_key="k_slot_update_heads_direct" if sharing else "k_slot_update"),
-            "clocks": cx.clk.window(t0, t1)}
+            "clocks": cx.clk.defer(t0, t1)}
 
 
 def leg_config4(cx, steps=8, warmup=3):
@@ -596,7 +615,7 @@ def leg_config4(cx, steps=8, warmup=3):
     for i in range(warmup):
         step(i)
     b.profile(steps, 1)
-    ms, t0, t1 = timed_region(cx, lambda i: step(warmup + i), steps, 0)
+    ms, t0, t1 = timed_region(cx, lambda i: step(warmup + i), steps, 0, collective=False)
     p = b.profile_read_stages()
     b.profile(0)
     st = b.status()
@@ -613,7 +632,7 @@ def leg_config4(cx, steps=8, warmup=3):
             "literal_loop_tracks_last_frame": fb,
             "roofline": roofline_of(cx, "k_slot_update<12, 0>", T * N, sm["slot_kernel"], sm["samples"],
                                     traffic_key="k_slot_update"),
-            "clocks": cx.clk.window(t0, t1)}
+            "clocks": cx.clk.defer(t0, t1)}
 
     # legacy plain particle filter, d = 8, K = 15 synthetic SPD GMM (no model file for it ships)
     d, K = 8, 15
@@ -638,7 +657,7 @@ def leg_config4(cx, steps=8, warmup=3):
     for i in range(warmup):
         pstep(i)
     pf.profile(steps)
-    msp, t0, t1 = timed_region(cx, pstep, steps, 0)
+    msp, t0, t1 = timed_region(cx, pstep, steps, 0, collective=False)
     pp = pf.profile_read()
     pf.profile(0)
     pf.close()
@@ -663,7 +682,7 @@ def leg_config4(cx, steps=8, warmup=3):
                                       "note": "the reference's unfused mul/add order is kept (bit-exact weights), so the "
                                               "kernel is FP64-issue bound, not HBM bound: ncu sm__inst_executed_pipe_fp64 "
                                               "in profiles/"}},
-            "clocks": cx.clk.window(t0, t1)}
+            "clocks": cx.clk.defer(t0, t1)}
     return out4, outp
 
 
@@ -760,7 +779,7 @@ def leg_config5(cx, steps=12, warmup=3):
             "stage_ms": sm, "status_flagged_tracks": bad,
             "roofline": roofline_of(cx, "k_slot_update<12, 0>", T * N, sm["slot_kernel"], sm["samples"],
                                     traffic_key="k_slot_update"),
-            "clocks": cx.clk.window(t0, t1)}
+            "clocks": cx.clk.defer(t0, t1)}
 
 
 def main():
@@ -802,7 +821,9 @@ def main():
         os.environ["NCCL_DEBUG"] = os.environ.get("MKF_NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # (a short collective timeout: a rank that dies must not leave the others waiting for ten minutes)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     # everything (our kernels, NCCL, the timing events) runs on ONE explicit stream: torch's default stream has
     # handle 0, which the C ABI reads as "make a private stream"
     cx.stream = torch.cuda.Stream(device=dev)
@@ -900,7 +921,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline(N)
         else:
             out["cpu_baseline"] = None
-        emit(out)
+        emit(cx.clk.resolve(out))
     cx.comm.close()
     if world > 1:
         dist.destroy_process_group()
