@@ -222,8 +222,9 @@ struct mkf_batch {
     const int32_t* cm_bins = nullptr;
     const double* cm_roi = nullptr;
     int cm_C = 0, cm_hand = 0;
+    const int32_t* cm_cuts = nullptr; // (T x 2) x 32 run boundaries of the candidate bins (k_resample_warp), or null
     DevBuf as_cand, as_L, as_roi, as_u, as_w, as_gate, as_bins, as_meas, as_wsum, as_hand, as_status, as_seed,
-        as_ui, as_up;
+        as_ui, as_up, as_cuts;
     int as_C = 0;
     // optional per-kernel timing (mkf_batch_profile): 4 events per update
     int stage = 3; // see SlotArgs::stage (mkf_kf_apply runs single stages)
@@ -317,7 +318,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     DevBuf* bufs[] = {&b->in_meas, &b->in_u0, &b->in_u1, &b->in_seed, &b->out_a,   &b->out_b,  &b->in_x,   &b->in_p,
                       &b->as_cand, &b->as_L,  &b->as_roi, &b->as_u,   &b->as_w,    &b->as_gate, &b->as_bins,
                       &b->as_meas, &b->as_wsum, &b->as_hand, &b->as_status, &b->as_seed, &b->pose_cache,
-                      &b->as_ui,   &b->as_up};
+                      &b->as_ui,   &b->as_up,  &b->as_cuts};
     for (DevBuf* d : bufs) d->release();
     b->aio.release();
     if (b->est_ready) cudaEventDestroy(b->est_ready);
@@ -588,8 +589,10 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
                         int u_stride, int normalise, double* d_wsum, int32_t* d_out, uint32_t* d_status,
                         const uint64_t* d_seeds, int seed_stride, int seed_off, uint32_t bit_fb, uint32_t bit_deg,
                         uint32_t* d_unsorted = nullptr, const int32_t* d_rep = nullptr, int32_t* d_src = nullptr,
-                        double* d_w_slot_out = nullptr, const double* d_wsum_in = nullptr)
+                        double* d_w_slot_out = nullptr, const double* d_wsum_in = nullptr, int32_t* d_cut_out = nullptr,
+                        bool* cuts_written = nullptr)
 {
+    if (cuts_written) *cuts_written = false;
     if (L <= 64 && N <= 64) {
         if (d_w_slot_out || d_wsum_in) {
             mkf_set_error("internal: per-record weights are not supported by the small-track resampler");
@@ -604,7 +607,8 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
     } else if (L <= 32 && !d_rep && !d_src && !d_w_slot_out && !d_wsum_in) {
         // few weights, many outputs (candidate resample): a warp per track
         mkf_launch(k_resample_warp, grid_for(nt, 4), 128, 0, stream, d_w, nt, L, N, d_u, u_stride, normalise, d_wsum, d_out,
-                   d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted);
+                   d_status, 1, bit_fb, bit_deg, d_seeds, seed_stride, seed_off, d_unsorted, d_cut_out);
+        if (cuts_written) *cuts_written = d_cut_out != nullptr;
     } else {
         // one CTA per track; wider CTAs for long weight / index vectors so a track's tiles are few
         const int span = L > N ? L : N;
@@ -689,8 +693,9 @@ static int heads_ctas_per_sm()
 }
 
 // one frame on a run-length particle set (mkf_runs.cuh): frame heads -> slot update of the heads -> repair -> resample
-static int update_device_runs(mkf_batch* b, const double* d_meas, const double* d_uind, const double* d_upost,
-                              const uint64_t* d_seeds, int seed_stride, int seed_off, cudaEvent_t* pe)
+static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layout, const double* d_uind,
+                              const double* d_upost, const uint64_t* d_seeds, int seed_stride, int seed_off,
+                              cudaEvent_t* pe)
 {
     const mkf_model* m = b->m;
     if (!b->run_mode) { // entering from a per-slot set (reset, upload, a per-slot frame): its run list
@@ -723,13 +728,19 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, const double* 
     f.nheads = b->nheads;
     f.hd16 = b->hd16;
     f.head_count = b->head_count + b->head_flip;
+    if (meas_layout == MKF_MEAS_CAND) {
+        f.bin_cuts = b->cm_cuts;
+        f.bins = b->cm_bins;
+        f.cand_C = b->cm_C;
+        f.hand = b->cm_hand;
+    }
     b->clear_status_next = false;
     mkf_launch(k_frame_heads, grid_for(b->T, MKF_FH_WARPS), 32 * MKF_FH_WARPS, 0, b->stream, f);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (pe) cudaEventRecord(pe[2], b->stream);
     SlotArgs a{};
-    fill_slot_args(b, a, d_meas, MKF_MEAS_SHARED);
+    fill_slot_args(b, a, d_meas, meas_layout);
     a.dedup = 1;
     a.split = 1;
     a.rep = nullptr;
@@ -825,8 +836,14 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
                         (meas_layout == MKF_MEAS_CAND && b->share_split && b->N > 64));
     // (tracks of <= 64 slots go to k_resample_small, which reads per-slot weights)
     const bool use_split = dedup && b->share_split && b->N > 64;
-    if (use_split && meas_layout == MKF_MEAS_SHARED && b->runs) {
-        rc = update_device_runs(b, d_meas, d_uind, d_upost, d_seeds, seed_stride, seed_off, pe);
+    // run-length pipeline: one measurement per track, or a few candidate columns whose bins came as run boundaries
+    if (use_split && b->runs &&
+        (meas_layout == MKF_MEAS_SHARED || (meas_layout == MKF_MEAS_CAND && b->cm_cuts && b->cm_C <= 32))) {
+        if (meas_layout == MKF_MEAS_CAND && (!b->cm_cand || !b->cm_bins || !b->cm_roi)) {
+            mkf_set_error("internal: MKF_MEAS_CAND without a candidate source");
+            return MKF_E_INVALID;
+        }
+        rc = update_device_runs(b, d_meas, meas_layout, d_uind, d_upost, d_seeds, seed_stride, seed_off, pe);
         if (prof && rc == MKF_OK) b->prof_n++;
         return rc;
     }

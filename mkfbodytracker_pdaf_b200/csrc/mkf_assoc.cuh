@@ -211,6 +211,7 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
         (rc = b->as_bins.ensure((size_t)T * 2 * N * sizeof(int32_t))) ||
         (rc = b->as_wsum.ensure((size_t)T * 2 * sizeof(double))) ||
         (rc = b->as_status.ensure((size_t)T * 2 * sizeof(uint32_t))) ||
+        (rc = b->as_cuts.ensure((size_t)T * 2 * 32 * sizeof(int32_t))) ||
         (!gather && (rc = b->as_meas.ensure((size_t)T * 2 * 6 * N * sizeof(double)))))
         return rc;
     b->as_C = C;
@@ -241,9 +242,11 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
     k_assoc_weights<<<grid_for(T * 2 * 32 * ((C + MKF_ASSOC_SPAN - 1) / MKF_ASSOC_SPAN), 128), 128, 0, b->stream>>>(aa);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    bool have_cuts = false; // few candidates: the bins also come as run boundaries (the run-length frame pipeline's input)
     if ((rc = run_resample(b->stream, T * 2, (const double*)b->as_w.p, C, N, d_uc, 1, 1,
                            (double*)b->as_wsum.p, (int32_t*)b->as_bins.p, (uint32_t*)b->as_status.p, d_seeds, 3, 0,
-                           MKF_ST_CAND_FALLBACK, MKF_ST_CAND_DEGENERATE)))
+                           MKF_ST_CAND_FALLBACK, MKF_ST_CAND_DEGENERATE, nullptr, nullptr, nullptr, nullptr, nullptr,
+                           (int32_t*)b->as_cuts.p, &have_cuts)))
         return rc;
     // With the update following at once the per-slot columns are not materialised: the slot kernels assemble a
     // slot's column from the ROI and the candidate its bin selects (MKF_MEAS_CAND; 4 bytes per slot instead of 48
@@ -287,8 +290,10 @@ extern "C" int mkf_batch_associate(mkf_batch* a0, mkf_batch* a1, int C, const do
         ab->cm_roi = d_roi;
         ab->cm_C = C;
         ab->cm_hand = h;
+        ab->cm_cuts = have_cuts ? (const int32_t*)b->as_cuts.p : nullptr;
         rc = update_device(ab, gather ? nullptr : (h ? d_meas1 : d_meas0), lay, ui[h], up[h], 1, d_seeds, 6, h ? 5 : 2);
         ab->cm_cand = nullptr;
+        ab->cm_cuts = nullptr;
         ab->cm_bins = nullptr;
         ab->cm_roi = nullptr;
         if (rc) return rc;

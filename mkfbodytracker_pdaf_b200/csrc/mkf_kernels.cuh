@@ -1409,8 +1409,12 @@ __global__ void __launch_bounds__(128) k_resample_warp(const double* __restrict_
                                                         uint32_t* __restrict__ status, int status_stride,
                                                         uint32_t bit_fb, uint32_t bit_deg,
                                                         const uint64_t* __restrict__ seeds, int seed_stride,
-                                                        int seed_off, uint32_t* __restrict__ unsorted)
+                                                        int seed_off, uint32_t* __restrict__ unsorted,
+                                                        int32_t* __restrict__ cut_out)
 {
+    // cut_out (T x 32, optional): e_k = number of outputs whose index is <= k, for k < L -- the outputs as L sorted runs
+    // (what k_frame_heads cuts the particle runs with); cut_out[t * 32] = -1 when the indices came from the literal
+    // loop or from cv::RNG and have to be read per output
     __shared__ double xn_s[4][32];
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
@@ -1437,6 +1441,7 @@ __global__ void __launch_bounds__(128) k_resample_warp(const double* __restrict_
             (void)rng.uniform_int(0, L); // `int idx = rng.uniform(0, L);` drawn and discarded
             for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, L);
             if (unsorted) unsorted[t] = 1u;
+            if (cut_out) cut_out[t * 32] = -1;
         }
         return;
     }
@@ -1470,9 +1475,11 @@ __global__ void __launch_bounds__(128) k_resample_warp(const double* __restrict_
             const double* xs = xn_s[wid];
             mkf_resample_sequential([&](int i) { return xs[i]; }, L, N, u[t * u_stride],
                                     [&](int i, int idx) { out[i] = idx; });
+            if (cut_out) cut_out[t * 32] = -1;
         }
         return;
     }
+    if (cut_out && lane < L) cut_out[t * 32 + lane] = e;
     for (int k = 0; k < L; k++) {
         const int lo = __shfl_sync(0xffffffffu, e_prev, k), hi = __shfl_sync(0xffffffffu, e, k);
         for (int i = lo + lane; i < hi; i += 32) out[i] = k;

@@ -83,6 +83,12 @@ struct FrameArgs {
     int* __restrict__ nheads;
     int4* __restrict__ hd16;
     int* __restrict__ head_count;
+    // MKF_MEAS_CAND (mkf_batch_associate with the update following): the slots of a track see the candidate their bin
+    // selects, so the bin joins the key -- bins are sorted like components, given as run boundaries (k_resample_warp's
+    // cut_out, 32 per (track, hand)); bins: the per-slot indices, read when the boundaries are flagged unusable
+    const int32_t* __restrict__ bin_cuts; // null: one measurement per track
+    const int32_t* __restrict__ bins;
+    int cand_C, hand;
 };
 
 // component of slot j = number of cuts <= j (cuts sorted, nc <= 63): branch-free binary search
@@ -97,9 +103,33 @@ __device__ __forceinline__ int mkf_cuts_le(const int* cuts, int nc, int j)
 
 constexpr int MKF_FH_WARPS = 8; // tracks per CTA of k_frame_heads
 
+// the pieces of one run [a, b): cut at every component boundary and every candidate-bin boundary inside it.
+// emit(key, length, first slot) per piece; returns the number of pieces.  key = component | bin << 8.
+template <class F>
+__device__ __forceinline__ int mkf_walk_pieces(const int* ccuts, int nc, const int* bcuts, int nb, int a, int b, int N,
+                                               F emit)
+{
+    int kc = mkf_cuts_le(ccuts, nc, a), kb = nb > 0 ? mkf_cuts_le(bcuts, nb, a) : 0;
+    int pos = a, np = 0;
+    for (;;) {
+        const int cc = kc < nc ? ccuts[kc] : N;
+        const int cb = kb < nb ? bcuts[kb] : N;
+        const int nx = cc < cb ? cc : cb;
+        const int end = nx < b ? nx : b;
+        emit(kc | (kb << 8), end - pos, pos, np);
+        np++;
+        if (nx >= b) break;
+        pos = nx;
+        while (kc < nc && ccuts[kc] <= pos) kc++;
+        while (kb < nb && bcuts[kb] <= pos) kb++;
+    }
+    return np;
+}
+
 __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameArgs f)
 {
     __shared__ int cuts_s[MKF_FH_WARPS][64];
+    __shared__ int bcuts_s[MKF_FH_WARPS][32];
     __shared__ int nh_s[MKF_FH_WARPS];
     __shared__ int base_s;
     mkf_pdl_launch_dependents();
@@ -116,11 +146,21 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
     if (32 + lane < nr) rn1 = rt[32 + lane];
     int nh = 0;
     int mode = 0; // 1: fast path (pieces still to be written, in one walk with the work list), 2: head table written
-    int a_[2] = {0, 0}, b_[2] = {0, 0}, k0_[2] = {0, 0}, h0_[2] = {0, 0};
+    int a_[2] = {0, 0}, b_[2] = {0, 0}, h0_[2] = {0, 0};
     int* cuts = cuts_s[wid];
+    int* bcuts = bcuts_s[wid];
     const int nc = K - 1; // cut q = first slot whose component exceeds q
+    int nb = 0;           // likewise for the candidate bins
     const int tN = (int)((live_t ? t : 0) * N);
     if (live_t) {
+        bool bins_per_slot = false;
+        if (f.bin_cuts) {
+            const int32_t* bc = f.bin_cuts + (t * 2 + f.hand) * 32;
+            nb = f.cand_C - 1;
+            const int v = lane < nb ? bc[lane] : 0;
+            bins_per_slot = __shfl_sync(0xffffffffu, (lane == 0 ? bc[0] : 0), 0) < 0;
+            if (lane < nb) bcuts[lane] = v;
+        }
         // the K -> N indicator draw: the lanes of this warp are the group of k_indicator_bounds<32>
         int e_lo, e_hi;
         const bool closed = mkf_indicator_bounds_group<32>(t, lane, true, f.u_ind, N, K, f.cw_hi, f.cw_lo, f.wprior, f.wmax,
@@ -137,7 +177,8 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
             wrap_from = __ldcg(bt + K);
         }
         __syncwarp();
-        if (wrap_from >= N && nr <= 64) {
+        const bool sorted_keys = wrap_from >= N && !bins_per_slot;
+        if (sorted_keys && nr <= 64) {
             // the common case: the track's runs fit two per lane; count the pieces first
             mode = 1;
             int pos_carry = 0;
@@ -152,19 +193,7 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
                     if (lane >= o) inc += n;
                 }
                 const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
-                int k0 = 0, np = 0;
-                if (live) {
-                    k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
-                    // one more piece per component change inside the run; empty components (equal cuts) change
-                    // nothing: count the distinct cut positions in (a, b)
-                    int k = k0, cnt = 0;
-                    while (k < nc && cuts[k] < b) {
-                        const int cpos = cuts[k];
-                        cnt++;
-                        while (k < nc && cuts[k] == cpos) k++;
-                    }
-                    np = 1 + cnt;
-                }
+                const int np = live ? mkf_walk_pieces(cuts, nc, bcuts, nb, a, b, N, [](int, int, int, int) {}) : 0;
                 int pinc = np;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -173,12 +202,11 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
                 }
                 a_[c] = a;
                 b_[c] = b;
-                k0_[c] = k0;
                 h0_[c] = nh + pinc - np;
                 nh += __shfl_sync(0xffffffffu, pinc, 31);
                 pos_carry += __shfl_sync(0xffffffffu, inc, 31);
             }
-        } else if (wrap_from >= N) {
+        } else if (sorted_keys) {
             mode = 2;
             int pos_carry = 0;
             for (int r0 = 0; r0 < nr; r0 += 32) {
@@ -191,17 +219,7 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
                     if (lane >= o) inc += n;
                 }
                 const int a = pos_carry + inc - rn.y, b = a + rn.y; // this run's slots [a, b)
-                int k0 = 0, np = 0;
-                if (r < nr) {
-                    k0 = mkf_cuts_le(cuts, nc, a); // component of slot a
-                    int k = k0;
-                    for (;;) {
-                        np++;
-                        const int c = k < nc ? cuts[k] : N;
-                        if (c >= b) break;
-                        while (k < nc && cuts[k] <= c) k++;
-                    }
-                }
+                const int np = r < nr ? mkf_walk_pieces(cuts, nc, bcuts, nb, a, b, N, [](int, int, int, int) {}) : 0;
                 int pinc = np;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -209,33 +227,31 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
                     if (lane >= o) pinc += n;
                 }
                 if (r < nr) {
-                    int h = nh + pinc - np, k = k0, pos = a;
-                    for (;;) {
-                        const int c = k < nc ? cuts[k] : N;
-                        const int end = c < b ? c : b;
-                        hm[h++] = make_int4(rn.x, k, end - pos, pos);
-                        if (c >= b) break;
-                        pos = c;
-                        while (k < nc && cuts[k] <= c) k++;
-                    }
+                    const int h0 = nh + pinc - np;
+                    mkf_walk_pieces(cuts, nc, bcuts, nb, a, b, N, [&](int key, int len, int pos, int q) {
+                        hm[h0 + q] = make_int4(rn.x, key, len, pos);
+                    });
                 }
                 nh += __shfl_sync(0xffffffffu, pinc, 31);
                 pos_carry += __shfl_sync(0xffffffffu, inc, 31);
             }
         } else {
-            // the draw wrapped past the last component (prior mass short of the thresholds): components per slot
+            // keys that are not sorted in the slot index -- the indicator draw wrapped past the last component (prior
+            // mass short of the thresholds), or the candidate bins came from the literal loop / cv::RNG: read per slot
             mode = 2;
             if (lane == 0) {
                 const uint8_t* tail = f.ind_tail ? f.ind_tail + t * N : nullptr;
+                const int32_t* bj = f.bins ? f.bins + (t * 2 + f.hand) * (long long)N : nullptr;
+                auto key_of = [&](int j) { return mkf_component_of(bt, K, j, tail) | ((bj ? bj[j] : 0) << 8); };
                 int pos = 0;
                 for (int r = 0; r < nr; r++) {
                     const int2 rn = rt[r];
                     int j = pos;
                     const int b = pos + rn.y;
                     while (j < b) {
-                        const int k = mkf_component_of(bt, K, j, tail);
+                        const int k = key_of(j);
                         int j2 = j + 1;
-                        while (j2 < b && mkf_component_of(bt, K, j2, tail) == k) j2++;
+                        while (j2 < b && key_of(j2) == k) j2++;
                         hm[nh++] = make_int4(rn.x, k, j2 - j, j);
                         j = j2;
                     }
@@ -245,8 +261,7 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
             nh = __shfl_sync(0xffffffffu, nh, 0);
         }
     }
-    // one atomicAdd per CTA reserves its tracks' stretch of the batch-wide work list (order immaterial); 4096
-    // same-address atomics, one per track, were what the kernel waited for
+    // one atomicAdd per CTA reserves its tracks' stretch of the batch-wide work list (order immaterial)
     if (lane == 0) {
         nh_s[wid] = nh;
         if (live_t) f.nheads[t] = nh;
@@ -266,18 +281,11 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
         for (int c = 0; c < 2; c++) {
             if (c * 32 + lane < nr) {
                 const int rec = c ? rn1.x : rn0.x;
-                const int b = b_[c];
-                int h = h0_[c], k = k0_[c], pos = a_[c];
-                for (;;) {
-                    const int cpos = k < nc ? cuts[k] : N;
-                    const int end = cpos < b ? cpos : b;
-                    hm[h] = make_int4(rec, k, end - pos, pos);
-                    f.hd16[lb + h] = make_int4(tN + rec, tN + h, (int)t, k);
-                    h++;
-                    if (cpos >= b) break;
-                    pos = cpos;
-                    while (k < nc && cuts[k] <= cpos) k++;
-                }
+                const int h0 = h0_[c];
+                mkf_walk_pieces(cuts, nc, bcuts, nb, a_[c], b_[c], N, [&](int key, int len, int pos, int q) {
+                    hm[h0 + q] = make_int4(rec, key, len, pos);
+                    f.hd16[lb + h0 + q] = make_int4(tN + rec, tN + h0 + q, (int)t, key);
+                });
             }
         }
     } else if (mode == 2) {
@@ -322,7 +330,10 @@ __global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const 
                 if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
             }
             double zc[MKF_M], w;
-            mkf_load_meas(a, t, 0, zc);
+            if (a.meas_layout == MKF_MEAS_CAND)
+                mkf_load_meas_cand(a, t, m.y >> 8, zc); // the column of the head's candidate bin
+            else
+                mkf_load_meas(a, t, 0, zc);
             slot_math<D, true>(v, a.comp_const + (long long)(m.y & 0xff) * L::CS, zc, a.r, a.chol_mode, a.stage, w);
             double2* dst = a.st_out + (so >> 5) * (long long)L::TILE2 + (so & 31) * L::H;
             for (int p = 0; p < L::NP; p++) {
