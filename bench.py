@@ -794,6 +794,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=5, help="repetitions of the timed region (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="config 2 only (skip the other configs' legs)")
+    ap.add_argument("--legs", default="3,4,5", help="which of the other configs' legs to run (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -845,12 +846,15 @@ def main():
     if rank == 0:
         cx.clk.start()
 
+    legs = set() if args.headline_only else set(args.legs.split(","))
     c2 = leg_config2(cx, args)
-    c5 = leg_config5(cx) if not args.headline_only else None
+    c5 = leg_config5(cx) if "5" in legs else None
     c3 = c4 = pf = None
-    if rank == 0 and not args.headline_only:  # single-GPU legs (independent persons: they scale like config 2)
-        c3 = leg_config3(cx)
-        c4, pf = leg_config4(cx)
+    if rank == 0:  # single-GPU legs (independent persons: they scale like config 2)
+        if "3" in legs:
+            c3 = leg_config3(cx)
+        if "4" in legs:
+            c4, pf = leg_config4(cx)
     if rank == 0:
         cx.clk.stop()
     barrier()
