@@ -735,40 +735,11 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         f.hand = b->cm_hand;
     }
     b->clear_status_next = false;
-    mkf_launch(k_frame_heads, grid_for(b->T, MKF_FH_WARPS), 32 * MKF_FH_WARPS, 0, b->stream, f);
-    MKF_LAUNCHED();
-    CK(cudaGetLastError());
-    if (pe) cudaEventRecord(pe[2], b->stream);
     SlotArgs a{};
     fill_slot_args(b, a, d_meas, meas_layout);
     a.dedup = 1;
     a.split = 1;
     a.rep = nullptr;
-    const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
-    {
-        static std::atomic<uint64_t> seen{0};
-        if (first_on_this_device(seen)) {
-            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        }
-    }
-    const unsigned hgrid = (unsigned)(heads_ctas_per_sm() * sm_count(b->device));
-    if (m->d == 12) {
-        mkf_launch(k_slot_update_heads_direct<12>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
-        MKF_LAUNCHED();
-        if (pe) cudaEventRecord(pe[3], b->stream);
-        mkf_launch(k_runs_repair<12>, grid_for(b->T, 128), 128, 0, b->stream, a, (const int4*)b->hmeta, (const int*)b->nheads);
-    } else {
-        mkf_launch(k_slot_update_heads_direct<10>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
-        MKF_LAUNCHED();
-        if (pe) cudaEventRecord(pe[3], b->stream);
-        mkf_launch(k_runs_repair<10>, grid_for(b->T, 128), 128, 0, b->stream, a, (const int4*)b->hmeta, (const int*)b->nheads);
-    }
-    b->head_flip ^= 1;
-    MKF_LAUNCHED();
-    CK(cudaGetLastError());
-    if (pe) cudaEventRecord(pe[4], b->stream);
-    b->cur ^= 1;
     ResampleRunsArgs ra{};
     ra.T = b->T;
     ra.N = b->N;
@@ -788,7 +759,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     // the estimate of the new set goes to the other slot (a host copy of the previous one may be in flight)
     b->est_slot ^= 1;
     if (b->est_used[b->est_slot]) CK(cudaStreamWaitEvent(b->stream, b->est_done[b->est_slot], 0));
-    ra.st_new = b->st[b->cur];
+    ra.st_new = b->st[b->cur ^ 1];
     ra.Dpose = m->D;
     ra.recon = b->d_recon;
     ra.pmean = b->d_pmean;
@@ -796,13 +767,72 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     ra.est_xbar = b->est[b->est_slot];
     ra.est_pose = b->est[b->est_slot] + (size_t)b->T * m->d;
     ra.est_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
+    const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
     const size_t coef_bytes = (size_t)(m->D + m->d) * m->d * sizeof(double);
+    {
+        static std::atomic<uint64_t> seen{0};
+        if (first_on_this_device(seen)) {
+            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update_heads_direct<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_frame_fused<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            CK(cudaFuncSetAttribute(k_frame_fused<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        }
+    }
+    // MKF_FUSED=0: the three grid-wide kernels (k_frame_heads, k_slot_update_heads_direct, k_resample_runs) instead of
+    // the single-launch frame kernel (A/B runs, profiles)
+    static const bool fused = [] {
+        const char* e = getenv("MKF_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    if (fused) {
+        // persistent grid: 2 CTAs of 4 warps per SM, but no more warps than tracks
+        long long ctas = 2ll * sm_count(b->device);
+        if (ctas * 4 > b->T) ctas = (b->T + 3) / 4;
+        if (m->d == 12)
+            mkf_launch(k_frame_fused<12>, (unsigned)ctas, 128, smem + coef_bytes, b->stream, f, a, ra);
+        else
+            mkf_launch(k_frame_fused<10>, (unsigned)ctas, 128, smem + coef_bytes, b->stream, f, a, ra);
+        MKF_LAUNCHED();
+        CK(cudaGetLastError());
+        if (pe) {
+            cudaEventRecord(pe[2], b->stream); // (one kernel: reported as the slot-kernel stage)
+            cudaEventRecord(pe[3], b->stream);
+        }
+    } else {
+        mkf_launch(k_frame_heads, grid_for(b->T, MKF_FH_WARPS), 32 * MKF_FH_WARPS, 0, b->stream, f);
+        MKF_LAUNCHED();
+        CK(cudaGetLastError());
+        if (pe) cudaEventRecord(pe[2], b->stream);
+        const unsigned hgrid = (unsigned)(heads_ctas_per_sm() * sm_count(b->device));
+        if (m->d == 12)
+            mkf_launch(k_slot_update_heads_direct<12>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
+        else
+            mkf_launch(k_slot_update_heads_direct<10>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
+        b->head_flip ^= 1;
+        MKF_LAUNCHED();
+        CK(cudaGetLastError());
+        if (pe) cudaEventRecord(pe[3], b->stream);
+    }
+    // flagged tracks (cv::Cholesky failure) are redone with the literal failure semantics; after the fused kernel, which
+    // leaves them unresampled, their resample happens here too
     if (m->d == 12)
-        mkf_launch(k_resample_runs<12>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
+        mkf_launch(k_runs_repair<12>, grid_for(b->T, 128), 128, coef_bytes, b->stream, a, (const int4*)b->hmeta,
+                   (const int*)b->nheads, ra, fused ? 1 : 0);
     else
-        mkf_launch(k_resample_runs<10>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
+        mkf_launch(k_runs_repair<10>, grid_for(b->T, 128), 128, coef_bytes, b->stream, a, (const int4*)b->hmeta,
+                   (const int*)b->nheads, ra, fused ? 1 : 0);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
+    if (pe) cudaEventRecord(pe[4], b->stream);
+    b->cur ^= 1;
+    if (!fused) {
+        if (m->d == 12)
+            mkf_launch(k_resample_runs<12>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
+        else
+            mkf_launch(k_resample_runs<10>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
+        MKF_LAUNCHED();
+        CK(cudaGetLastError());
+    }
     if (pe) cudaEventRecord(pe[5], b->stream);
     b->shared = true;
     b->slots_valid = false;

@@ -297,56 +297,6 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
     }
 }
 
-// literal cv::Cholesky-failure semantics for flagged tracks, head by head (see k_slot_update_repair)
-template <int D>
-__global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const int4* __restrict__ hmeta,
-                                                        const int* __restrict__ nheads)
-{
-    using L = SlotLay<D>;
-    __shared__ uint32_t flags[128];
-    mkf_pdl_launch_dependents();
-    mkf_pdl_wait();
-    const long long T = a.total / a.N;
-    const long long base = (long long)blockIdx.x * 128;
-    {
-        const long long t = base + threadIdx.x;
-        uint32_t fl = 0;
-        if (t < T) fl = (a.status[t] & MKF_ST_CHOL_FAIL) ? 1u : 0u;
-        flags[threadIdx.x] = fl;
-        if (!__syncthreads_or((int)fl)) return;
-    }
-    for (int q = 0; q < 128; q++) {
-        if (!flags[q]) continue;
-        const long long t = base + q;
-        const int nh = nheads[t];
-        for (int i = threadIdx.x; i < nh; i += 128) {
-            const int4 m = hmeta[t * a.N + i];
-            const long long sp = t * a.N + m.x, so = t * a.N + i;
-            const double2* src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
-            double v[L::NE];
-            for (int p = 0; p < L::NP; p++) {
-                const double2 qq = src[L::po(p)];
-                v[2 * p] = qq.x;
-                if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
-            }
-            double zc[MKF_M], w;
-            if (a.meas_layout == MKF_MEAS_CAND)
-                mkf_load_meas_cand(a, t, m.y >> 8, zc); // the column of the head's candidate bin
-            else
-                mkf_load_meas(a, t, 0, zc);
-            slot_math<D, true>(v, a.comp_const + (long long)(m.y & 0xff) * L::CS, zc, a.r, a.chol_mode, a.stage, w);
-            double2* dst = a.st_out + (so >> 5) * (long long)L::TILE2 + (so & 31) * L::H;
-            for (int p = 0; p < L::NP; p++) {
-                double2 qq;
-                qq.x = v[2 * p];
-                qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-                dst[L::po(p)] = qq;
-            }
-            a.w_rec[so] = w;
-        }
-    }
-}
-
 __device__ __forceinline__ dd dd_shfl_xor(dd v, int o)
 {
     dd r;
@@ -404,26 +354,18 @@ struct ResampleRunsArgs {
     double* __restrict__ est_pose2; // the association step's copy of the pose (or null)
 };
 
+// One track, by one warp (every lane enters).  coef: the reconstruction coefficients staged in shared memory as
+// [c][r], r < Dpose + D (rows of recon, then rows of tinv).  The head table and the weights may have been written by
+// this very warp a moment ago (k_frame_fused), so they are read past the L1 (ld.global.cg).
 template <int D>
-__global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs a)
+__device__ __forceinline__ void mkf_resample_runs_track(const ResampleRunsArgs& a, const long long t, const int lane,
+                                                        const double* coef, const int nh)
 {
     using L = SlotLay<D>;
-    extern __shared__ double coef[]; // [c][r], r < Dpose + D: rows of recon (pose) then rows of tinv (xbar)
-    mkf_pdl_launch_dependents();
     const int R = a.Dpose + D;
-    for (int i = threadIdx.x; i < R * D; i += 128) { // model constants: safe before the dependency wait
-        const int r = i / D, c = i - r * D;
-        coef[c * R + r] = r < a.Dpose ? a.recon[r * D + c] : a.tinv[(r - a.Dpose) * D + c];
-    }
-    mkf_pdl_wait();
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (t >= a.T) return;
     const int N = a.N;
-    const int nh = a.nheads[t];
-    const int4* __restrict__ hm = a.hmeta + t * N;
-    const double* __restrict__ wr = a.w_rec + t * N;
+    const int4* hm = a.hmeta + t * N;
+    const double* wr = a.w_rec + t * N;
     int2* rt = a.runs + t * N;
     // estimator of the new set (sum over its runs of children x mean): gathered as soon as a head's children are known
     double xs[D];
@@ -434,7 +376,7 @@ __global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs
     dd acc = dd_make(0.0);
     double mx = 0.0, sq = 0.0;
     for (int i = lane; i < nh; i += 32) {
-        const double w = wr[i], md = (double)hm[i].z;
+        const double w = __ldcg(wr + i), md = (double)__ldcg(&hm[i].z);
         acc = dd_add_pos(acc, dd_mul_exact(md, w));
         if (w > mx) mx = w;
         sq = fma(__dmul_rn(md, w), w, sq);
@@ -466,7 +408,7 @@ __global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs
                 int lo = 0, hi = nh - 1;
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (hm[mid].w <= idx)
+                    if (__ldcg(&hm[mid].w) <= idx)
                         lo = mid;
                     else
                         hi = mid - 1;
@@ -507,8 +449,8 @@ __global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs
             for (int i0 = 0; i0 < nh; i0 += 32) {
                 const int i = i0 + lane;
                 const bool valid = i < nh;
-                const double wn = valid ? __ddiv_rn(wr[i], wsum) : 0.0; // the normalised weight of each of the head's slots
-                const double md = valid ? (double)hm[i].z : 0.0;
+                const double wn = valid ? __ddiv_rn(__ldcg(wr + i), wsum) : 0.0; // normalised weight of each of the head's slots
+                const double md = valid ? (double)__ldcg(&hm[i].z) : 0.0;
                 dd C;
                 if (pass == 0) {
                     double inc = __dmul_rn(md, wn);
@@ -562,8 +504,8 @@ __global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs
             // undecidable in closed form: the reference's loop itself (src/pf2DRao.cpp:195-207), slot by slot
             if (lane == 0) {
                 atomicOr(a.status + t, MKF_ST_POST_FALLBACK);
-                int h = 0, left = hm[0].z;
-                double wi = __ddiv_rn(wr[0], wsum);
+                int h = 0, left = __ldcg(&hm[0].z);
+                double wi = __ddiv_rn(__ldcg(wr), wsum);
                 double beta = beta0;
                 int cur = -1, cnt = 0;
                 nr = 0;
@@ -572,8 +514,8 @@ __global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs
                         beta = __dsub_rn(beta, wi);
                         if (--left == 0) { // idx = (idx + 1) % L moved on to the next head's first slot
                             h = (h + 1 == nh) ? 0 : h + 1;
-                            left = hm[h].z;
-                            wi = __ddiv_rn(wr[h], wsum);
+                            left = __ldcg(&hm[h].z);
+                            wi = __ddiv_rn(__ldcg(wr + h), wsum);
                         }
                     }
                     beta = __dadd_rn(beta, step);
@@ -626,6 +568,289 @@ __global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs
             if (a.est_pose2) a.est_pose2[t * a.Dpose + r] = v;
         } else {
             a.est_xbar[t * D + (r - a.Dpose)] = sacc;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs a)
+{
+    extern __shared__ double coef[]; // [c][r], r < Dpose + D: rows of recon (pose) then rows of tinv (xbar)
+    mkf_pdl_launch_dependents();
+    const int R = a.Dpose + D;
+    for (int i = threadIdx.x; i < R * D; i += 128) { // model constants: safe before the dependency wait
+        const int r = i / D, c = i - r * D;
+        coef[c * R + r] = r < a.Dpose ? a.recon[r * D + c] : a.tinv[(r - a.Dpose) * D + c];
+    }
+    mkf_pdl_wait();
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= a.T) return;
+    mkf_resample_runs_track<D>(a, t, threadIdx.x & 31, coef, a.nheads[t]);
+}
+
+// -----------------------------------------------------------------------------------------
+// The whole frame in ONE launch.  k_frame_heads / k_slot_update_heads_direct / k_resample_runs are three grid-wide
+// phases, but nothing in a frame couples two tracks: a warp can take a few tracks through all three phases on its own
+// -- head table (K -> N draw, runs cut at the component boundaries), predict + likelihood + update of those heads (one
+// lane per head, the heads of the warp's tracks packed into full steps of 32), weight sum / resample / estimate -- with
+// no grid-wide dependency, no work list and no atomics.  The bookkeeping phases are latency chains of a few
+// microseconds; here they run in the shadow of the other resident warps' slot arithmetic instead of as separate
+// kernels in front of and behind it, and the warps of an SM drift out of phase, which the grid-wide version's
+// load-all / compute-all / store-all rhythm never did.
+//   Tracks are block-partitioned over the warps of a persistent grid (2 CTAs of 4 warps per SM); a warp works through
+//   its block in groups of up to MKF_FUSE_G tracks.  The head table, weights and run lists live in global memory
+//   exactly as in the three-kernel pipeline (they are L2-resident and the per-slot replay reads them later).
+//   A cv::Cholesky failure (never seen on real data) only flags the track: k_runs_repair redoes it AND its resample.
+// -----------------------------------------------------------------------------------------
+constexpr int MKF_FUSE_G = 4;
+
+// the head table of one track (same result as k_frame_heads, without the batch-wide work list); every lane enters
+__device__ __forceinline__ int mkf_frame_heads_track(const FrameArgs& f, const long long t, const int lane, int* cuts,
+                                                     int* bcuts)
+{
+    const int N = f.N, K = f.K;
+    const int2* rt = f.runs + t * N;
+    int4* hm = f.hmeta + t * N;
+    const int nr = __ldcg(f.nruns + t);
+    const int nc = K - 1;
+    int nb = 0;
+    bool bins_per_slot = false;
+    if (f.bin_cuts) {
+        const int32_t* bc = f.bin_cuts + (t * 2 + f.hand) * 32;
+        nb = f.cand_C - 1;
+        const int v = lane < nb ? bc[lane] : 0;
+        bins_per_slot = __shfl_sync(0xffffffffu, (lane == 0 ? bc[0] : 0), 0) < 0;
+        if (lane < nb) bcuts[lane] = v;
+    }
+    int e_lo, e_hi;
+    const bool closed = mkf_indicator_bounds_group<32>(t, lane, true, f.u_ind, N, K, f.cw_hi, f.cw_lo, f.wprior, f.wmax,
+                                                       f.bounds, f.status, f.clear_status, f.ind_tail, e_lo, e_hi);
+    const bool fast = __all_sync(0xffffffffu, closed);
+    const int32_t* bt = f.bounds + t * (K + 2);
+    int wrap_from = N;
+    if (fast) {
+        if (lane < nc) cuts[lane] = e_lo;
+        if (32 + lane < nc) cuts[32 + lane] = e_hi;
+    } else {
+        __syncwarp();
+        for (int q = lane; q < nc; q += 32) cuts[q] = __ldcg(bt + q);
+        wrap_from = __ldcg(bt + K);
+    }
+    __syncwarp();
+    int nh = 0;
+    if (wrap_from >= N && !bins_per_slot) {
+        int pos_carry = 0;
+        for (int r0 = 0; r0 < nr; r0 += 32) {
+            const int r = r0 + lane;
+            const int2 rn = r < nr ? __ldcg(rt + r) : make_int2(0, 0);
+            int inc = rn.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            const int a = pos_carry + inc - rn.y, b = a + rn.y;
+            const int np = r < nr ? mkf_walk_pieces(cuts, nc, bcuts, nb, a, b, N, [](int, int, int, int) {}) : 0;
+            int pinc = np;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, pinc, o);
+                if (lane >= o) pinc += n;
+            }
+            if (r < nr) {
+                const int h0 = nh + pinc - np;
+                mkf_walk_pieces(cuts, nc, bcuts, nb, a, b, N,
+                                [&](int key, int len, int pos, int q) { hm[h0 + q] = make_int4(rn.x, key, len, pos); });
+            }
+            nh += __shfl_sync(0xffffffffu, pinc, 31);
+            pos_carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    } else {
+        if (lane == 0) {
+            const uint8_t* tail = f.ind_tail ? f.ind_tail + t * N : nullptr;
+            const int32_t* bj = f.bins ? f.bins + (t * 2 + f.hand) * (long long)N : nullptr;
+            auto key_of = [&](int j) { return mkf_component_of(bt, K, j, tail) | ((bj ? bj[j] : 0) << 8); };
+            int pos = 0;
+            for (int r = 0; r < nr; r++) {
+                const int2 rn = __ldcg(rt + r);
+                int j = pos;
+                const int b = pos + rn.y;
+                while (j < b) {
+                    const int k = key_of(j);
+                    int j2 = j + 1;
+                    while (j2 < b && key_of(j2) == k) j2++;
+                    hm[nh++] = make_int4(rn.x, k, j2 - j, j);
+                    j = j2;
+                }
+                pos = b;
+            }
+        }
+        nh = __shfl_sync(0xffffffffu, nh, 0);
+    }
+    if (lane == 0) f.nheads[t] = nh;
+    __syncwarp();
+    return nh;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 2) k_frame_fused(const FrameArgs f, const SlotArgs a, const ResampleRunsArgs ra)
+{
+    using L = SlotLay<D>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cst = reinterpret_cast<double*>(smem_raw);          // K x CS model constants (TMA)
+    double* coef = cst + a.K * L::CS;                            // (Dpose + D) x D reconstruction coefficients
+    __shared__ int cuts_s[4][64];
+    __shared__ int bcuts_s[4][32];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t cbytes = (uint32_t)(a.K * L::CS * sizeof(double));
+    if (tid == 0) mkf_mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mkf_mbar_expect_tx(&mbar, cbytes);
+        mkf_tma_load_1d(cst, a.comp_const, cbytes, &mbar); // model constants: never written by the frame chain
+    }
+    const int R = ra.Dpose + D;
+    for (int i = tid; i < R * D; i += 128) {
+        const int r = i / D, c = i - r * D;
+        coef[c * R + r] = r < ra.Dpose ? ra.recon[r * D + c] : ra.tinv[(r - ra.Dpose) * D + c];
+    }
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    __syncthreads();
+    mkf_mbar_wait(&mbar, 0);
+
+    // this warp's block of tracks
+    const long long nwarps = (long long)gridDim.x * 4, w = (long long)blockIdx.x * 4 + wid;
+    const long long t_begin = f.T * w / nwarps, t_end = f.T * (w + 1) / nwarps;
+    const int N = f.N;
+    for (long long t0 = t_begin; t0 < t_end; t0 += MKF_FUSE_G) {
+        const int ng = (int)((t_end - t0) < MKF_FUSE_G ? (t_end - t0) : MKF_FUSE_G);
+        // phase 1: head tables
+        int nh[MKF_FUSE_G], hsum = 0;
+#pragma unroll
+        for (int g = 0; g < MKF_FUSE_G; g++) {
+            nh[g] = 0;
+            if (g < ng) nh[g] = mkf_frame_heads_track(f, t0 + g, lane, cuts_s[wid], bcuts_s[wid]);
+            hsum += nh[g];
+        }
+        // phase 2: one lane per head, the group's heads packed into steps of 32
+        for (int q0 = 0; q0 < hsum; q0 += 32) {
+            int q = q0 + lane;
+            if (q < hsum) {
+                int g = 0;
+#pragma unroll
+                for (int gg = 0; gg < MKF_FUSE_G - 1; gg++)
+                    if (g == gg && q >= nh[gg]) {
+                        q -= nh[gg];
+                        g = gg + 1;
+                    }
+                const long long t = t0 + g;
+                const int4 m = __ldcg(f.hmeta + t * N + q);
+                const long long sp = t * N + m.x, so_rec = t * N + q;
+                const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+                double v[L::NE];
+#pragma unroll
+                for (int p = 0; p < L::NP; p++) {
+                    const double2 qq = __ldg(src + L::po(p));
+                    v[2 * p] = qq.x;
+                    if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
+                }
+                double zc[MKF_M];
+                if (a.meas_layout == MKF_MEAS_CAND)
+                    mkf_load_meas_cand(a, t, m.y >> 8, zc); // the column of the head's candidate bin
+                else
+                    mkf_load_meas(a, t, 0, zc); // shared layout: the track's column
+                double wgt;
+                const bool ok = slot_math<D, false>(v, cst + (m.y & 0xff) * L::CS, zc, a.r, a.chol_mode, a.stage, wgt);
+                if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+                double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)L::TILE2 + (so_rec & 31) * L::H;
+#pragma unroll
+                for (int p = 0; p < L::NP; p++) {
+                    double2 qq;
+                    qq.x = v[2 * p];
+                    qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                    __stcg(dst + L::po(p), qq); // (read back below for the estimate: keep it in L2)
+                }
+                __stcg(a.w_rec + so_rec, wgt);
+            }
+        }
+        __syncwarp();
+        // phase 3: weight sum, resample, estimate
+#pragma unroll
+        for (int g = 0; g < MKF_FUSE_G; g++) {
+            if (g < ng) {
+                const long long t = t0 + g;
+                const uint32_t st = __ldcg(a.status + t); // (a failure flagged by one of this warp's lanes above)
+                if (!(st & MKF_ST_CHOL_FAIL)) mkf_resample_runs_track<D>(ra, t, lane, coef, nh[g]);
+            }
+        }
+    }
+}
+
+// literal cv::Cholesky-failure semantics for flagged tracks, head by head (see k_slot_update_repair)
+// ra (optional): the fused frame kernel skipped the resample of a flagged track -- done here after its heads
+template <int D>
+__global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const int4* __restrict__ hmeta,
+                                                        const int* __restrict__ nheads, const ResampleRunsArgs ra,
+                                                        int with_resample)
+{
+    using L = SlotLay<D>;
+    extern __shared__ double coef_r[];
+    __shared__ uint32_t flags[128];
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const long long T = a.total / a.N;
+    const long long base = (long long)blockIdx.x * 128;
+    {
+        const long long t = base + threadIdx.x;
+        uint32_t fl = 0;
+        if (t < T) fl = (a.status[t] & MKF_ST_CHOL_FAIL) ? 1u : 0u;
+        flags[threadIdx.x] = fl;
+        if (!__syncthreads_or((int)fl)) return;
+    }
+    for (int q = 0; q < 128; q++) {
+        if (!flags[q]) continue;
+        const long long t = base + q;
+        const int nh = nheads[t];
+        for (int i = threadIdx.x; i < nh; i += 128) {
+            const int4 m = hmeta[t * a.N + i];
+            const long long sp = t * a.N + m.x, so = t * a.N + i;
+            const double2* src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+            double v[L::NE];
+            for (int p = 0; p < L::NP; p++) {
+                const double2 qq = src[L::po(p)];
+                v[2 * p] = qq.x;
+                if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
+            }
+            double zc[MKF_M], w;
+            if (a.meas_layout == MKF_MEAS_CAND)
+                mkf_load_meas_cand(a, t, m.y >> 8, zc); // the column of the head's candidate bin
+            else
+                mkf_load_meas(a, t, 0, zc);
+            slot_math<D, true>(v, a.comp_const + (long long)(m.y & 0xff) * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+            double2* dst = a.st_out + (so >> 5) * (long long)L::TILE2 + (so & 31) * L::H;
+            for (int p = 0; p < L::NP; p++) {
+                double2 qq;
+                qq.x = v[2 * p];
+                qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                dst[L::po(p)] = qq;
+            }
+            a.w_rec[so] = w;
+        }
+        if (with_resample) {
+            __syncthreads();
+            __threadfence_block();
+            const int R = ra.Dpose + D;
+            for (int i = threadIdx.x; i < R * D; i += 128) {
+                const int r = i / D, c = i - r * D;
+                coef_r[c * R + r] = r < ra.Dpose ? ra.recon[r * D + c] : ra.tinv[(r - ra.Dpose) * D + c];
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) mkf_resample_runs_track<D>(ra, t, threadIdx.x, coef_r, nh);
+            __syncthreads();
         }
     }
 }
