@@ -778,11 +778,13 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
             CK(cudaFuncSetAttribute(k_frame_fused<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         }
     }
-    // MKF_FUSED=0: the three grid-wide kernels (k_frame_heads, k_slot_update_heads_direct, k_resample_runs) instead of
-    // the single-launch frame kernel (A/B runs, profiles)
-    static const bool fused = [] {
+    // MKF_FUSED=1: the single-launch frame kernel k_frame_fused instead of the three grid-wide kernels (k_frame_heads,
+    // k_slot_update_heads_direct, k_resample_runs).  Measured at 4096 x 500: 0.147 ms per frame against 0.104 -- a warp
+    // that owns its tracks walks their bookkeeping latency chains one after the other with only 8 warps per SM to hide
+    // them -- so it is an experiment kept for A/B runs, not the default.
+    const bool fused = [] {
         const char* e = getenv("MKF_FUSED");
-        return !(e && e[0] == '0');
+        return e && e[0] == '1';
     }();
     if (fused) {
         // persistent grid: 2 CTAs of 4 warps per SM, but no more warps than tracks

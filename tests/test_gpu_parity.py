@@ -652,7 +652,7 @@ def test_record_sharing_variants_agree(left_arm, T, N, monkeypatch):
     u0 = synth_u_init(seed, tracks)
 
     def make(env):
-        for k in ("MKF_DEDUP", "MKF_SHARE_SPLIT", "MKF_RUNS"):
+        for k in ("MKF_DEDUP", "MKF_SHARE_SPLIT", "MKF_RUNS", "MKF_FUSED"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -662,6 +662,23 @@ def test_record_sharing_variants_agree(left_arm, T, N, monkeypatch):
 
     variants = [make({"MKF_DEDUP": "0"}), make({"MKF_SHARE_SPLIT": "0"}), make({"MKF_RUNS": "0"}), make({})]
     keys = ("parents", "indicators", "x", "P", "w_raw", "w_norm", "wsum", "status")
+    # the run-length frame as ONE launch (k_frame_fused, an experiment kept for A/B runs): MKF_FUSED is read per frame
+    monkeypatch.setenv("MKF_FUSED", "1")
+    fused = mk.TrackBatch(left_arm.mk, T, N)
+    fused.reset(u0)
+    for fr in range(3):
+        m, ui, up = synth_frame(seed, tracks, fr)
+        fused.update(m, ui, up)
+    monkeypatch.delenv("MKF_FUSED")
+    ref3 = mk.TrackBatch(left_arm.mk, T, N)
+    ref3.reset(u0)
+    for fr in range(3):
+        m, ui, up = synth_frame(seed, tracks, fr)
+        ref3.update(m, ui, up)
+    d_f, d_r = fused.download(), ref3.download()
+    for key in keys:
+        assert np.array_equal(d_f[key], d_r[key]), ("fused", key)
+    assert np.array_equal(fused.estimate()[1], ref3.estimate()[1])
 
     def check_estimates():
         e0 = variants[0].estimate()
