@@ -205,6 +205,11 @@ struct mkf_batch {
     uint32_t* status = nullptr;
     uint32_t* unsorted = nullptr;  // per track: last posterior resample left unsorted parents
     int32_t* chain_last = nullptr; // T x N scratch of the literal alias mode
+    // literal alias mode with dynamic run assignment (k_alias_runs + k_slot_update_chain_dyn): the run starts, and four
+    // counters {runs listed, runs taken} x 2 used alternately (a frame's walker clears the pair the next frame uses)
+    int* alias_list = nullptr;
+    int* alias_cnt = nullptr;
+    int alias_flip = 0;
     // model constants on this device
     double *d_comp = nullptr, *d_init = nullptr, *d_cw_hi = nullptr, *d_cw_lo = nullptr, *d_wprior = nullptr,
            *d_recon = nullptr, *d_pmean = nullptr, *d_tm = nullptr, *d_tinv = nullptr;
@@ -311,7 +316,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->alias_list, b->alias_cnt, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -432,6 +437,15 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
     if (m->prm.alias_mode == MKF_ALIAS_CV_SHALLOW_LITERAL &&
         (rc = dmalloc((void**)&b->chain_last, (size_t)b->total * sizeof(int32_t))))
         return fail(rc);
+    {
+        const char* e4 = getenv("MKF_ALIAS_DYN"); // MKF_ALIAS_DYN=0: the thread-per-run-start kernel (A/B runs)
+        if (m->prm.alias_mode == MKF_ALIAS_CV_SHALLOW_LITERAL && !(e4 && e4[0] == '0')) {
+            if ((rc = dmalloc((void**)&b->alias_list, (size_t)b->total * sizeof(int))) ||
+                (rc = dmalloc((void**)&b->alias_cnt, 4 * sizeof(int))))
+                return fail(rc);
+            if (cudaMemset(b->alias_cnt, 0, 4 * sizeof(int)) != cudaSuccess) return fail(MKF_E_CUDA);
+        }
+    }
     // the tail lanes of the last tile are read by nobody but keep them defined
     if (cudaMemset(b->st[0], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
         cudaMemset(b->st[1], 0, (size_t)b->n_tiles * tile_bytes) != cudaSuccess ||
@@ -907,6 +921,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             MKF_SLOT_ATTR(10, false);
             MKF_SLOT_ATTR(10, true);
 #undef MKF_SLOT_ATTR
+            CK(cudaFuncSetAttribute(k_slot_update_chain_dyn<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update_chain_dyn<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         }
         const unsigned g = grid_for(b->total, 128);
         // slots per CTA of the record-sharing kernel = 128 * share_g (MKF_SHARE_G overrides for experiments)
@@ -916,7 +932,8 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
             return (v == 4 || v == 8 || v == 16) ? v : 8;
         }();
         a.split = use_split ? 1 : 0;
-        if (prof && !use_split) cudaEventRecord(pe[2], b->stream); // no k_share_keys in this frame: an empty interval
+        const bool alias_dyn = a.alias_chain && b->alias_list && b->stage == 3;
+        if (prof && !use_split && !alias_dyn) cudaEventRecord(pe[2], b->stream); // no keys kernel: an empty interval
         const size_t smem_shared = smem + (size_t)128 * share_g * (8 + 4 * 4 + 1);
         static std::atomic<uint64_t> seen_shared{0};
         if (dedup && first_on_this_device(seen_shared)) {
@@ -936,7 +953,16 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     mkf_launch(k_slot_update_shared<DD, GG>, grid_for(b->total, 128 * GG), 128, smem_shared, b->stream, a)
 #define MKF_SLOT_LAUNCH(DD)                                                            \
     do {                                                                               \
-        if (a.alias_chain)                                                             \
+        if (a.alias_chain && b->alias_list && b->stage == 3) {                         \
+            int* cnt = b->alias_cnt + 2 * b->alias_flip;                               \
+            mkf_launch(k_alias_runs, grid_for(b->total, 1024), 256, 0, b->stream, a.src, (const uint32_t*)b->unsorted, \
+                       b->total, b->N, b->alias_list, cnt);                            \
+            MKF_LAUNCHED();                                                            \
+            if (prof) cudaEventRecord(pe[2], b->stream);                               \
+            mkf_launch(k_slot_update_chain_dyn<DD>, (unsigned)(2 * sm_count(b->device)), 128, smem, b->stream, a, \
+                       (const int*)b->alias_list, (const int*)cnt, cnt + 1, b->alias_cnt + 2 * (b->alias_flip ^ 1)); \
+            b->alias_flip ^= 1;                                                        \
+        } else if (a.alias_chain)                                                      \
             mkf_launch(k_slot_update<DD, true>, g, 128, smem, b->stream, a);    \
         else if (use_split) {                                                          \
             if (meas_layout == MKF_MEAS_CAND)                                                                          \

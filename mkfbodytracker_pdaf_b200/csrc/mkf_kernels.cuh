@@ -496,6 +496,152 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
 }
 
 // -----------------------------------------------------------------------------------------
+// MKF_ALIAS_CV_SHALLOW_LITERAL with dynamic run assignment.  k_slot_update<D, true> gives every run of duplicates to
+// the thread of its first slot: half the lanes of a warp retire at once (they are not run starts) and the rest wait for
+// the longest run among them (mean run length 2, the longest of 32 is 6-8: ncu showed ~10 of 32 lanes active).  Here
+//   k_alias_runs             lists the run starts (one atomicAdd per 1024-slot chunk, like k_share_keys);
+//   k_slot_update_chain_dyn  persistent warps whose lanes each walk one run at a time -- predict / likelihood / update,
+//                            snapshot stored per slot, exactly the in-place sequence of src/pf2DRao.cpp:134-142 on a
+//                            shared cv::Mat -- and, when a lane's run ends, take the next run from the list (one
+//                            warp-aggregated atomicAdd per refill).  Every iteration of the warp's loop is then the
+//                            gather / arithmetic / store step of the independent kernel with all lanes busy; a parent
+//                            is read once per run, so the kernel moves N x 720 B of snapshots + runs x 720 B of parents.
+// Tracks with unsorted parents (after the cv::RNG fallback) are left to k_slot_update_repair, as before.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_alias_runs(const int32_t* __restrict__ src, const uint32_t* __restrict__ unsorted,
+                                                    long long total, int N, int* __restrict__ list,
+                                                    int* __restrict__ count)
+{
+    constexpr int G = 4;
+    __shared__ int warp_tot[8];
+    __shared__ int list_base;
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long s0 = ((long long)blockIdx.x * 256 + tid) * G;
+    unsigned flags = 0;
+    if (s0 < total) {
+        int prev = s0 > 0 ? __ldg(src + s0 - 1) : -1;
+        long long t = s0 / N;
+        int j = (int)(s0 - t * N);
+        bool skip = unsorted[t] != 0u;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (s0 + g >= total) break;
+            const int cur = __ldg(src + s0 + g);
+            if (!skip && (j == 0 || cur != prev)) flags |= 1u << g;
+            prev = cur;
+            if (++j == N) {
+                j = 0;
+                t++;
+                skip = (s0 + g + 1 < total) ? unsorted[t] != 0u : false;
+            }
+        }
+    }
+    const int cnt = __popc(flags);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int before = inc - cnt;
+    for (int w = 0; w < wid; w++) before += warp_tot[w];
+    if (tid == 255) list_base = atomicAdd(count, before + cnt);
+    __syncthreads();
+    int r = list_base + before;
+#pragma unroll
+    for (int g = 0; g < G; g++)
+        if (flags & (1u << g)) list[r++] = (int)(s0 + g);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs a, const int* __restrict__ list,
+                                                                  const int* __restrict__ count, int* __restrict__ next,
+                                                                  int* __restrict__ to_clear)
+{
+    using L = SlotLay<D>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cst = reinterpret_cast<double*>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t cbytes = (uint32_t)(a.K * L::CS * sizeof(double));
+    if (tid == 0) mkf_mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mkf_mbar_expect_tx(&mbar, cbytes);
+        mkf_tma_load_1d(cst, a.comp_const, cbytes, &mbar);
+    }
+    mkf_pdl_launch_dependents();
+    mkf_pdl_wait();
+    const int n = *reinterpret_cast<const volatile int*>(count);
+    if (blockIdx.x == 0 && tid == 0) { // the counters the NEXT frame's k_alias_runs / this kernel start from
+        to_clear[0] = 0;
+        to_clear[1] = 0;
+    }
+    mkf_mbar_wait(&mbar, 0);
+
+    double v[L::NE];
+    bool have = false, drained = false;
+    long long s = 0, t = 0;
+    int j = 0, par = 0;
+    for (;;) {
+        // refill: lanes without a run take the next ones from the list
+        const bool need = !have && !drained;
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+            int base = 0;
+            const int leader = __ffs(mask) - 1;
+            if (lane == leader) base = atomicAdd(next, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                const int my = base + __popc(mask & ((1u << lane) - 1u));
+                if (my < n) {
+                    s = __ldg(list + my);
+                    t = s / a.N;
+                    j = (int)(s - t * a.N);
+                    par = __ldg(a.src + s);
+                    const long long sp = t * a.N + par;
+                    const double2* __restrict__ srcp = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+#pragma unroll
+                    for (int p = 0; p < L::NP; p++) {
+                        const double2 q = __ldg(srcp + L::po(p));
+                        v[2 * p] = q.x;
+                        if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+                    }
+                    have = true;
+                } else {
+                    drained = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            double zc[MKF_M], w;
+            mkf_load_meas(a, t, j, zc);
+            const int k = mkf_component_of(a.bounds + t * (a.K + 2), a.K, j, a.ind_tail ? a.ind_tail + t * a.N : nullptr);
+            const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
+            if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
+            double2* __restrict__ dst = a.st_out + (s >> 5) * (long long)L::TILE2 + (s & 31) * L::H;
+#pragma unroll
+            for (int p = 0; p < L::NP; p++) {
+                double2 q;
+                q.x = v[2 * p];
+                q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                __stcs(dst + L::po(p), q);
+            }
+            a.w_raw[s] = w;
+            // the next slot continues this run when it drew the same parent (it shares the cv::Mat just updated)
+            s++;
+            j++;
+            if (j >= a.N || __ldg(a.src + s) != par) have = false;
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------
 // Slot update with record sharing (MKF_ALIAS_INDEPENDENT, one measurement per track).
 // Children of one parent RECORD that drew the same component are bit-identical Gaussians, and because resampled parents
 // are sorted they are consecutive slots.  A CTA takes CHUNK = 128 G consecutive slots:
