@@ -583,13 +583,32 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs
     }
     mkf_mbar_wait(&mbar, 0);
 
+    // A lane holds the run it is walking and, claimed one step ahead, the run it will walk next: the claim (atomicAdd,
+    // list entry, parent index -- three dependent round trips) is issued while the current step computes, so that a
+    // lane whose run ends only has the gather of the new parent in front of its next step.
     double v[L::NE];
-    bool have = false, drained = false;
+    bool have = false, has_next = false, drained = false;
     long long s = 0, t = 0;
-    int j = 0, par = 0;
+    int j = 0, par = 0, ns = 0, npar = 0;
     for (;;) {
-        // refill: lanes without a run take the next ones from the list
-        const bool need = !have && !drained;
+        if (!have && has_next) { // start the run claimed earlier: gather its parent
+            s = ns;
+            t = s / a.N;
+            j = (int)(s - t * a.N);
+            par = npar;
+            const long long sp = t * a.N + par;
+            const double2* __restrict__ srcp = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+#pragma unroll
+            for (int p = 0; p < L::NP; p++) {
+                const double2 q = __ldg(srcp + L::po(p));
+                v[2 * p] = q.x;
+                if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+            }
+            have = true;
+            has_next = false;
+        }
+        // claim ahead: lanes without a next run take the following list entries (one atomicAdd per warp)
+        const bool need = !has_next && !drained;
         const unsigned mask = __ballot_sync(0xffffffffu, need);
         if (mask) {
             int base = 0;
@@ -599,26 +618,18 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs
             if (need) {
                 const int my = base + __popc(mask & ((1u << lane) - 1u));
                 if (my < n) {
-                    s = __ldg(list + my);
-                    t = s / a.N;
-                    j = (int)(s - t * a.N);
-                    par = __ldg(a.src + s);
-                    const long long sp = t * a.N + par;
-                    const double2* __restrict__ srcp = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
-#pragma unroll
-                    for (int p = 0; p < L::NP; p++) {
-                        const double2 q = __ldg(srcp + L::po(p));
-                        v[2 * p] = q.x;
-                        if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
-                    }
-                    have = true;
+                    ns = __ldg(list + my);
+                    npar = __ldg(a.src + ns);
+                    has_next = true;
                 } else {
                     drained = true;
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, have)) break;
+        if (!__any_sync(0xffffffffu, have || has_next)) break;
         if (have) {
+            // does the next slot continue this run?  (it drew the same parent: it shares the cv::Mat updated below)
+            const bool cont = (j + 1 < a.N) && (__ldg(a.src + s + 1) == par);
             double zc[MKF_M], w;
             mkf_load_meas(a, t, j, zc);
             const int k = mkf_component_of(a.bounds + t * (a.K + 2), a.K, j, a.ind_tail ? a.ind_tail + t * a.N : nullptr);
@@ -633,10 +644,9 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs
                 __stcs(dst + L::po(p), q);
             }
             a.w_raw[s] = w;
-            // the next slot continues this run when it drew the same parent (it shares the cv::Mat just updated)
             s++;
             j++;
-            if (j >= a.N || __ldg(a.src + s) != par) have = false;
+            have = cont;
         }
     }
 }
