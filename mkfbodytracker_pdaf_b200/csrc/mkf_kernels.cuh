@@ -502,8 +502,8 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
 //   k_alias_runs             lists the run starts (one atomicAdd per 1024-slot chunk, like k_share_keys);
 //   k_slot_update_chain_dyn  persistent warps whose lanes each walk one run at a time -- predict / likelihood / update,
 //                            snapshot stored per slot, exactly the in-place sequence of src/pf2DRao.cpp:134-142 on a
-//                            shared cv::Mat -- and, when a lane's run ends, take the next run from the list (one
-//                            warp-aggregated atomicAdd per refill).  Every iteration of the warp's loop is then the
+//                            shared cv::Mat -- and, when a lane's run ends, take the next run of the warp's stretch
+//                            of the list.  Every iteration of the warp's loop is then the
 //                            gather / arithmetic / store step of the independent kernel with all lanes busy; a parent
 //                            is read once per run, so the kernel moves N x 720 B of snapshots + runs x 720 B of parents.
 // Tracks with unsorted parents (after the cv::RNG fallback) are left to k_slot_update_repair, as before.
@@ -590,6 +590,10 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs
     bool have = false, has_next = false, drained = false;
     long long s = 0, t = 0;
     int j = 0, par = 0, ns = 0, npar = 0;
+    // the list is split evenly over the warps of the grid (run lengths average out over the ~900 runs of a stretch)
+    const long long nwarps = (long long)gridDim.x * 4, gw = (long long)blockIdx.x * 4 + (tid >> 5);
+    long long wcur = (long long)n * gw / nwarps;
+    const long long wend = (long long)n * (gw + 1) / nwarps;
     for (;;) {
         if (!have && has_next) { // start the run claimed earlier: gather its parent
             s = ns;
@@ -607,17 +611,15 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs
             have = true;
             has_next = false;
         }
-        // claim ahead: lanes without a next run take the following list entries (one atomicAdd per warp)
+        // claim ahead: lanes without a next run take the following entries of this warp's stretch of the list.  (A
+        // batch-wide cursor advanced with one atomicAdd per refill was the first version: 64 k same-address atomics per
+        // frame serialise in the L2 -- 1.13 ms per frame against 0.91 for the static kernel.)
         const bool need = !has_next && !drained;
         const unsigned mask = __ballot_sync(0xffffffffu, need);
         if (mask) {
-            int base = 0;
-            const int leader = __ffs(mask) - 1;
-            if (lane == leader) base = atomicAdd(next, __popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
             if (need) {
-                const int my = base + __popc(mask & ((1u << lane) - 1u));
-                if (my < n) {
+                const long long my = wcur + __popc(mask & ((1u << lane) - 1u));
+                if (my < wend) {
                     ns = __ldg(list + my);
                     npar = __ldg(a.src + ns);
                     has_next = true;
@@ -625,6 +627,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs
                     drained = true;
                 }
             }
+            wcur += __popc(mask);
         }
         if (!__any_sync(0xffffffffu, have || has_next)) break;
         if (have) {
