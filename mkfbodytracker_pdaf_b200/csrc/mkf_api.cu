@@ -438,8 +438,12 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
         (rc = dmalloc((void**)&b->chain_last, (size_t)b->total * sizeof(int32_t))))
         return fail(rc);
     {
-        const char* e4 = getenv("MKF_ALIAS_DYN"); // MKF_ALIAS_DYN=0: the thread-per-run-start kernel (A/B runs)
-        if (m->prm.alias_mode == MKF_ALIAS_CV_SHALLOW_LITERAL && !(e4 && e4[0] == '0')) {
+        // MKF_ALIAS_DYN=1: the dynamic chain walker (k_alias_runs + k_slot_update_chain_dyn) instead of the
+        // thread-per-run-start kernel.  An experiment kept for A/B runs: every lane stays busy, but lanes walking
+        // different runs touch 16-byte pieces two or three slots apart and out of step, and DRAM moves 6.8 GB per frame
+        // where 2.2 GB are needed (ncu, profiles/r02_ncu_chain_dyn.csv): 1.70 ms per frame against 0.91.
+        const char* e4 = getenv("MKF_ALIAS_DYN");
+        if (m->prm.alias_mode == MKF_ALIAS_CV_SHALLOW_LITERAL && e4 && e4[0] == '1') {
             if ((rc = dmalloc((void**)&b->alias_list, (size_t)b->total * sizeof(int))) ||
                 (rc = dmalloc((void**)&b->alias_cnt, 4 * sizeof(int))))
                 return fail(rc);

@@ -644,7 +644,8 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_chain_dyn(const SlotArgs
                 double2 q;
                 q.x = v[2 * p];
                 q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-                __stcs(dst + L::po(p), q);
+                dst[L::po(p)] = q; // (not streaming: the neighbouring slot's half of the sector arrives a step or two
+                                   // later, from another lane -- evict-first stores turned those into read-modify-writes)
             }
             a.w_raw[s] = w;
             s++;

@@ -328,11 +328,16 @@ def literal_model(arm):
     return mk.Model.from_arrays(a["means"], a["covs"], a["weights"], a["gamma"], a["pca_proj"], a["pca_mean"], p)
 
 
-@pytest.mark.parametrize("N", [500, 37])
-def test_literal_alias_mode_matches_oracle_and_reference_sources(left_arm, N):
+@pytest.mark.parametrize("N,dyn", [(500, False), (37, False), (500, True), (1100, True)])
+def test_literal_alias_mode_matches_oracle_and_reference_sources(left_arm, N, dyn, monkeypatch):
     """alias_mode = CV_SHALLOW_LITERAL (quirk B3): the GPU must equal the oracle in literal mode and -- through
-    oracle/_ref -- the reference's own pf2DRao.cpp, free-running, indices bit-exact"""
+    oracle/_ref -- the reference's own pf2DRao.cpp, free-running, indices bit-exact.  dyn: the dynamic chain walker
+    (MKF_ALIAS_DYN=1, k_alias_runs + k_slot_update_chain_dyn), an A/B experiment that must give the same results."""
     import mkf_ref
+    if dyn:
+        monkeypatch.setenv("MKF_ALIAS_DYN", "1")
+    else:
+        monkeypatch.delenv("MKF_ALIAS_DYN", raising=False)
     have_ref = mkf_ref.available()
     T, frames, seed = 3, 10, 0x5EED0001
     rng = np.random.default_rng(17)
