@@ -67,6 +67,11 @@ def read_report(path):
 
 def main(argv):
     traffic_json = None
+    captured = None
+    if "--captured" in argv:
+        i = argv.index("--captured")
+        captured = argv[i + 1]
+        argv = argv[:i] + argv[i + 2:]
     if "--traffic-json" in argv:
         i = argv.index("--traffic-json")
         traffic_json = argv[i + 1]
@@ -111,7 +116,8 @@ def main(argv):
             return float(val.replace(",", "")) * UNIT_SCALE[unit]
 
         found = 0
-        for base in ("k_slot_update_heads_direct", "k_share_keys", "k_slot_update_shared", "k_slot_update"):
+        for base in ("k_slot_update_heads_direct", "k_share_keys", "k_slot_update_shared", "k_slot_update",
+                     "k_frame_heads", "k_resample_runs"):
             sel = [c for c in cols if c[1].replace("void ", "").strip().split("<")[0].split("(")[0] == base]
             if not sel:
                 continue
@@ -134,7 +140,9 @@ def main(argv):
                 doc["kernels"][base]["algorithmic_bytes_per_launch"] = 4096 * 500 * 1500
         if not found:
             raise SystemExit("no slot-update launch in the reports; %s left untouched" % traffic_json)
-        doc["round"] = 1
+        doc["round"] = 2
+        if captured:
+            doc["captured"] = captured
         with open(traffic_json, "w") as f:
             json.dump(doc, f, indent=1)
             f.write("\n")
