@@ -700,12 +700,29 @@ static void fill_slot_args(mkf_batch* b, SlotArgs& a, const double* d_meas, int 
 // CTAs of k_slot_update_heads_direct per SM: 2 are resident; with more, the later ones start as earlier ones finish and
 // the gather / arithmetic / store phases of the resident CTAs drift apart (measured at 4096 x 500: 77.7 us with 2, 74.5
 // with 4, 72.1 with 12-24).  The kernel strides over the list, so any grid is correct.  MKF_HEADS_CTAS_PER_SM overrides.
-static int heads_ctas_per_sm()
+// The head count is only known on the device; ~1/8 of the slots is what a shared-measurement frame keeps in steady state,
+// so the default grid is one CTA per 1024 slots, at least 12 and at most 128 per SM: large batches then also run one
+// step per CTA (32768 x 500: 0.765 -> 0.80 of the HBM peak; profiles/r02_heads_sweep.jsonl).
+static unsigned heads_grid(const mkf_batch* b, int sms)
+{
+    static const int forced = [] {
+        const char* e = getenv("MKF_HEADS_CTAS_PER_SM");
+        const int x = e ? atoi(e) : 0;
+        return (x >= 1 && x <= 128) ? x : 0;
+    }();
+    if (forced) return (unsigned)(forced * sms);
+    long long g = b->total / 1024;
+    if (g < 12ll * sms) g = 12ll * sms;
+    if (g > 128ll * sms) g = 128ll * sms;
+    return (unsigned)g;
+}
+
+static int heads_block()
 {
     static const int v = [] {
-        const char* e = getenv("MKF_HEADS_CTAS_PER_SM");
-        const int x = e ? atoi(e) : 12;
-        return (x >= 1 && x <= 64) ? x : 12;
+        const char* e = getenv("MKF_HEADS_BLOCK");
+        const int x = e ? atoi(e) : 128;
+        return (x == 64 || x == 128) ? x : 128;
     }();
     return v;
 }
@@ -823,11 +840,12 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         MKF_LAUNCHED();
         CK(cudaGetLastError());
         if (pe) cudaEventRecord(pe[2], b->stream);
-        const unsigned hgrid = (unsigned)(heads_ctas_per_sm() * sm_count(b->device));
+        const unsigned hblock = (unsigned)heads_block();
+        const unsigned hgrid = heads_grid(b, sm_count(b->device)) * (128 / hblock);
         if (m->d == 12)
-            mkf_launch(k_slot_update_heads_direct<12>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
+            mkf_launch(k_slot_update_heads_direct<12>, hgrid, hblock, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
         else
-            mkf_launch(k_slot_update_heads_direct<10>, hgrid, 128, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
+            mkf_launch(k_slot_update_heads_direct<10>, hgrid, hblock, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
         b->head_flip ^= 1;
         MKF_LAUNCHED();
         CK(cudaGetLastError());
@@ -975,7 +993,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
                 mkf_launch(k_share_keys<false>, grid_for(b->total, MKF_SHARE_CHUNK), 256, 0, b->stream, a);           \
             MKF_LAUNCHED();                                                            \
             if (prof) cudaEventRecord(pe[2], b->stream);                               \
-            mkf_launch(k_slot_update_heads_direct<DD>, (unsigned)(heads_ctas_per_sm() * sm_count(b->device)), 128, smem, b->stream, a,   \
+            mkf_launch(k_slot_update_heads_direct<DD>, heads_grid(b, sm_count(b->device)), 128, smem, b->stream, a,   \
                        b->head_count + (b->head_flip ^ 1));                            \
             b->head_flip ^= 1;                                                         \
         } else if (dedup && share_g == 4)                                                \

@@ -1025,8 +1025,8 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
 
     const int n = *reinterpret_cast<const volatile int*>(a.head_count);
     if (blockIdx.x == 0 && tid == 0) *count_to_clear = 0; // the counter the next frame's k_share_keys appends with
-    const int step = (int)gridDim.x * 128;
-    int h = (int)blockIdx.x * 128 + tid;
+    const int step = (int)(gridDim.x * blockDim.x); // (the block size is a launch parameter: 128, or 64 for A/B runs)
+    int h = (int)(blockIdx.x * blockDim.x) + tid;
     int4 rec = make_int4(-1, 0, 0, 0);
     if (h < n) rec = __ldg(a.hd16 + h);
     mkf_mbar_wait(&mbar, 0);
