@@ -848,7 +848,8 @@ def main():
 
     legs = set() if args.headline_only else set(args.legs.split(","))
     c2 = leg_config2(cx, args)
-    c5 = leg_config5(cx) if "5" in legs else None
+    # config 5 runs up to the 100 frames BASELINE names (as many as --steps asks for), then gathers once
+    c5 = leg_config5(cx, steps=max(4, min(args.steps, 100))) if "5" in legs else None
     c3 = c4 = pf = None
     if rank == 0:  # single-GPU legs (independent persons: they scale like config 2)
         if "3" in legs:
