@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Secondary measurements of BASELINE.json configs 2 (N=15 bank), 3, 4, 5 and the legacy pf2D filter on
-one B200 (device-resident inputs, CUDA events on the launching stream).  Writes one JSON object per
+"""Secondary measurements (bank mode, association-only variants, the reference operating point ...) beside the legs
+bench.py itself carries for BASELINE.json configs 2-5 and the legacy pf2D filter, on one B200 (device-resident inputs, CUDA events on the launching stream).  Writes one JSON object per
 line; results are summarised in BASELINE.md section 4.  Not the headline bench (that is bench.py)."""
 import json
 import os
@@ -167,7 +167,7 @@ if "2lit" in which:
 if "2b" in which:
     rbpf("config 2 (bank): 4096 tracks x 15 slots, shared column", left, 4096, 15, 50, False, 0x5EED0002)
 if "3" in which:
-    assoc("config 3: 16384 persons, 17 candidates/hand, N=500", left, right, 16384 // 4, 500, 17, 10, 0x5EED0003)
+    assoc("config 3: 16384 persons, 17 candidates/hand, N=500", left, right, 16384, 500, 17, 10, 0x5EED0003)
     assoc("config 3 (assoc-heavy): 16384 persons, 17 candidates/hand, N=15", left, right, 16384, 15, 17, 20, 0x5EED0003)
     assoc("reference operating point: 5000 candidates/hand, N=500, 256 persons", left, right, 256, 500, 5000, 10, 3)
 if "4" in which:

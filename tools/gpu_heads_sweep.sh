@@ -15,4 +15,8 @@ EXTRA="--tracks 8192" run "8192 tracks" MKF_X=0
 EXTRA="--tracks 16384" run "16384 tracks" MKF_X=0
 EXTRA="--tracks 32768" run "32768 tracks" MKF_X=0
 EXTRA="--tracks 2048" run "2048 tracks" MKF_X=0
+EXTRA="--tracks 32768" run "32768 tracks, 64 CTAs/SM" MKF_HEADS_CTAS_PER_SM=64
+EXTRA="--tracks 32768" run "32768 tracks, 32 CTAs/SM" MKF_HEADS_CTAS_PER_SM=32
+EXTRA="--tracks 16384" run "16384 tracks, 48 CTAs/SM" MKF_HEADS_CTAS_PER_SM=48
+EXTRA="--tracks 16384" run "16384 tracks, 24 CTAs/SM" MKF_HEADS_CTAS_PER_SM=24
 cat $out
