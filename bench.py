@@ -352,18 +352,27 @@ def timed_region(cx, fn, steps, warmup, tail=None, collective=True):
 
 def stage_means(prof):
     n = max(prof["n"], 1)
-    return {"indicator_bounds": prof["ms_bounds"] / n, "share_keys": prof["ms_share_keys"] / n,
-            "slot_kernel": prof["ms_slot_kernel"] / n, "repair": prof["ms_repair"] / n,
-            "normalise_resample": prof["ms_resample"] / n, "samples": prof["n"]}
+    out = {"indicator_bounds": prof["ms_bounds"] / n, "share_keys": prof["ms_share_keys"] / n,
+           "slot_kernel": prof["ms_slot_kernel"] / n, "repair": prof["ms_repair"] / n,
+           "normalise_resample": prof["ms_resample"] / n, "samples": prof["n"]}
+    if prof.get("n_span"):  # the slot kernel's own span on the device (earliest CTA start .. latest CTA end)
+        out["slot_kernel_device_span"] = prof["ms_slot_span"] / prof["n_span"]
+    return out
 
 
-def roofline_of(cx, kernel, units, kernel_ms, samples, traffic_key=None, extra=None):
+def roofline_of(cx, kernel, units, kernel_ms, samples, traffic_key=None, extra=None, span_ms=None):
     ach = units * BYTES_PER_SLOT_UPDATE / (kernel_ms * 1e-3) / 1e9 if kernel_ms and kernel_ms > 0 else None
     tr = ((cx.traffic or {}).get("kernels") or {}).get(traffic_key or kernel) or {}
     out = {"bound": "hbm", "kernel": kernel, "kernel_ms": kernel_ms, "kernel_samples": samples,
            "units_per_launch": int(units), "algorithmic_bytes_per_launch": int(units) * BYTES_PER_SLOT_UPDATE,
            "achieved": ach, "peak": cx.peak, "unit": "GB/s", "frac": (ach / cx.peak) if ach else None,
            "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": (cx.traffic or {}).get("captured")}
+    if span_ms:
+        # kernel_ms is the interval between two CUDA events, which on a sampled step includes the launch gap the event
+        # records open in the programmatic-launch chain; the kernel's own span (first CTA start to last CTA end,
+        # %globaltimer stamps taken by the kernel itself) is reported beside it
+        out["kernel_ms_device_span"] = span_ms
+        out["frac_device_span"] = units * BYTES_PER_SLOT_UPDATE / (span_ms * 1e-3) / 1e9 / cx.peak
     if extra:
         out.update(extra)
     return out
@@ -494,7 +503,8 @@ def leg_config2(cx, args):
         sm = stage_means(p2)
         return {"steps": K2, "ms_per_step": ms2, "value": T * 1e3 / ms2, "unit": UNIT,
                 "slot_updates_per_s": T * N * 1e3 / ms2, "stage_ms": sm, "status_flagged_tracks": bad,
-                "roofline": roofline_of(cx, label_kernel, T * N, sm["slot_kernel"], sm["samples"]),
+                "roofline": roofline_of(cx, label_kernel, T * N, sm["slot_kernel"], sm["samples"],
+                                        span_ms=sm.get("slot_kernel_device_span")),
                 "clocks": cx.clk.defer(ta, tb)}
 
     every_slot = literal = None
@@ -586,7 +596,8 @@ def leg_config3(cx, steps=12, warmup=3):
             "distinct_records_fraction": rec / max(nslots, 1), "stage_ms_left_arm": sm, "status_flagged_persons": bad,
             "roofline": roofline_of(cx, "k_slot_update_heads_direct<12> (left arm)" if sharing else "k_slot_update<12, 0>",
                                     rec if sharing else nslots, sm["slot_kernel"], sm["samples"],
-                                    traffic_key="k_slot_update_heads_direct" if sharing else "k_slot_update"),
+                                    traffic_key="k_slot_update_heads_direct" if sharing else "k_slot_update",
+                                    span_ms=sm.get("slot_kernel_device_span")),
             "clocks": cx.clk.defer(t0, t1)}
 
 
@@ -631,7 +642,7 @@ def leg_config4(cx, steps=8, warmup=3):
             "slot_updates_per_s": T * N * 1e3 / ms_step, "stage_ms": sm, "status_flagged_tracks": bad,
             "literal_loop_tracks_last_frame": fb,
             "roofline": roofline_of(cx, "k_slot_update<12, 0>", T * N, sm["slot_kernel"], sm["samples"],
-                                    traffic_key="k_slot_update"),
+                                    traffic_key="k_slot_update", span_ms=sm.get("slot_kernel_device_span")),
             "clocks": cx.clk.defer(t0, t1)}
 
     # legacy plain particle filter, d = 8, K = 15 synthetic SPD GMM (no model file for it ships)
@@ -778,7 +789,7 @@ def leg_config5(cx, steps=12, warmup=3):
             "cross_rank_mismatches_max_over_ranks": int(flag.item()), "cross_rank_check": "ok" if flag.item() == 0 else "FAILED",
             "stage_ms": sm, "status_flagged_tracks": bad,
             "roofline": roofline_of(cx, "k_slot_update<12, 0>", T * N, sm["slot_kernel"], sm["samples"],
-                                    traffic_key="k_slot_update"),
+                                    traffic_key="k_slot_update", span_ms=sm.get("slot_kernel_device_span")),
             "clocks": cx.clk.defer(t0, t1)}
 
 
@@ -873,7 +884,7 @@ def main():
         units = c2.rec if sharing else c2.nslots
         split = sharing and sm["share_keys"] > 0
         kname = ("k_slot_update_heads_direct" if split else "k_slot_update_shared") if sharing else "k_slot_update"
-        roof = roofline_of(cx, kname, units, slot_ms, sm["samples"], extra={
+        roof = roofline_of(cx, kname, units, slot_ms, sm["samples"], span_ms=sm.get("slot_kernel_device_span"), extra={
             "kernel_sampling": f"CUDA events on every {c2.prof_every}th step of the timed region",
             "slots_per_launch": int(c2.nslots), "peak_source": cx.peak_src,
             "distinct_records_fraction": c2.rec / max(c2.nslots, 1),

@@ -297,6 +297,10 @@ int mkf_batch_profile_read(mkf_batch* b, double* ms_bounds, double* ms_slot_upda
 /* the same per kernel: ms[5] = indicator bounds, record-sharing keys (0 when the frame has none), the slot kernel
  * (k_slot_update / k_slot_update_heads_direct / k_slot_update_shared), the repair pass, normalise+resample */
 int mkf_batch_profile_read_stages(mkf_batch* b, double* ms, int* n_updates);
+/* the slot kernel's own span on the device over the same sampled updates: earliest CTA start to latest CTA end in
+ * %globaltimer time, summed (ms) -- what the kernel takes without the launch gap an event-bracketed kernel pays when the
+ * event records suspend the programmatic overlap.  Call before mkf_batch_profile_read_stages (which rearms sampling). */
+int mkf_batch_profile_read_slot_span(mkf_batch* b, double* ms, int* n_updates);
 
 /* Record sharing.  When the slots of a track see one measurement (MKF_MEAS_SHARED, MKF_ALIAS_INDEPENDENT), children
  * that drew the same parent and the same component are bit-identical Gaussians; the device computes and stores such a

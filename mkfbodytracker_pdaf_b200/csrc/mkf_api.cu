@@ -234,6 +234,8 @@ struct mkf_batch {
     // optional per-kernel timing (mkf_batch_profile): 4 events per update
     int stage = 3; // see SlotArgs::stage (mkf_kf_apply runs single stages)
     bool prof_on = false;
+    unsigned long long* prof_ts = nullptr; // per sampled update: {min CTA start, max CTA end} of the slot kernel
+    int prof_ts_cap = 0;
     std::vector<cudaEvent_t> prof_ev;
     int prof_n = 0, prof_every = 1;
     uint64_t prof_tick = 0;
@@ -316,7 +318,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->alias_list, b->alias_cnt, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->alias_list, b->alias_cnt, b->prof_ts, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -775,6 +777,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     a.dedup = 1;
     a.split = 1;
     a.rep = nullptr;
+    if (pe && b->prof_ts) a.ts = b->prof_ts + 2 * (size_t)b->prof_n;
     ResampleRunsArgs ra{};
     ra.T = b->T;
     ra.N = b->N;
@@ -932,6 +935,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     }
     a.dedup = dedup ? 1 : 0;
     a.rep = dedup ? b->rep : nullptr;
+    if (prof && b->prof_ts) a.ts = b->prof_ts + 2 * (size_t)b->prof_n;
     const size_t smem = (size_t)m->K * b->lay.cs * sizeof(double);
     {
         static std::atomic<uint64_t> seen{0};
@@ -1059,6 +1063,21 @@ extern "C" int mkf_batch_profile_every(mkf_batch* b, int max_updates, int every)
         CK(cudaEventCreate(&e));
         b->prof_ev.push_back(e);
     }
+    if (max_updates > b->prof_ts_cap) {
+        if (b->prof_ts) cudaFree(b->prof_ts);
+        b->prof_ts = nullptr;
+        b->prof_ts_cap = 0;
+        CK(cudaMalloc((void**)&b->prof_ts, (size_t)max_updates * 16));
+        b->prof_ts_cap = max_updates;
+    }
+    if (max_updates > 0) { // start stamps take atomicMin, end stamps atomicMax
+        std::vector<unsigned long long> init((size_t)max_updates * 2);
+        for (int i = 0; i < max_updates; i++) {
+            init[2 * i] = ~0ull;
+            init[2 * i + 1] = 0ull;
+        }
+        CK(cudaMemcpy(b->prof_ts, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    }
     return MKF_OK;
 }
 
@@ -1082,6 +1101,39 @@ extern "C" int mkf_batch_profile_read_stages(mkf_batch* b, double* ms /* 5 */, i
         for (int k = 0; k < MKF_PROF_EV - 1; k++) ms[k] = acc[k];
     if (n_updates) *n_updates = b->prof_n;
     b->prof_n = 0;
+    if (b->prof_ts && b->prof_ts_cap > 0) { // rearm the device-span stamps as well
+        std::vector<unsigned long long> init((size_t)b->prof_ts_cap * 2);
+        for (int i = 0; i < b->prof_ts_cap; i++) {
+            init[2 * i] = ~0ull;
+            init[2 * i + 1] = 0ull;
+        }
+        CK(cudaMemcpy(b->prof_ts, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    }
+    return MKF_OK;
+}
+
+// the slot kernel's own span on the device (earliest CTA start to latest CTA end, %globaltimer) summed over the sampled
+// updates; call BEFORE mkf_batch_profile_read_stages (which rearms the sample counter)
+extern "C" int mkf_batch_profile_read_slot_span(mkf_batch* b, double* ms, int* n_updates)
+{
+    if (!b || !ms) {
+        mkf_set_error("mkf_batch_profile_read_slot_span: null argument");
+        return MKF_E_INVALID;
+    }
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    *ms = 0.0;
+    int n = 0;
+    if (b->prof_ts && b->prof_n > 0) {
+        std::vector<unsigned long long> h((size_t)b->prof_n * 2);
+        CK(cudaMemcpy(h.data(), b->prof_ts, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < b->prof_n; i++)
+            if (h[2 * i] != ~0ull && h[2 * i + 1] > h[2 * i]) {
+                *ms += (double)(h[2 * i + 1] - h[2 * i]) * 1e-6;
+                n++;
+            }
+    }
+    if (n_updates) *n_updates = n;
     return MKF_OK;
 }
 

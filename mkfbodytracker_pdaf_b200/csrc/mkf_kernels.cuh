@@ -91,8 +91,18 @@ struct SlotArgs {
     const double* __restrict__ roi;    // T x 4
     double neck;
     int cand_C, hand;
+    // profiling only (null otherwise): {earliest CTA start, latest CTA end} of the slot kernel in %globaltimer
+    // nanoseconds -- the kernel's own span on the device, free of the launch gap an event-bracketed kernel pays
+    unsigned long long* ts;
 };
-#define MKF_MEAS_CAND 2 // internal third value of meas_layout (the public ones: include/mkf_b200.h)
+#define MKF_MEAS_CAND 2
+
+__device__ __forceinline__ unsigned long long mkf_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+} // internal third value of meas_layout (the public ones: include/mkf_b200.h)
 
 // -----------------------------------------------------------------------------------------
 // cv::Cholesky failure branch (a pivot < DBL_EPSILON, src/pf2DRao.cpp:37,52), literal:
@@ -422,6 +432,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
 
+    if (a.ts && threadIdx.x == 0) atomicMin(a.ts, mkf_globaltimer());
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = s < a.total;
     double v[L::NE];
@@ -473,6 +484,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update(const SlotArgs a)
             __stcs(dst + L::po(p), q);
         }
         a.w_raw[s] = w;
+        if (a.ts && (threadIdx.x & 31) == 0) atomicMax(a.ts + 1, mkf_globaltimer());
     } else {
         for (int i = 0;;) {
             double w;
@@ -1025,6 +1037,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
 
     const int n = *reinterpret_cast<const volatile int*>(a.head_count);
     if (blockIdx.x == 0 && tid == 0) *count_to_clear = 0; // the counter the next frame's k_share_keys appends with
+    if (a.ts && tid == 0) atomicMin(a.ts, mkf_globaltimer());
     const int step = (int)(gridDim.x * blockDim.x); // (the block size is a launch parameter: 128, or 64 for A/B runs)
     int h = (int)(blockIdx.x * blockDim.x) + tid;
     int4 rec = make_int4(-1, 0, 0, 0);
@@ -1061,6 +1074,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
         }
         a.w_rec[so_rec] = w;
     }
+    if (a.ts && (tid & 31) == 0) atomicMax(a.ts + 1, mkf_globaltimer());
 }
 
 // Rare tracks redone after k_slot_update: (i) a cv::Cholesky failure was flagged (literal failure semantics

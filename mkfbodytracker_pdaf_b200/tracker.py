@@ -201,7 +201,16 @@ class TrackBatch:
         return dict(ms_bounds=a.value, ms_slot_update=b_.value, ms_resample=c.value, n=n.value)
 
     def profile_read_stages(self):
-        """summed milliseconds per kernel of the profiled updates: bounds, share keys, slot kernel, repair, resample"""
+        """summed milliseconds per kernel of the profiled updates: bounds, share keys, slot kernel, repair, resample
+        (+ ms_slot_span / n_span: the slot kernel's own device span, %globaltimer)"""
+        sp, ns = C.c_double(), C.c_int()
+        L.check(L.lib.mkf_batch_profile_read_slot_span(self._h, C.byref(sp), C.byref(ns)))
+        out = self._profile_read_stages()
+        out["ms_slot_span"] = sp.value
+        out["n_span"] = ns.value
+        return out
+
+    def _profile_read_stages(self):
         ms, n = (C.c_double * 5)(), C.c_int()
         L.check(L.lib.mkf_batch_profile_read_stages(self._h, ms, C.byref(n)))
         return dict(ms_bounds=ms[0], ms_share_keys=ms[1], ms_slot_kernel=ms[2], ms_repair=ms[3], ms_resample=ms[4],
