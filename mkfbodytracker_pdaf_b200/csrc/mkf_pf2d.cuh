@@ -234,7 +234,34 @@ static bool pf2d_gaussian(int d, const double* s, double* inv, double* det_s)
             inv[i * d + c] = t * Lm[i * d + i];
         }
     }
-    for (int i = 0; i < d; i++) det *= (1.0 / Lm[i * d + i]) * (1.0 / Lm[i * d + i]);
+    {   // cv::determinant(s) is a partially pivoted LU on a copy (not the Cholesky factor above): the pivots' reciprocals
+        // are multiplied up, then inverted once -- the last bits of det_s follow that order
+        std::vector<double> U(s, s + (size_t)d * d);
+        double acc = 1.0;
+        for (int c = 0; c < d && acc != 0.0; c++) {
+            int piv = c;
+            for (int r = c + 1; r < d; r++)
+                if (std::fabs(U[r * d + c]) > std::fabs(U[piv * d + c])) piv = r;
+            if (std::fabs(U[piv * d + c]) < 2.220446049250313e-16) { acc = 0.0; break; }
+            if (piv != c) {
+                for (int q = c; q < d; q++) std::swap(U[c * d + q], U[piv * d + q]);
+                acc = -acc;
+            }
+            const double neg_rcp = -1 / U[c * d + c];
+            for (int r = c + 1; r < d; r++) {
+                const double f = U[r * d + c] * neg_rcp;
+                for (int q = c + 1; q < d; q++) U[r * d + q] += f * U[c * d + q];
+            }
+            U[c * d + c] = -neg_rcp;
+        }
+        if (acc != 0.0) {
+            // sign first, then the reciprocal pivots in order
+            double r = acc;
+            for (int c = 0; c < d; c++) r *= U[c * d + c];
+            det = 1. / r;
+        } else
+            det = 0.0;
+    }
     *det_s = 1.0 / (std::pow(2.0 * 3.14159265358979323846, d / 2.0) * std::sqrt(det));
     return true;
 }

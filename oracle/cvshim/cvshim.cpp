@@ -153,6 +153,28 @@ int LU(double* A, size_t astep, int m, double* b, size_t bstep, int n)
     return p;
 }
 
+// cv::determinant (core/src/lapack.cpp, OpenCV 2.4): closed forms for 1 x 1 .. 3 x 3, otherwise LU on a copy with
+// det = sign / prod(stored diagonal) -- LU() leaves the RECIPROCALS of the pivots on the diagonal
+double determinant(const Mat& m)
+{
+    cvshim_assert(m.rows == m.cols && m.rows > 0, "determinant needs a square matrix");
+    const int n = m.rows;
+#define Md(y, x) m.at<double>(y, x)
+    if (n == 1) return Md(0, 0);
+    if (n == 2) return Md(0, 0) * Md(1, 1) - Md(0, 1) * Md(1, 0);
+    if (n == 3)
+        return Md(0, 0) * (Md(1, 1) * Md(2, 2) - Md(1, 2) * Md(2, 1)) - Md(0, 1) * (Md(1, 0) * Md(2, 2) - Md(1, 2) * Md(2, 0)) +
+               Md(0, 2) * (Md(1, 0) * Md(2, 1) - Md(1, 1) * Md(2, 0));
+#undef Md
+    Mat a = m.clone();
+    double result = LU(a.ptr<double>(), a.step, n, 0, 0, 0);
+    if (result) {
+        for (int i = 0; i < n; i++) result *= a.at<double>(i, i);
+        result = 1. / result;
+    }
+    return result;
+}
+
 double invert(const Mat& src, Mat& dst, int method)
 {
     cvshim_assert(src.rows == src.cols, "invert needs a square matrix");
@@ -380,6 +402,22 @@ void randn(Mat& dst, const Mat& mean, const Mat& stddev)
     std::vector<double> rec;
     for (int r = 0; r < dst.rows; r++)
         for (int c = 0; c < dst.cols * cn; c++) rec.push_back(dst.ptr<double>(r)[c]);
+    cvshim_random_log().push_back(rec);
+}
+// scalar form cv::randn(dst, 0, 5) on a view (src/pf2D.cpp:96-98): dst = mean + stddev * N(0, 1) per element, same
+// Gaussian source as above
+void randn(const Mat& dstc, double mean, double stddev)
+{
+    Mat dst = dstc;
+    std::vector<double> rec;
+    for (int r = 0; r < dst.rows; r++)
+        for (int c = 0; c < dst.cols; c++) {
+            const double u1 = g_the_rng.uniform(0.0, 1.0), u2 = g_the_rng.uniform(0.0, 1.0);
+            const double z = std::sqrt(-2.0 * std::log(1.0 - u1)) * std::cos(2 * M_PI * u2);
+            const double v = z * stddev + mean;
+            dst.el(r, c) = v;
+            rec.push_back(v);
+        }
     cvshim_random_log().push_back(rec);
 }
 std::vector<std::vector<double> >& cvshim_random_log()
@@ -811,5 +849,7 @@ MatExpr operator*(double s, const Mat& a) { return makeAddEx(a, Mat(), s, 0); }
 MatExpr operator*(const Mat& a, double s) { return makeAddEx(a, Mat(), s, 0); }
 MatExpr operator*(double s, const MatExpr& e) { return expr_scale(e, s); }
 MatExpr operator*(const MatExpr& e, double s) { return expr_scale(e, s); }
+MatExpr operator/(const MatExpr& e, double s) { return expr_scale(e, 1. / s); }
+MatExpr operator/(const Mat& a, double s) { return makeAddEx(a, Mat(), 1. / s, 0); }
 
 } // namespace cv

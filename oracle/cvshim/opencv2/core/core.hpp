@@ -122,6 +122,7 @@ class Mat {
     uchar* data;
     Mat() : rows(0), cols(0), step(0), data(0), cn_(1), depth_(CV_64F) {}
     Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(0), cn_(1), depth_(CV_64F) { create(r, c, type); }
+    Mat(Size sz, int type) : rows(0), cols(0), step(0), data(0), cn_(1), depth_(CV_64F) { create(sz.height, sz.width, type); }
     Mat(const Mat& m)
         : rows(m.rows), cols(m.cols), step(m.step), data(m.data), cn_(m.cn_), depth_(m.depth_), buf_(m.buf_)
     {
@@ -335,7 +336,10 @@ Mat repeat(const Mat& src, int ny, int nx);
 void split(const Mat& src, std::vector<Mat>& mv);
 void vconcat(const Mat& a, const Mat& b, Mat& dst);
 void randn(Mat& dst, const Mat& mean, const Mat& stddev);
+void randn(const Mat& dst, double mean, double stddev); // scalar form on a (view of a) CV_64F matrix (src/pf2D.cpp:96-98)
 void randu(const Mat& dst, double low, double high); // fills a (view of a) CV_64F matrix
+inline void randu(const Mat& dst, const Scalar& low, const Scalar& high) { randu(dst, low.val[0], high.val[0]); }
+double determinant(const Mat& m); // core/src/lapack.cpp: closed forms up to 3 x 3, LU beyond
 void hconcat(const Mat& a, const Mat& b, Mat& dst);
 // every array produced by randn / randu, in call order (the harness replays the reference's internal draws)
 std::vector<std::vector<double> >& cvshim_random_log();
@@ -468,6 +472,8 @@ MatExpr operator*(double s, const Mat& a);
 MatExpr operator*(const Mat& a, double s);
 MatExpr operator*(double s, const MatExpr& e);
 MatExpr operator*(const MatExpr& e, double s);
+MatExpr operator/(const MatExpr& e, double s); // MatOp::divide(e, s) = multiply(e, 1. / s)
+MatExpr operator/(const Mat& a, double s);
 
 } // namespace cv
 

@@ -824,6 +824,7 @@ struct orc_pf2d {
     // randomisation of the constructor / degenerate branch (src/pf2D.cpp:58-70,232-250) from the counter generator
     uint64_t seed = 0, track = 0, epoch = 0;
     int side = 0, im_w = 640, im_h = 480;
+    int noise_scaled = 0; // 1: `noise` holds what predict() adds (cv::randn(.., 0, 5) values), not standard normals
 };
 static void pf2d_randomise(orc_pf2d* p)
 {
@@ -841,6 +842,7 @@ extern "C" void orc_pf2d_set_random(orc_pf2d* p, uint64_t seed, uint64_t track, 
     p->im_h = im_h;
 }
 // ParticleFilter(numParticles, numDims, side1) (src/pf2D.cpp:44-71): uniform weights, particles across the image
+extern "C" void orc_pf2d_set_noise_scaled(orc_pf2d* p, int on) { p->noise_scaled = on; }
 extern "C" void orc_pf2d_randomise(orc_pf2d* p)
 {
     p->epoch = 0;
@@ -848,7 +850,7 @@ extern "C" void orc_pf2d_randomise(orc_pf2d* p)
     pf2d_randomise(p);
 }
 
-// cv::invert(DECOMP_CHOLESKY) and cv::determinant restated with plain LU / Cholesky solves:
+// cv::invert(DECOMP_CHOLESKY) = Cholesky solve against the identity; cv::determinant = pivoted LU (as OpenCV 2.4 does):
 // sigma_i = inv(s), det_s = 1/(pow(2 pi, d/2) * sqrt(det(s)))   (src/pf2D.cpp:28-37)
 extern "C" orc_pf2d* orc_pf2d_create(int N, int d, int K, const double* means, const double* covs,
                                      const double* weights)
@@ -882,7 +884,15 @@ extern "C" orc_pf2d* orc_pf2d_create(int N, int d, int K, const double* means, c
                     inv[i * d + c] = t * L[i * d + i];
                 }
             }
-            for (int i = 0; i < d; i++) det *= (1.0 / L[i * d + i]) * (1.0 / L[i * d + i]);
+        }
+        {   // cv::determinant(s) for n > 3 (OpenCV 2.4 lapack.cpp): LU on a copy, sign / prod(stored reciprocal pivots)
+            std::vector<double> a(s, s + (size_t)d * d);
+            double r = lu_impl(a.data(), d, nullptr, 0);
+            if (r) {
+                for (int i = 0; i < d; i++) r *= a[i * d + i];
+                r = 1. / r;
+            }
+            det = r;
         }
         std::copy(inv.begin(), inv.end(), p->sigma_i.begin() + (size_t)k * d * d);
         p->det_s[k] = 1.0 / (std::pow(2.0 * M_PI, d / 2.0) * std::sqrt(det));
@@ -993,7 +1003,9 @@ extern "C" int orc_pf2d_update(orc_pf2d* p, const double* meas, double u, const 
     if (noise) {
         for (int i = 0; i < N; i++)
             for (int c = 0; c < d && c < 8; c++)
-                p->particles[(size_t)i * d + c] = p->particles[(size_t)i * d + c] + noise[(size_t)i * d + c] * 5.0;
+                p->particles[(size_t)i * d + c] =
+                    p->particles[(size_t)i * d + c] +
+                    (p->noise_scaled ? noise[(size_t)i * d + c] : noise[(size_t)i * d + c] * 5.0);
     }
     return status;
 }

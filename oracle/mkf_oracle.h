@@ -113,6 +113,8 @@ void orc_pf2d_set_particles(orc_pf2d* p, const double* particles /* N x d */);
 /* constructor / degenerate-branch randomisation (src/pf2D.cpp:44-71,232-250) from the counter generator of mkf_synth.h */
 void orc_pf2d_set_random(orc_pf2d* p, uint64_t seed, uint64_t track, int side, int im_w, int im_h);
 void orc_pf2d_randomise(orc_pf2d* p);
+/* 1: the `noise` of orc_pf2d_update is what predict() adds (the reference's cv::randn(.., 0, 5) values), not N(0,1) draws */
+void orc_pf2d_set_noise_scaled(orc_pf2d* p, int on);
 /* include/mkf_expf.h (glibc's expf restated) and the host libm's expf, for tests/test_expf.py */
 float orc_expf(float x);
 float orc_libm_expf(float x);

@@ -90,6 +90,8 @@ def lib():
     L.orc_pf2d_set_random.restype = None
     L.orc_pf2d_randomise.argtypes = [C.c_void_p]
     L.orc_pf2d_randomise.restype = None
+    L.orc_pf2d_set_noise_scaled.argtypes = [C.c_void_p, C.c_int]
+    L.orc_pf2d_set_noise_scaled.restype = None
     L.orc_expf.argtypes = [C.c_float]
     L.orc_expf.restype = C.c_float
     L.orc_libm_expf.argtypes = [C.c_float]
@@ -303,6 +305,10 @@ class Pf2d:
     def randomise(self):
         """the constructor's draw: particles across the image, weights 1/N"""
         lib().orc_pf2d_randomise(self.h)
+
+    def set_noise_scaled(self, on=True):
+        """update()'s `noise` then holds what predict() adds (already x 5), as the reference's cv::randn calls return it"""
+        lib().orc_pf2d_set_noise_scaled(self.h, 1 if on else 0)
 
     def get(self):
         p = np.zeros((self.N, self.d))

@@ -303,3 +303,83 @@ class DropinTracker(RefTracker):
         _LIB_DROPIN.ref_dropin_configure.argtypes = [C.c_int]
         _LIB_DROPIN.ref_dropin_configure(self._alias_mode)
         return _LIB_DROPIN
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's LEGACY plain particle filter: its own src/pf2D.cpp compiled against the shim (libref_pf2d.so)
+# ---------------------------------------------------------------------------------------------------------------------
+SO_PF2D = os.path.join(_HERE, "_ref", "libref_pf2d.so")
+_LIB_PF2D = None
+
+
+def pf2d_available() -> bool:
+    available()  # `make ref` builds both libraries when the reference sources are present
+    return os.path.exists(SO_PF2D)
+
+
+def lib_pf2d():
+    global _LIB_PF2D
+    if _LIB_PF2D is None:
+        if not pf2d_available():
+            raise FileNotFoundError(SO_PF2D)
+        L = C.CDLL(SO_PF2D)
+        L.refpf_create.restype = C.c_void_p
+        L.refpf_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64]
+        L.refpf_destroy.argtypes = [C.c_void_p]
+        L.refpf_load_gaussian.argtypes = [C.c_void_p, _dp, _dp, C.c_double]
+        L.refpf_get_gmm.argtypes = [C.c_void_p, _dp, _dp]
+        L.refpf_set_particles.argtypes = [C.c_void_p, _dp]
+        L.refpf_get.argtypes = [C.c_void_p, _dp, _dp]
+        L.refpf_update.restype = C.c_double
+        L.refpf_update.argtypes = [C.c_void_p, _dp, C.c_uint, _dp, C.POINTER(C.c_int)]
+        L.refpf_estimate.argtypes = [C.c_void_p, _dp]
+        _LIB_PF2D = L
+    return _LIB_PF2D
+
+
+class RefPf2d:
+    """the reference's own legacy ParticleFilter(numParticles, numDims, side1) of src/pf2D.{h,cpp}"""
+
+    def __init__(self, N, d, side, means, covs, weights, rng_seed=1):
+        self.N, self.d, self.K = N, d, len(weights)
+        self.h = lib_pf2d().refpf_create(N, d, int(side), int(rng_seed))
+        for k in range(self.K):
+            m, c = _f(means[k]), _f(covs[k])
+            lib_pf2d().refpf_load_gaussian(self.h, _p(m), _p(c), float(weights[k]))
+
+    def gmm(self):
+        si = np.zeros((self.K, self.d, self.d))
+        ds = np.zeros(self.K)
+        lib_pf2d().refpf_get_gmm(self.h, _p(si), _p(ds))
+        return si, ds
+
+    def set_particles(self, x):
+        x = _f(x)
+        lib_pf2d().refpf_set_particles(self.h, _p(x))
+
+    def get(self):
+        x = np.zeros((self.N, self.d))
+        w = np.zeros(self.N)
+        lib_pf2d().refpf_get(self.h, _p(x), _p(w))
+        return x, w
+
+    def update(self, meas, srand_seed):
+        """returns (u drawn by resample(), noise added by predict() (N x d), degenerate flag)"""
+        meas = _f(meas)
+        noise = np.zeros((self.N, self.d))
+        deg = C.c_int(0)
+        u = lib_pf2d().refpf_update(self.h, _p(meas), int(srand_seed), _p(noise), C.byref(deg))
+        return u, noise, bool(deg.value)
+
+    def estimate(self):
+        e = np.zeros(self.d)
+        lib_pf2d().refpf_estimate(self.h, _p(e))
+        return e
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib_pf2d().refpf_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
