@@ -15,6 +15,7 @@
 #include "mkf_internal.h"
 #include "mkf_kernels.cuh"
 #include "mkf_runs.cuh"
+#include "mkf_heads_tma.cuh"
 #include "../../include/mkf_expf.h"
 
 // events per profiled update: start | bounds | share keys | slot kernel | repair | resample
@@ -193,6 +194,8 @@ struct mkf_batch {
     bool est_valid = false;
     cudaEvent_t est_ready = nullptr, est_done[2] = {nullptr, nullptr};
     bool est_used[2] = {false, false};
+    bool aos = false;         // st[cur] holds contiguous records (mkf_heads_tma.cuh) instead of tiles: only between
+                              // run-length frames; relayout() converts before anything else reads the state
     bool run_mode = false;    // `runs` describes the current particle set
     bool slots_valid = true;  // parent / src / rep / w_raw describe it too (false after a run-level frame until
                               // ensure_slots() replays the resample per slot)
@@ -579,6 +582,7 @@ extern "C" int mkf_batch_reset(mkf_batch* b, const double* u_init, int mem)
     CK(cudaMemsetAsync(b->unsorted, 0, (size_t)b->T * sizeof(uint32_t), b->stream));
     if ((rc = launch_bounds_kernel(b, d_u))) return rc;
     b->cur = 0;
+    b->aos = false;
     b->shared = false;
     b->run_mode = false;
     b->slots_valid = true;
@@ -651,8 +655,29 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
 
 // per-slot views of a run-level particle set (mkf_runs.cuh): rep[] from the head table, then the exact per-slot resampler
 // replays the last resample from the same head weights, normaliser, draw and seed -> parent[], src[], w_raw[]
+// st[cur] between the tile layout and contiguous records, out of place into the idle ping-pong buffer.  In run-length
+// mode only the records the last frame wrote are live (head i of track t at t*N + i, i < nheads[t]).
+static int relayout(mkf_batch* b, bool to_aos)
+{
+    if (b->aos == to_aos) return MKF_OK;
+    const int* cnt = b->run_mode ? b->nheads : nullptr;
+    if (b->m->d == 12)
+        k_relayout<12><<<(unsigned)b->T, 128, 0, b->stream>>>(b->st[b->cur], b->st[b->cur ^ 1], cnt, b->N, to_aos ? 1 : 0);
+    else
+        k_relayout<10><<<(unsigned)b->T, 128, 0, b->stream>>>(b->st[b->cur], b->st[b->cur ^ 1], cnt, b->N, to_aos ? 1 : 0);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    b->cur ^= 1;
+    b->aos = to_aos;
+    return MKF_OK;
+}
+
 static int ensure_slots(mkf_batch* b)
 {
+    if (b->aos) {
+        int rc0 = relayout(b, false);
+        if (rc0) return rc0;
+    }
     if (!b->run_mode || b->slots_valid) return MKF_OK;
     k_expand_rep<<<grid_for(b->T, 4), 128, 0, b->stream>>>(b->hmeta, b->nheads, b->T, b->N, b->rep);
     MKF_LAUNCHED();
@@ -719,6 +744,15 @@ static unsigned heads_grid(const mkf_batch* b, int sms)
     return (unsigned)g;
 }
 
+static bool heads_tma_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("MKF_HEADS_TMA");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static int heads_block()
 {
     static const int v = [] {
@@ -729,12 +763,52 @@ static int heads_block()
     return v;
 }
 
+// Tracks whose records the heads kernel keeps in L2 (SlotArgs::l2_tracks).  A run-length track holds ~N/8 records of
+// 720 bytes in each of the two ping-pong buffers; MKF_L2_RESIDENT_MB (default below) is the L2 budget those may take,
+// MKF_L2_TRACKS sets the track count directly (0 switches the hints off).
+static int l2_resident_tracks(const mkf_batch* b)
+{
+    static const long long forced = [] {
+        const char* e = getenv("MKF_L2_TRACKS");
+        return e ? atoll(e) : -1ll;
+    }();
+    static const long long budget_mb = [] {
+        const char* e = getenv("MKF_L2_RESIDENT_MB");
+        return e ? atoll(e) : 0ll;
+    }();
+    long long t;
+    if (forced >= 0)
+        t = forced;
+    else {
+        const long long per_track = 2ll * (b->N / 8 + b->m->K) * b->lay.np * 16;
+        t = (budget_mb << 20) / (per_track > 0 ? per_track : 1);
+    }
+    if (t > b->T) t = b->T;
+    return (int)t;
+}
+
 // one frame on a run-length particle set (mkf_runs.cuh): frame heads -> slot update of the heads -> repair -> resample
 static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layout, const double* d_uind,
                               const double* d_upost, const uint64_t* d_seeds, int seed_stride, int seed_off,
                               cudaEvent_t* pe)
 {
     const mkf_model* m = b->m;
+    // MKF_FUSED=1: the single-launch frame kernel k_frame_fused instead of the three grid-wide kernels (k_frame_heads,
+    // k_slot_update_heads_direct, k_resample_runs).  Measured at 4096 x 500: 0.147 ms per frame against 0.104 -- a warp
+    // that owns its tracks walks their bookkeeping latency chains one after the other with only 8 warps per SM to hide
+    // them -- so it is an experiment kept for A/B runs, not the default (DESIGN.md section 7).
+    const bool fused = [] {
+        const char* e = getenv("MKF_FUSED");
+        return e && e[0] == '1';
+    }();
+    // the heads' slot update with TMA-staged contiguous records (mkf_heads_tma.cuh) unless MKF_HEADS_TMA=0 or the model
+    // constants leave no room for the stages (K > ~50)
+    const bool use_tma = !fused && heads_tma_enabled() &&
+                         (m->d == 12 ? HeadsTmaLay<12>::smem_bytes(m->K) : HeadsTmaLay<10>::smem_bytes(m->K)) <= 226 * 1024;
+    {
+        int rc0 = relayout(b, use_tma);
+        if (rc0) return rc0;
+    }
     if (!b->run_mode) { // entering from a per-slot set (reset, upload, a per-slot frame): its run list
         mkf_launch(k_runs_from_slots, grid_for(b->T, 4), 128, 0, b->stream, b->gather_index(), b->T, b->N, b->runs,
                    b->nruns);
@@ -777,6 +851,9 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     a.dedup = 1;
     a.split = 1;
     a.rep = nullptr;
+    a.l2_tracks = l2_resident_tracks(b);
+    a.aos = use_tma ? 1 : 0;
+    a.st_in_alias = a.st_in;
     if (pe && b->prof_ts) a.ts = b->prof_ts + 2 * (size_t)b->prof_n;
     ResampleRunsArgs ra{};
     ra.T = b->T;
@@ -798,6 +875,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     b->est_slot ^= 1;
     if (b->est_used[b->est_slot]) CK(cudaStreamWaitEvent(b->stream, b->est_done[b->est_slot], 0));
     ra.st_new = b->st[b->cur ^ 1];
+    ra.aos = use_tma ? 1 : 0;
     ra.Dpose = m->D;
     ra.recon = b->d_recon;
     ra.pmean = b->d_pmean;
@@ -812,18 +890,12 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         if (first_on_this_device(seen)) {
             CK(cudaFuncSetAttribute(k_slot_update_heads_direct<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CK(cudaFuncSetAttribute(k_slot_update_heads_direct<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update_heads_tma<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            CK(cudaFuncSetAttribute(k_slot_update_heads_tma<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             CK(cudaFuncSetAttribute(k_frame_fused<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
             CK(cudaFuncSetAttribute(k_frame_fused<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         }
     }
-    // MKF_FUSED=1: the single-launch frame kernel k_frame_fused instead of the three grid-wide kernels (k_frame_heads,
-    // k_slot_update_heads_direct, k_resample_runs).  Measured at 4096 x 500: 0.147 ms per frame against 0.104 -- a warp
-    // that owns its tracks walks their bookkeeping latency chains one after the other with only 8 warps per SM to hide
-    // them -- so it is an experiment kept for A/B runs, not the default (DESIGN.md section 7).
-    const bool fused = [] {
-        const char* e = getenv("MKF_FUSED");
-        return e && e[0] == '1';
-    }();
     if (fused) {
         // persistent grid: 2 CTAs of 4 warps per SM, but no more warps than tracks
         long long ctas = 2ll * sm_count(b->device);
@@ -845,7 +917,15 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         if (pe) cudaEventRecord(pe[2], b->stream);
         const unsigned hblock = (unsigned)heads_block();
         const unsigned hgrid = heads_grid(b, sm_count(b->device)) * (128 / hblock);
-        if (m->d == 12)
+        if (use_tma) {
+            const unsigned tgrid = (unsigned)sm_count(b->device);
+            if (m->d == 12)
+                mkf_launch(k_slot_update_heads_tma<12>, tgrid, 128, HeadsTmaLay<12>::smem_bytes(m->K), b->stream, a,
+                           b->head_count + (b->head_flip ^ 1));
+            else
+                mkf_launch(k_slot_update_heads_tma<10>, tgrid, 128, HeadsTmaLay<10>::smem_bytes(m->K), b->stream, a,
+                           b->head_count + (b->head_flip ^ 1));
+        } else if (m->d == 12)
             mkf_launch(k_slot_update_heads_direct<12>, hgrid, hblock, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
         else
             mkf_launch(k_slot_update_heads_direct<10>, hgrid, hblock, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
@@ -1251,6 +1331,10 @@ static bool launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose) // f
 }
 static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
 {
+    if (b->aos && !(b->run_mode && b->est_valid)) { // the estimate kernels read tiles
+        int rc0 = relayout(b, false);
+        if (rc0) return rc0;
+    }
     const bool kernel = (b->m->d == 12) ? launch_estimate_d<12>(b, d_xbar, d_pose) : launch_estimate_d<10>(b, d_xbar, d_pose);
     if (kernel) MKF_LAUNCHED();
     CK(cudaGetLastError());
@@ -1415,6 +1499,7 @@ extern "C" int mkf_batch_upload(mkf_batch* b, const double* x, const double* P, 
     if ((rc = in_ptr(b, x, (size_t)b->total * d, mem, b->in_x, &dx))) return rc;
     if ((rc = in_ptr(b, P, (size_t)b->total * d * d, mem, b->in_p, &dP))) return rc;
     b->cur = 0;
+    b->aos = false;
     b->shared = false;
     b->run_mode = false;
     b->slots_valid = true;

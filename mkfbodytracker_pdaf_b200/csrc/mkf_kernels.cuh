@@ -94,8 +94,52 @@ struct SlotArgs {
     // profiling only (null otherwise): {earliest CTA start, latest CTA end} of the slot kernel in %globaltimer
     // nanoseconds -- the kernel's own span on the device, free of the launch gap an event-bracketed kernel pays
     unsigned long long* ts;
+    // L2-resident tracks (run-length pipeline): the records of tracks [0, l2_tracks) are read and written with the
+    // L2 evict_last policy -- frame f+1 overwrites the lines frame f-1 wrote (ping-pong buffers, same addresses), so in
+    // steady state those tracks cause no DRAM traffic at all -- every other track's with evict_first (read once, written
+    // once per frame: nothing of theirs is worth a line).  0: no hints (plain __ldg / __stcs).
+    int l2_tracks;
+    // run-length pipeline with contiguous records (mkf_heads_tma.cuh): st_in / st_out hold record r at r * NP double2
+    // instead of the tile layout; st_in_alias == st_in (see k_slot_update_heads_tma)
+    int aos;
+    const double2* __restrict__ st_in_alias;
 };
+
+// record `sp` of a state buffer in either layout: pair p lives at mkf_rec<D>(st, sp, aos)[mkf_rec_off<D>(p, aos)]
+template <int D>
+__device__ __forceinline__ long long mkf_rec_base(long long sp, int aos)
+{
+    using L = SlotLay<D>;
+    return aos ? sp * L::NP : (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+}
+template <int D>
+__device__ __forceinline__ int mkf_rec_off(int p, int aos)
+{
+    return aos ? p : SlotLay<D>::po(p);
+}
 #define MKF_MEAS_CAND 2
+
+// L2 cache-policy descriptors (createpolicy) and 16-byte accesses that carry one
+// The policy operand travels in a uniform register: it has to be a constant the compiler can see (the value
+// `createpolicy.fractional.L2::evict_last / evict_first ..., 1.0` produces; routed through a vector register by an asm
+// output it costs two R2UR per access).
+#define MKF_L2_EVICT_LAST 0x14F0000000000000ull
+#define MKF_L2_EVICT_FIRST 0x12F0000000000000ull
+template <bool KEEP>
+__device__ __forceinline__ constexpr uint64_t mkf_l2_policy()
+{
+    return KEEP ? MKF_L2_EVICT_LAST : MKF_L2_EVICT_FIRST;
+}
+__device__ __forceinline__ double2 mkf_ldg_policy(const double2* p, uint64_t pol)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void mkf_stg_policy(double2* p, double2 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long mkf_globaltimer()
 {
@@ -1048,11 +1092,29 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
         const int k = rec.w & 0xff;
         const double2* __restrict__ src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
         double v[L::NE];
+        if (t < a.l2_tracks) {
+            const uint64_t pol = mkf_l2_policy<true>();
 #pragma unroll
-        for (int p = 0; p < L::NP; p++) {
-            const double2 q = __ldg(src + L::po(p));
-            v[2 * p] = q.x;
-            if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+            for (int p = 0; p < L::NP; p++) {
+                const double2 q = mkf_ldg_policy(src + L::po(p), pol);
+                v[2 * p] = q.x;
+                if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+            }
+        } else if (a.l2_tracks) {
+            const uint64_t pol = mkf_l2_policy<false>();
+#pragma unroll
+            for (int p = 0; p < L::NP; p++) {
+                const double2 q = mkf_ldg_policy(src + L::po(p), pol);
+                v[2 * p] = q.x;
+                if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < L::NP; p++) {
+                const double2 q = __ldg(src + L::po(p));
+                v[2 * p] = q.x;
+                if (2 * p + 1 < L::NE) v[2 * p + 1] = q.y;
+            }
         }
         double zc[MKF_M];
         if (a.meas_layout == MKF_MEAS_CAND)
@@ -1065,12 +1127,23 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
         const bool ok = slot_math<D, false>(v, cst + k * L::CS, zc, a.r, a.chol_mode, a.stage, w);
         if (!ok) atomicOr(a.status + t, MKF_ST_CHOL_FAIL);
         double2* __restrict__ dst = a.st_out + (so_rec >> 5) * (long long)L::TILE2 + (so_rec & 31) * L::H;
+        if (t < a.l2_tracks) {
+            const uint64_t pol = mkf_l2_policy<true>();
 #pragma unroll
-        for (int p = 0; p < L::NP; p++) {
-            double2 q;
-            q.x = v[2 * p];
-            q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-            __stcs(dst + L::po(p), q);
+            for (int p = 0; p < L::NP; p++) {
+                double2 q;
+                q.x = v[2 * p];
+                q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                mkf_stg_policy(dst + L::po(p), q, pol);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < L::NP; p++) {
+                double2 q;
+                q.x = v[2 * p];
+                q.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
+                __stcs(dst + L::po(p), q);
+            }
         }
         a.w_rec[so_rec] = w;
     }

@@ -352,6 +352,7 @@ struct ResampleRunsArgs {
     double* __restrict__ est_xbar;  // T x d
     double* __restrict__ est_pose;  // T x Dpose
     double* __restrict__ est_pose2; // the association step's copy of the pose (or null)
+    int aos;                        // st_new holds contiguous records (mkf_heads_tma.cuh)
 };
 
 // One track, by one warp (every lane enters).  coef: the reconstruction coefficients staged in shared memory as
@@ -481,11 +482,11 @@ __device__ __forceinline__ void mkf_resample_runs_track(const ResampleRunsArgs& 
                 if (c > 0) {
                     rt[nr + __popc(msk & ((1u << lane) - 1u))] = make_int2(i, c);
                     const long long sp = t * N + i; // head i's record, just written by the slot kernel
-                    const double2* __restrict__ src = a.st_new + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+                    const double2* __restrict__ src = a.st_new + mkf_rec_base<D>(sp, a.aos);
                     const double m = (double)c;
 #pragma unroll
                     for (int p = 0; p < D / 2; p++) {
-                        const double2 q = __ldg(src + L::po(p));
+                        const double2 q = __ldg(src + mkf_rec_off<D>(p, a.aos));
                         xs[2 * p] = fma(m, q.x, xs[2 * p]);
                         xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
                     }
@@ -541,11 +542,11 @@ __device__ __forceinline__ void mkf_resample_runs_track(const ResampleRunsArgs& 
         for (int r = lane; r < nr; r += 32) {
             const int2 rn = __ldcg(rt + r); // written by lane 0 just above
             const long long sp = t * N + rn.x;
-            const double2* __restrict__ src = a.st_new + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+            const double2* __restrict__ src = a.st_new + mkf_rec_base<D>(sp, a.aos);
             const double m = (double)rn.y;
 #pragma unroll
             for (int p = 0; p < D / 2; p++) {
-                const double2 q = __ldg(src + L::po(p));
+                const double2 q = __ldg(src + mkf_rec_off<D>(p, a.aos));
                 xs[2 * p] = fma(m, q.x, xs[2 * p]);
                 xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
             }
@@ -818,10 +819,10 @@ __global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const 
         for (int i = threadIdx.x; i < nh; i += 128) {
             const int4 m = hmeta[t * a.N + i];
             const long long sp = t * a.N + m.x, so = t * a.N + i;
-            const double2* src = a.st_in + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+            const double2* src = a.st_in + mkf_rec_base<D>(sp, a.aos);
             double v[L::NE];
             for (int p = 0; p < L::NP; p++) {
-                const double2 qq = src[L::po(p)];
+                const double2 qq = src[mkf_rec_off<D>(p, a.aos)];
                 v[2 * p] = qq.x;
                 if (2 * p + 1 < L::NE) v[2 * p + 1] = qq.y;
             }
@@ -831,12 +832,12 @@ __global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const 
             else
                 mkf_load_meas(a, t, 0, zc);
             slot_math<D, true>(v, a.comp_const + (long long)(m.y & 0xff) * L::CS, zc, a.r, a.chol_mode, a.stage, w);
-            double2* dst = a.st_out + (so >> 5) * (long long)L::TILE2 + (so & 31) * L::H;
+            double2* dst = a.st_out + mkf_rec_base<D>(so, a.aos);
             for (int p = 0; p < L::NP; p++) {
                 double2 qq;
                 qq.x = v[2 * p];
                 qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
-                dst[L::po(p)] = qq;
+                dst[mkf_rec_off<D>(p, a.aos)] = qq;
             }
             a.w_rec[so] = w;
         }
