@@ -185,6 +185,9 @@ struct mkf_batch {
     int* nruns = nullptr;
     int4* hmeta = nullptr;
     int* nheads = nullptr;
+    int* lbase = nullptr; // 2 x T: first list position of every track's heads (contiguous records), ping-pong by lb_flip
+    int lb_flip = 0;
+    double2* xs = nullptr; // the heads' means tiled by list position (allocated with the first contiguous-record frame)
     double* u_keep = nullptr;
     uint64_t* seed_keep = nullptr;
     // the estimate of the current set as k_resample_runs left it: est[slot] = [xbar T x d | pose T x D]; two slots so that
@@ -321,7 +324,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
-    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->alias_list, b->alias_cnt, b->prof_ts, b->d_comp, b->d_init,
+    void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->lbase, b->xs, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->alias_list, b->alias_cnt, b->prof_ts, b->d_comp, b->d_init,
                     b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -420,6 +423,7 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
                 (rc = dmalloc((void**)&b->nruns, (size_t)T * sizeof(int))) ||
                 (rc = dmalloc((void**)&b->hmeta, (size_t)b->total * sizeof(int4))) ||
                 (rc = dmalloc((void**)&b->nheads, (size_t)T * sizeof(int))) ||
+                (rc = dmalloc((void**)&b->lbase, (size_t)T * 2 * sizeof(int))) ||
                 (rc = dmalloc((void**)&b->u_keep, (size_t)T * sizeof(double))) ||
                 (rc = dmalloc((void**)&b->seed_keep, (size_t)T * sizeof(uint64_t))) ||
                 (rc = dmalloc((void**)&b->est[0], (size_t)T * (m->d + m->D) * sizeof(double))) ||
@@ -656,15 +660,17 @@ static int run_resample(cudaStream_t stream, long long nt, const double* d_w, in
 // per-slot views of a run-level particle set (mkf_runs.cuh): rep[] from the head table, then the exact per-slot resampler
 // replays the last resample from the same head weights, normaliser, draw and seed -> parent[], src[], w_raw[]
 // st[cur] between the tile layout and contiguous records, out of place into the idle ping-pong buffer.  In run-length
-// mode only the records the last frame wrote are live (head i of track t at t*N + i, i < nheads[t]).
+// mode only the records the last frame wrote are live (head i of track t, i < nheads[t]: at t*N + i in tiles, at
+// lbase[t] + i as contiguous records).
 static int relayout(mkf_batch* b, bool to_aos)
 {
     if (b->aos == to_aos) return MKF_OK;
     const int* cnt = b->run_mode ? b->nheads : nullptr;
+    int* lb = b->lbase + (size_t)b->lb_flip * b->T;
     if (b->m->d == 12)
-        k_relayout<12><<<(unsigned)b->T, 128, 0, b->stream>>>(b->st[b->cur], b->st[b->cur ^ 1], cnt, b->N, to_aos ? 1 : 0);
+        k_relayout<12><<<(unsigned)b->T, 128, 0, b->stream>>>(b->st[b->cur], b->st[b->cur ^ 1], cnt, b->N, to_aos ? 1 : 0, lb);
     else
-        k_relayout<10><<<(unsigned)b->T, 128, 0, b->stream>>>(b->st[b->cur], b->st[b->cur ^ 1], cnt, b->N, to_aos ? 1 : 0);
+        k_relayout<10><<<(unsigned)b->T, 128, 0, b->stream>>>(b->st[b->cur], b->st[b->cur ^ 1], cnt, b->N, to_aos ? 1 : 0, lb);
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     b->cur ^= 1;
@@ -753,6 +759,16 @@ static bool heads_tma_enabled()
     return on;
 }
 
+// shape of k_slot_update_heads_tma, MKF_HEADS_TMA_CFG = consumer warps * 100 + output stages * 10 + producer warps
+static int heads_tma_cfg()
+{
+    static const int v = [] {
+        const char* e = getenv("MKF_HEADS_TMA_CFG");
+        return e ? atoi(e) : 442;
+    }();
+    return v;
+}
+
 static int heads_block()
 {
     static const int v = [] {
@@ -803,8 +819,15 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     }();
     // the heads' slot update with TMA-staged contiguous records (mkf_heads_tma.cuh) unless MKF_HEADS_TMA=0 or the model
     // constants leave no room for the stages (K > ~50)
-    const bool use_tma = !fused && heads_tma_enabled() &&
-                         (m->d == 12 ? HeadsTmaLay<12>::smem_bytes(m->K) : HeadsTmaLay<10>::smem_bytes(m->K)) <= 226 * 1024;
+    const int tma_cfg = heads_tma_cfg(); // consumer warps * 100 + output stages * 10 + producer warps
+    size_t tma_smem = 0;
+#define MKF_TMA_CASES(X) X(4, 4, 2) X(4, 4, 0) X(4, 4, 4) X(4, 4, 1) X(6, 3, 2)
+#define MKF_TMA_SMEM(W_, O_, P_)                                                                                     \
+    if (tma_cfg == W_ * 100 + O_ * 10 + P_)                                                                           \
+        tma_smem = m->d == 12 ? HeadsTmaLay<12, W_, O_>::smem_bytes(m->K) : HeadsTmaLay<10, W_, O_>::smem_bytes(m->K);
+    MKF_TMA_CASES(MKF_TMA_SMEM)
+#undef MKF_TMA_SMEM
+    const bool use_tma = !fused && heads_tma_enabled() && tma_smem && tma_smem <= 226 * 1024;
     {
         int rc0 = relayout(b, use_tma);
         if (rc0) return rc0;
@@ -854,6 +877,24 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     a.l2_tracks = l2_resident_tracks(b);
     a.aos = use_tma ? 1 : 0;
     a.st_in_alias = a.st_in;
+    {
+        static std::atomic<int> frame_no{0};
+        f.dbg_frame = a.dbg_frame = frame_no.fetch_add(1, std::memory_order_relaxed);
+    }
+    static const bool no_xs = [] {
+        const char* e = getenv("MKF_NO_XS");
+        return e && e[0] == '1';
+    }();
+    if (use_tma && !b->xs && !no_xs) {
+        const size_t n32 = ((size_t)b->total + 31) / 32;
+        CK(cudaMalloc((void**)&b->xs, n32 * 32 * (size_t)(m->d / 2) * sizeof(double2)));
+    }
+    if (use_tma) { // records in list order: this frame's parents at lbase[lb_flip], its heads at lbase[lb_flip ^ 1]
+        a.xs = b->xs;
+        f.lbase_prev = a.lbase_prev = b->lbase + (size_t)b->lb_flip * b->T;
+        f.lbase_cur = b->lbase + (size_t)(b->lb_flip ^ 1) * b->T;
+        a.lbase_cur = f.lbase_cur;
+    }
     if (pe && b->prof_ts) a.ts = b->prof_ts + 2 * (size_t)b->prof_n;
     ResampleRunsArgs ra{};
     ra.T = b->T;
@@ -876,6 +917,9 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     if (b->est_used[b->est_slot]) CK(cudaStreamWaitEvent(b->stream, b->est_done[b->est_slot], 0));
     ra.st_new = b->st[b->cur ^ 1];
     ra.aos = use_tma ? 1 : 0;
+    ra.dbg_frame = a.dbg_frame;
+    ra.xs = use_tma ? b->xs : nullptr; // (null with MKF_NO_XS=1: the estimator then gathers from the records)
+    ra.lbase = use_tma ? b->lbase + (size_t)(b->lb_flip ^ 1) * b->T : nullptr;
     ra.Dpose = m->D;
     ra.recon = b->d_recon;
     ra.pmean = b->d_pmean;
@@ -890,8 +934,11 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         if (first_on_this_device(seen)) {
             CK(cudaFuncSetAttribute(k_slot_update_heads_direct<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CK(cudaFuncSetAttribute(k_slot_update_heads_direct<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_slot_update_heads_tma<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            CK(cudaFuncSetAttribute(k_slot_update_heads_tma<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+#define MKF_TMA_ATTR(W_, O_, P_)                                                                                      \
+    CK(cudaFuncSetAttribute(k_slot_update_heads_tma<12, W_, O_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+    CK(cudaFuncSetAttribute(k_slot_update_heads_tma<10, W_, O_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            MKF_TMA_CASES(MKF_TMA_ATTR)
+#undef MKF_TMA_ATTR
             CK(cudaFuncSetAttribute(k_frame_fused<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
             CK(cudaFuncSetAttribute(k_frame_fused<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         }
@@ -919,12 +966,16 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         const unsigned hgrid = heads_grid(b, sm_count(b->device)) * (128 / hblock);
         if (use_tma) {
             const unsigned tgrid = (unsigned)sm_count(b->device);
-            if (m->d == 12)
-                mkf_launch(k_slot_update_heads_tma<12>, tgrid, 128, HeadsTmaLay<12>::smem_bytes(m->K), b->stream, a,
-                           b->head_count + (b->head_flip ^ 1));
-            else
-                mkf_launch(k_slot_update_heads_tma<10>, tgrid, 128, HeadsTmaLay<10>::smem_bytes(m->K), b->stream, a,
-                           b->head_count + (b->head_flip ^ 1));
+            int* const clr = b->head_count + (b->head_flip ^ 1);
+#define MKF_TMA_LAUNCH(W_, O_, P_)                                                                                   \
+    if (tma_cfg == W_ * 100 + O_ * 10 + P_) {                                                                         \
+        if (m->d == 12)                                                                                               \
+            mkf_launch(k_slot_update_heads_tma<12, W_, O_, P_>, tgrid, 32 * (W_ + P_), tma_smem, b->stream, a, clr);  \
+        else                                                                                                          \
+            mkf_launch(k_slot_update_heads_tma<10, W_, O_, P_>, tgrid, 32 * (W_ + P_), tma_smem, b->stream, a, clr);  \
+    }
+            MKF_TMA_CASES(MKF_TMA_LAUNCH)
+#undef MKF_TMA_LAUNCH
         } else if (m->d == 12)
             mkf_launch(k_slot_update_heads_direct<12>, hgrid, hblock, smem, b->stream, a, b->head_count + (b->head_flip ^ 1));
         else
@@ -946,6 +997,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     CK(cudaGetLastError());
     if (pe) cudaEventRecord(pe[4], b->stream);
     b->cur ^= 1;
+    if (use_tma) b->lb_flip ^= 1;
     if (!fused) {
         if (m->d == 12)
             mkf_launch(k_resample_runs<12>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
@@ -1611,3 +1663,41 @@ extern "C" int mkf_synth_fill(mkf_batch* b, uint64_t seed, int64_t track0, uint6
 #include "mkf_extra.cuh"
 #include "mkf_pf2d.cuh"
 #include "mkf_comm.cuh"
+
+// debugging aid of MKF_TIMELINE builds: {start, end} of the four frame kernels for the last 64 frames (reset arms it)
+extern "C" int mkf_debug_timeline(unsigned long long* out512, int reset)
+{
+#ifdef MKF_TIMELINE
+    if (out512 && cudaMemcpyFromSymbol(out512, g_timeline, 64 * 4 * 2 * 8) != cudaSuccess) return MKF_E_CUDA;
+    if (reset) {
+        std::vector<unsigned long long> z(64 * 4 * 2);
+        for (size_t i = 0; i < z.size(); i += 2) {
+            z[i] = ~0ull;
+            z[i + 1] = 0;
+        }
+        if (cudaMemcpyToSymbol(g_timeline, z.data(), z.size() * 8) != cudaSuccess) return MKF_E_CUDA;
+    }
+    return MKF_OK;
+#else
+    (void)out512;
+    (void)reset;
+    return MKF_E_INVALID;
+#endif
+}
+
+// debugging aid of MKF_TMA_PROF builds (not part of include/mkf_b200.h): per-phase cycle counters of k_slot_update_heads_tma
+extern "C" int mkf_debug_tma_prof(unsigned long long* out8, int reset)
+{
+#ifdef MKF_TMA_PROF
+    if (out8 && cudaMemcpyFromSymbol(out8, g_tma_prof, 64) != cudaSuccess) return MKF_E_CUDA;
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(g_tma_prof, z, 64) != cudaSuccess) return MKF_E_CUDA;
+    }
+    return MKF_OK;
+#else
+    (void)out8;
+    (void)reset;
+    return MKF_E_INVALID;
+#endif
+}

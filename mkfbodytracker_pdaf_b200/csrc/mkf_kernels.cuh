@@ -103,6 +103,10 @@ struct SlotArgs {
     // instead of the tile layout; st_in_alias == st_in (see k_slot_update_heads_tma)
     int aos;
     const double2* __restrict__ st_in_alias;
+    const int* __restrict__ lbase_prev; // (aos) list-order records: the parents of track t start at lbase_prev[t] ...
+    const int* __restrict__ lbase_cur;  // ... its heads' records at lbase_cur[t]
+    double2* __restrict__ xs;           // (aos) the heads' means again, tiled by list position (ResampleRunsArgs::xs)
+    int dbg_frame;
 };
 
 // record `sp` of a state buffer in either layout: pair p lives at mkf_rec<D>(st, sp, aos)[mkf_rec_off<D>(p, aos)]
@@ -118,6 +122,23 @@ __device__ __forceinline__ int mkf_rec_off(int p, int aos)
     return aos ? p : SlotLay<D>::po(p);
 }
 #define MKF_MEAS_CAND 2
+
+// MKF_TIMELINE builds: first-CTA-start / last-thread-end of the four kernels of a run-length frame in %globaltimer ns,
+// for the last 64 frames (mkf_debug_timeline); dbg_frame travels in the kernels' argument blocks
+#ifdef MKF_TIMELINE
+__device__ unsigned long long g_timeline[64][4][2];
+#define MKF_TL_START(k, fr)                                                                                            \
+    do {                                                                                                               \
+        if (threadIdx.x == 0) atomicMin(&g_timeline[(fr) & 63][k][0], mkf_globaltimer());                             \
+    } while (0)
+#define MKF_TL_END(k, fr)                                                                                              \
+    do {                                                                                                               \
+        if ((threadIdx.x & 31) == 0) atomicMax(&g_timeline[(fr) & 63][k][1], mkf_globaltimer());                      \
+    } while (0)
+#else
+#define MKF_TL_START(k, fr)
+#define MKF_TL_END(k, fr)
+#endif
 
 // L2 cache-policy descriptors (createpolicy) and 16-byte accesses that carry one
 // The policy operand travels in a uniform register: it has to be a constant the compiler can see (the value
@@ -1082,6 +1103,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
     const int n = *reinterpret_cast<const volatile int*>(a.head_count);
     if (blockIdx.x == 0 && tid == 0) *count_to_clear = 0; // the counter the next frame's k_share_keys appends with
     if (a.ts && tid == 0) atomicMin(a.ts, mkf_globaltimer());
+    MKF_TL_START(1, a.dbg_frame);
     const int step = (int)(gridDim.x * blockDim.x); // (the block size is a launch parameter: 128, or 64 for A/B runs)
     int h = (int)(blockIdx.x * blockDim.x) + tid;
     int4 rec = make_int4(-1, 0, 0, 0);
@@ -1148,6 +1170,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
         a.w_rec[so_rec] = w;
     }
     if (a.ts && (tid & 31) == 0) atomicMax(a.ts + 1, mkf_globaltimer());
+    MKF_TL_END(1, a.dbg_frame);
 }
 
 // Rare tracks redone after k_slot_update: (i) a cv::Cholesky failure was flagged (literal failure semantics

@@ -89,6 +89,12 @@ struct FrameArgs {
     const int32_t* __restrict__ bin_cuts; // null: one measurement per track
     const int32_t* __restrict__ bins;
     int cand_C, hand;
+    // contiguous records in LIST order (mkf_heads_tma.cuh): the record of head i of track t is the one at the head's
+    // position in the work list, lbase[t] + i.  lbase_prev: where the previous frame's heads (this frame's parents) lie,
+    // lbase_cur (out): this frame's.  Null: records at t*N + i in the tile layout.
+    const int* __restrict__ lbase_prev;
+    int* __restrict__ lbase_cur;
+    int dbg_frame;
 };
 
 // component of slot j = number of cuts <= j (cuts sorted, nc <= 63): branch-free binary search
@@ -134,6 +140,7 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
     __shared__ int base_s;
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
+    MKF_TL_START(0, f.dbg_frame);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long t = (long long)blockIdx.x * MKF_FH_WARPS + wid;
     const bool live_t = t < f.T; // (a warp without a track still meets the CTA's barriers below)
@@ -276,6 +283,9 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
     __syncthreads();
     int lb = base_s;
     for (int w = 0; w < wid; w++) lb += nh_s[w];
+    // where the parents' records lie: the track's stretch of the previous list, or its own N slots
+    const int src0 = f.lbase_prev ? (live_t ? f.lbase_prev[t] : 0) : tN;
+    if (f.lbase_cur && live_t && lane == 0) f.lbase_cur[t] = lb;
     if (mode == 1) { // head table and work list in one walk
 #pragma unroll
         for (int c = 0; c < 2; c++) {
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
                 const int h0 = h0_[c];
                 mkf_walk_pieces(cuts, nc, bcuts, nb, a_[c], b_[c], N, [&](int key, int len, int pos, int q) {
                     hm[h0 + q] = make_int4(rec, key, len, pos);
-                    f.hd16[lb + h0 + q] = make_int4(tN + rec, tN + h0 + q, (int)t, key);
+                    f.hd16[lb + h0 + q] = make_int4(src0 + rec, tN + h0 + q, (int)t, key);
                 });
             }
         }
@@ -292,9 +302,10 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
         __syncwarp();
         for (int i = lane; i < nh; i += 32) {
             const int4 m = __ldcg(hm + i);
-            f.hd16[lb + i] = make_int4(tN + m.x, tN + i, (int)t, m.y);
+            f.hd16[lb + i] = make_int4(src0 + m.x, tN + i, (int)t, m.y);
         }
     }
+    MKF_TL_END(0, f.dbg_frame);
 }
 
 __device__ __forceinline__ dd dd_shfl_xor(dd v, int o)
@@ -352,7 +363,12 @@ struct ResampleRunsArgs {
     double* __restrict__ est_xbar;  // T x d
     double* __restrict__ est_pose;  // T x Dpose
     double* __restrict__ est_pose2; // the association step's copy of the pose (or null)
-    int aos;                        // st_new holds contiguous records (mkf_heads_tma.cuh)
+    int aos;                        // st_new holds contiguous records (mkf_heads_tma.cuh) ...
+    const int* __restrict__ lbase;  // ... in list order: head i of track t at lbase[t] + i
+    // (aos) the heads' means x' once more, as [list position / 32][pair][list position % 32] double2: what the estimator
+    // gathers, coalesced (the 96 bytes at the start of 720-byte records are a scattered read: 18 -> 29 us at 4096 x 500)
+    const double2* __restrict__ xs;
+    int dbg_frame;
 };
 
 // One track, by one warp (every lane enters).  coef: the reconstruction coefficients staged in shared memory as
@@ -368,6 +384,7 @@ __device__ __forceinline__ void mkf_resample_runs_track(const ResampleRunsArgs& 
     const int4* hm = a.hmeta + t * N;
     const double* wr = a.w_rec + t * N;
     int2* rt = a.runs + t * N;
+    const long long rbase = a.lbase ? (long long)a.lbase[t] : t * N; // the track's records in st_new
     // estimator of the new set (sum over its runs of children x mean): gathered as soon as a head's children are known
     double xs[D];
     bool xs_done = false;
@@ -481,12 +498,13 @@ __device__ __forceinline__ void mkf_resample_runs_track(const ResampleRunsArgs& 
                 const unsigned msk = __ballot_sync(0xffffffffu, c > 0);
                 if (c > 0) {
                     rt[nr + __popc(msk & ((1u << lane) - 1u))] = make_int2(i, c);
-                    const long long sp = t * N + i; // head i's record, just written by the slot kernel
-                    const double2* __restrict__ src = a.st_new + mkf_rec_base<D>(sp, a.aos);
+                    const long long sp = rbase + i; // head i's record, just written by the slot kernel
+                    const double2* __restrict__ src =
+                        a.xs ? a.xs + (sp >> 5) * (D / 2 * 32) + (sp & 31) : a.st_new + mkf_rec_base<D>(sp, a.aos);
                     const double m = (double)c;
 #pragma unroll
                     for (int p = 0; p < D / 2; p++) {
-                        const double2 q = __ldg(src + mkf_rec_off<D>(p, a.aos));
+                        const double2 q = __ldg(src + (a.xs ? 32 * p : mkf_rec_off<D>(p, a.aos)));
                         xs[2 * p] = fma(m, q.x, xs[2 * p]);
                         xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
                     }
@@ -541,12 +559,13 @@ __device__ __forceinline__ void mkf_resample_runs_track(const ResampleRunsArgs& 
         for (int e = 0; e < D; e++) xs[e] = 0.0;
         for (int r = lane; r < nr; r += 32) {
             const int2 rn = __ldcg(rt + r); // written by lane 0 just above
-            const long long sp = t * N + rn.x;
-            const double2* __restrict__ src = a.st_new + mkf_rec_base<D>(sp, a.aos);
+            const long long sp = rbase + rn.x;
+            const double2* __restrict__ src =
+                a.xs ? a.xs + (sp >> 5) * (D / 2 * 32) + (sp & 31) : a.st_new + mkf_rec_base<D>(sp, a.aos);
             const double m = (double)rn.y;
 #pragma unroll
             for (int p = 0; p < D / 2; p++) {
-                const double2 q = __ldg(src + mkf_rec_off<D>(p, a.aos));
+                const double2 q = __ldg(src + (a.xs ? 32 * p : mkf_rec_off<D>(p, a.aos)));
                 xs[2 * p] = fma(m, q.x, xs[2 * p]);
                 xs[2 * p + 1] = fma(m, q.y, xs[2 * p + 1]);
             }
@@ -584,10 +603,12 @@ __global__ void __launch_bounds__(128, 7) k_resample_runs(const ResampleRunsArgs
         coef[c * R + r] = r < a.Dpose ? a.recon[r * D + c] : a.tinv[(r - a.Dpose) * D + c];
     }
     mkf_pdl_wait();
+    MKF_TL_START(3, a.dbg_frame);
     __syncthreads();
     const long long t = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= a.T) return;
     mkf_resample_runs_track<D>(a, t, threadIdx.x & 31, coef, a.nheads[t]);
+    MKF_TL_END(3, a.dbg_frame);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -803,6 +824,8 @@ __global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const 
     __shared__ uint32_t flags[128];
     mkf_pdl_launch_dependents();
     mkf_pdl_wait();
+    MKF_TL_START(2, a.dbg_frame);
+    MKF_TL_END(2, a.dbg_frame);
     const long long T = a.total / a.N;
     const long long base = (long long)blockIdx.x * 128;
     {
@@ -818,7 +841,9 @@ __global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const 
         const int nh = nheads[t];
         for (int i = threadIdx.x; i < nh; i += 128) {
             const int4 m = hmeta[t * a.N + i];
-            const long long sp = t * a.N + m.x, so = t * a.N + i;
+            const long long so = t * a.N + i;
+            const long long sp = a.lbase_prev ? (long long)a.lbase_prev[t] + m.x : t * a.N + m.x;
+            const long long sd = a.lbase_cur ? (long long)a.lbase_cur[t] + i : so;
             const double2* src = a.st_in + mkf_rec_base<D>(sp, a.aos);
             double v[L::NE];
             for (int p = 0; p < L::NP; p++) {
@@ -832,12 +857,13 @@ __global__ void __launch_bounds__(128, 2) k_runs_repair(const SlotArgs a, const 
             else
                 mkf_load_meas(a, t, 0, zc);
             slot_math<D, true>(v, a.comp_const + (long long)(m.y & 0xff) * L::CS, zc, a.r, a.chol_mode, a.stage, w);
-            double2* dst = a.st_out + mkf_rec_base<D>(so, a.aos);
+            double2* dst = a.st_out + mkf_rec_base<D>(sd, a.aos);
             for (int p = 0; p < L::NP; p++) {
                 double2 qq;
                 qq.x = v[2 * p];
                 qq.y = (2 * p + 1 < L::NE) ? v[2 * p + 1] : 0.0;
                 dst[mkf_rec_off<D>(p, a.aos)] = qq;
+                if (a.xs && p < D / 2) a.xs[(sd >> 5) * (D / 2 * 32) + 32 * p + (sd & 31)] = qq;
             }
             a.w_rec[so] = w;
         }
