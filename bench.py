@@ -431,6 +431,7 @@ def leg_config2(cx, args):
         reps.append(r_ms)
     ms_med = sorted(reps)[len(reps) // 2]
     rec, nslots = batch.shared_records()  # distinct Gaussians the last frame stored (record sharing)
+    heads_kernel = batch.heads_kernel()   # which kernel ran them (k_slot_update_heads_tma<...> unless MKF_HEADS_TMA=0)
     status_bad = int((batch.status() & (mk._lib.ST_POST_DEGENERATE | mk._lib.ST_CHOL_FAIL)).astype(bool).sum())
     rows_ok = bool(torch.equal(gathered[rank * T:(rank + 1) * T, :model.D], pose))
     pose_check = float(gathered[:, :2].mean())
@@ -524,7 +525,8 @@ def leg_config2(cx, args):
     res.__dict__.update(T=T, N=N, K=K, W=W, ms=ms_med, ms_first=ms, ms_reps=reps, ms_e2e=ms_e2e, ms_e2e_sync=ms_e2e_sync,
                         prof=prof, rec=rec, nslots=nslots, launches=launches, clocks=clocks, status_bad=status_bad,
                         rows_ok=rows_ok, pose_check=pose_check, gathered_rows=int(gathered.shape[0]),
-                        every_slot=every_slot, literal=literal, prof_every=PROF_EVERY, model=model)
+                        every_slot=every_slot, literal=literal, prof_every=PROF_EVERY, model=model,
+                        heads_kernel=heads_kernel)
     return res
 
 
@@ -579,6 +581,7 @@ def leg_config3(cx, steps=12, warmup=3):
     p0 = b0.profile_read_stages()
     b0.profile(0)
     rec, nslots = b0.shared_records()
+    hk3 = b0.heads_kernel() or "k_slot_update_heads_direct<12>"
     st = b0.status() | b1.status()
     bad = int(((st & (mk._lib.ST_POST_DEGENERATE | mk._lib.ST_CHOL_FAIL | mk._lib.ST_CAND_DEGENERATE)) != 0).sum())
     b0.close()
@@ -594,9 +597,9 @@ def leg_config3(cx, steps=12, warmup=3):
             "assoc_only_ms": ms_a / steps, "candidate_weights_per_s": T * 2 * Cn / (ms_a / steps) * 1e3,
             "gate_decisions_per_s": T * 2 * Cn / (ms_a / steps) * 1e3,
             "distinct_records_fraction": rec / max(nslots, 1), "stage_ms_left_arm": sm, "status_flagged_persons": bad,
-            "roofline": roofline_of(cx, "k_slot_update_heads_direct<12> (left arm)" if sharing else "k_slot_update<12, 0>",
+            "roofline": roofline_of(cx, hk3 + " (left arm)" if sharing else "k_slot_update<12, 0>",
                                     rec if sharing else nslots, sm["slot_kernel"], sm["samples"],
-                                    traffic_key="k_slot_update_heads_direct" if sharing else "k_slot_update",
+                                    traffic_key=None if sharing else "k_slot_update",
                                     span_ms=sm.get("slot_kernel_device_span")),
             "clocks": cx.clk.defer(t0, t1)}
 
@@ -883,8 +886,10 @@ def main():
         # frame's count, stationary after the first ~20 frames -- else every slot
         units = c2.rec if sharing else c2.nslots
         split = sharing and sm["share_keys"] > 0
-        kname = ("k_slot_update_heads_direct" if split else "k_slot_update_shared") if sharing else "k_slot_update"
-        roof = roofline_of(cx, kname, units, slot_ms, sm["samples"], span_ms=sm.get("slot_kernel_device_span"), extra={
+        kname = ((c2.heads_kernel or "k_slot_update_heads_direct") if split else "k_slot_update_shared") if sharing \
+            else "k_slot_update"
+        roof = roofline_of(cx, kname, units, slot_ms, sm["samples"], traffic_key=kname.split("<")[0],
+                           span_ms=sm.get("slot_kernel_device_span"), extra={
             "kernel_sampling": f"CUDA events on every {c2.prof_every}th step of the timed region",
             "slots_per_launch": int(c2.nslots), "peak_source": cx.peak_src,
             "distinct_records_fraction": c2.rec / max(c2.nslots, 1),

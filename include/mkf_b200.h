@@ -310,6 +310,12 @@ int mkf_batch_profile_read_slot_span(mkf_batch* b, double* ms, int* n_updates);
  * last update stored for how many slots. */
 int mkf_batch_shared_records(mkf_batch* b, int64_t* records, int64_t* slots);
 
+/* Name of the kernel that ran the distinct Gaussians ("heads") of the last run-length frame -- k_slot_update_heads_tma<d,
+ * consumer warps, output stages, producer warps> (contiguous records staged through shared memory by TMA bulk copies;
+ * the default) or k_slot_update_heads_direct<d> (MKF_HEADS_TMA=0, or a model whose constants leave no room for the
+ * stages) -- empty before the first such frame.  For bench.py's roofline label. */
+int mkf_batch_heads_kernel(mkf_batch* b, char* name, int len);
+
 /* number of kernel launches issued through this library since load (bench.py "gpu_launches") */
 uint64_t mkf_launch_count(void);
 

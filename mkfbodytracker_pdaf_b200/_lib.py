@@ -29,7 +29,7 @@ SYMBOLS = [
     "mkf_batch_destroy", "mkf_batch_sync", "mkf_batch_reset", "mkf_batch_update", "mkf_batch_estimate",
     "mkf_batch_associate", "mkf_batch_assoc_results", "mkf_batch_download", "mkf_batch_upload", "mkf_resample",
     "mkf_pf2d_create", "mkf_pf2d_destroy", "mkf_pf2d_set_particles", "mkf_pf2d_get", "mkf_pf2d_update",
-    "mkf_pf2d_sync", "mkf_pf2d_estimate", "mkf_pf2d_set_random", "mkf_pf2d_randomise", "mkf_pf2d_profile", "mkf_pf2d_profile_read", "mkf_synth_fill", "mkf_launch_count", "mkf_batch_join", "mkf_batch_shared_records", "mkf_batch_profile", "mkf_batch_profile_every", "mkf_batch_profile_read", "mkf_batch_profile_read_stages", "mkf_batch_profile_read_slot_span", "mkf_kf_apply", "mkf_batch_sample_prob", "mkf_batch_pose3d", "mkf_batch_skeleton", "mkf_load_camera_matrix", "mkf_batch_propose",
+    "mkf_pf2d_sync", "mkf_pf2d_estimate", "mkf_pf2d_set_random", "mkf_pf2d_randomise", "mkf_pf2d_profile", "mkf_pf2d_profile_read", "mkf_synth_fill", "mkf_launch_count", "mkf_batch_join", "mkf_batch_shared_records", "mkf_batch_heads_kernel", "mkf_batch_profile", "mkf_batch_profile_every", "mkf_batch_profile_read", "mkf_batch_profile_read_stages", "mkf_batch_profile_read_slot_span", "mkf_kf_apply", "mkf_batch_sample_prob", "mkf_batch_pose3d", "mkf_batch_skeleton", "mkf_load_camera_matrix", "mkf_batch_propose",
     "mkf_shard_tracks", "mkf_comm_unique_id", "mkf_comm_create", "mkf_comm_wrap", "mkf_comm_destroy", "mkf_comm_info",
     "mkf_batch_summaries", "mkf_batch_gather_summaries",
 ]
@@ -112,6 +112,7 @@ lib.mkf_batch_skeleton.argtypes = [_vp, _vp, _dp, _dp, _dp, C.c_int]
 lib.mkf_load_camera_matrix.argtypes = [C.c_char_p, _dp]
 lib.mkf_batch_join.argtypes = [_vp]
 lib.mkf_batch_shared_records.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+lib.mkf_batch_heads_kernel.argtypes = [_vp, C.c_char_p, C.c_int]
 lib.mkf_batch_profile.argtypes = [_vp, C.c_int]
 lib.mkf_batch_profile_every.argtypes = [_vp, C.c_int, C.c_int]
 lib.mkf_batch_profile_read_stages.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]

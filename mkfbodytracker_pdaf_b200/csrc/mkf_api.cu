@@ -187,6 +187,7 @@ struct mkf_batch {
     int* nheads = nullptr;
     int* lbase = nullptr; // 2 x T: first list position of every track's heads (contiguous records), ping-pong by lb_flip
     int lb_flip = 0;
+    char heads_kernel[64] = ""; // name of the heads' slot kernel the last run-length frame launched (mkf_batch_heads_kernel)
     double2* xs = nullptr; // the heads' means tiled by list position (allocated with the first contiguous-record frame)
     double* u_keep = nullptr;
     uint64_t* seed_keep = nullptr;
@@ -503,6 +504,16 @@ __global__ void k_count_records(const int32_t* __restrict__ rep, long long total
     if (s < total) first = (s % N == 0) || rep[s] != rep[s - 1]; // rep is non-decreasing within a track
     const unsigned m = __ballot_sync(0xffffffffu, first);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+extern "C" int mkf_batch_heads_kernel(mkf_batch* b, char* name, int len)
+{
+    if (!b || !name || len <= 0) {
+        mkf_set_error("mkf_batch_heads_kernel: null argument");
+        return MKF_E_INVALID;
+    }
+    snprintf(name, (size_t)len, "%s", b->heads_kernel);
+    return MKF_OK;
 }
 
 extern "C" int mkf_batch_shared_records(mkf_batch* b, int64_t* records, int64_t* slots)
@@ -964,6 +975,9 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         if (pe) cudaEventRecord(pe[2], b->stream);
         const unsigned hblock = (unsigned)heads_block();
         const unsigned hgrid = heads_grid(b, sm_count(b->device)) * (128 / hblock);
+        snprintf(b->heads_kernel, sizeof b->heads_kernel,
+                 use_tma ? "k_slot_update_heads_tma<%d, %d, %d, %d>" : "k_slot_update_heads_direct<%d>", m->d,
+                 tma_cfg / 100, tma_cfg / 10 % 10, tma_cfg % 10);
         if (use_tma) {
             const unsigned tgrid = (unsigned)sm_count(b->device);
             int* const clr = b->head_count + (b->head_flip ^ 1);

@@ -187,6 +187,12 @@ class TrackBatch:
         L.check(L.lib.mkf_batch_shared_records(self._h, C.byref(r), C.byref(n)))
         return r.value, n.value
 
+    def heads_kernel(self):
+        """name of the kernel that ran the distinct Gaussians of the last run-length frame ('' before the first one)"""
+        buf = C.create_string_buffer(64)
+        L.check(L.lib.mkf_batch_heads_kernel(self._h, buf, 64))
+        return buf.value.decode()
+
     def join(self):
         """order the batch's stream after all MEM_HOST_ASYNC copies issued so far (no host synchronisation)"""
         L.check(L.lib.mkf_batch_join(self._h))

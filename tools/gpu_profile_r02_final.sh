@@ -5,7 +5,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
     python bench.py --steps 20 --warmup 3 --repeats 1 --no-cpu-baseline > gpurun_out/b_ncu_full.log 2>&1
 echo "launch list rc=$?"
 # headline pipeline, steady state (frames 20+)
-for k in k_frame_heads k_slot_update_heads_direct k_resample_runs; do
+for k in k_frame_heads k_slot_update_heads_tma k_resample_runs; do
   ncu --set full --clock-control none --import-source on -k "regex:^${k}" -s 20 -c 2 -f -o gpurun_out/r02_prof_${k} \
       python bench.py --steps 24 --warmup 3 --repeats 1 --headline-only --no-cpu-baseline > /dev/null 2>&1
   echo "$k rc=$?"
