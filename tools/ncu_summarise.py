@@ -116,7 +116,7 @@ def main(argv):
             return float(val.replace(",", "")) * UNIT_SCALE[unit]
 
         found = 0
-        for base in ("k_slot_update_heads_direct", "k_share_keys", "k_slot_update_shared", "k_slot_update",
+        for base in ("k_slot_update_heads_tma", "k_slot_update_heads_direct", "k_share_keys", "k_slot_update_shared", "k_slot_update",
                      "k_frame_heads", "k_resample_runs"):
             sel = [c for c in cols if c[1].replace("void ", "").strip().split("<")[0].split("(")[0] == base]
             if not sel:
