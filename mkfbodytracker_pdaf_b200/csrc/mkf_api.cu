@@ -16,6 +16,7 @@
 #include "mkf_kernels.cuh"
 #include "mkf_runs.cuh"
 #include "mkf_heads_tma.cuh"
+#include "mkf_frame_small.cuh"
 #include "../../include/mkf_expf.h"
 
 // events per profiled update: start | bounds | share keys | slot kernel | repair | resample
@@ -204,6 +205,8 @@ struct mkf_batch {
     bool slots_valid = true;  // parent / src / rep / w_raw describe it too (false after a run-level frame until
                               // ensure_slots() replays the resample per slot)
     bool dedup_ok = true; // MKF_DEDUP=0 in the environment turns the sharing off (A/B measurements)
+    bool small_fused = false; // short tracks (9 <= N <= 16) in batches of <= 16384: the frame is k_frame_small
+                              // (mkf_frame_small.cuh); MKF_SMALL_FUSED=0 / 1 force the five-launch frame / this one
     const int32_t* gather_index() const { return shared ? src : parent; }
     int32_t* bounds = nullptr;
     uint8_t* ind_tail = nullptr; // T x N: per-slot components behind a wrapped indicator draw (SlotArgs::ind_tail)
@@ -220,6 +223,8 @@ struct mkf_batch {
     // model constants on this device
     double *d_comp = nullptr, *d_init = nullptr, *d_cw_hi = nullptr, *d_cw_lo = nullptr, *d_wprior = nullptr,
            *d_recon = nullptr, *d_pmean = nullptr, *d_tm = nullptr, *d_tinv = nullptr;
+    double* d_small_const = nullptr; // k_frame_small: [comp_const | reconstruction coefficients [c][r]] (SmallTailArgs)
+    unsigned small_const_bytes = 0;
     // staging
     DevBuf in_meas, in_u0, in_u1, in_seed, out_a, out_b, in_x, in_p;
     AsyncIo aio;
@@ -326,7 +331,7 @@ extern "C" void mkf_batch_destroy(mkf_batch* b)
     for (int i = 0; i < 2; i++)
         if (b->st[i]) cudaFree(b->st[i]);
     void* ptrs[] = {b->parent, b->rep, b->src, b->runs, b->nruns, b->hmeta, b->nheads, b->lbase, b->xs, b->u_keep, b->seed_keep, b->est[0], b->est[1], b->hd16, b->head_count, b->w_rec, b->bounds, b->ind_tail, b->w_raw, b->wsum,   b->status, b->unsorted, b->chain_last, b->alias_list, b->alias_cnt, b->prof_ts, b->d_comp, b->d_init,
-                    b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv};
+                    b->d_cw_hi, b->d_cw_lo, b->d_wprior, b->d_recon, b->d_pmean, b->d_tm,   b->d_tinv, b->d_small_const};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     DevBuf* bufs[] = {&b->in_meas, &b->in_u0, &b->in_u1, &b->in_seed, &b->out_a,   &b->out_b,  &b->in_x,   &b->in_p,
@@ -408,6 +413,28 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
         const char* e2 = getenv("MKF_SHARE_SPLIT");
         b->share_split = !(e2 && e2[0] == '0');
     }
+    {
+        // Worth it while the frame is launch-bound: at 4096 x 15 the five-launch frame takes 49.5 us, this one 35.2.  A
+        // warp carries its tracks' indicator draw, resample and estimate around the slot arithmetic -- 2 390 instructions
+        // where k_slot_update executes 1 580, at two warps per scheduler -- so past ~30 k tracks, where the slot kernel
+        // alone runs at the HBM roofline, the separate kernels win (1 M x 15: 4.51 ms against 4.99).
+        // MKF_SMALL_FUSED=0 / =1 force either (A/B runs and tests).
+        const char* e = getenv("MKF_SMALL_FUSED");
+        const bool forced_on = e && e[0] == '1';
+        b->small_fused = !(e && e[0] == '0') && N >= 9 && N <= 16 && m->K <= 32 &&
+                         m->prm.alias_mode == MKF_ALIAS_INDEPENDENT && (forced_on || T <= 16384);
+        if (b->small_fused) {
+            if ((rc = dmalloc((void**)&b->est[0], (size_t)T * (m->d + m->D) * sizeof(double))) ||
+                (rc = dmalloc((void**)&b->est[1], (size_t)T * (m->d + m->D) * sizeof(double))))
+                return fail(rc);
+            if (cudaEventCreateWithFlags(&b->est_ready, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b->est_done[0], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b->est_done[1], cudaEventDisableTiming) != cudaSuccess) {
+                mkf_set_error("cudaEventCreate failed");
+                return fail(MKF_E_CUDA);
+            }
+        }
+    }
     if (b->dedup_ok && ((rc = dmalloc((void**)&b->rep, (size_t)b->total * sizeof(int32_t))) ||
                         (rc = dmalloc((void**)&b->src, (size_t)b->total * sizeof(int32_t)))))
         return fail(rc);
@@ -478,6 +505,18 @@ extern "C" int mkf_batch_create(mkf_batch** out, const mkf_model* m, int64_t T, 
         (rc = upload_const(m->pmean, &b->d_pmean)) || (rc = upload_const(m->Tm, &b->d_tm)) ||
         (rc = upload_const(m->Tinv, &b->d_tinv)))
         return fail(rc);
+    if (b->small_fused) {
+        const int R = m->D + m->d;
+        std::vector<double> sc(m->comp_const);
+        sc.resize(sc.size() + (size_t)R * m->d + 1, 0.0);
+        double* coef = sc.data() + m->comp_const.size();
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < m->d; c++)
+                coef[(size_t)c * R + r] = r < m->D ? m->recon[(size_t)r * m->d + c] : m->Tinv[(size_t)(r - m->D) * m->d + c];
+        sc.resize((m->comp_const.size() + (size_t)R * m->d + 1) / 2 * 2); // (bulk copies move multiples of 16 bytes)
+        b->small_const_bytes = (unsigned)(sc.size() * sizeof(double));
+        if ((rc = upload_const(sc, &b->d_small_const))) return fail(rc);
+    }
     *out = b;
     return MKF_OK;
 }
@@ -1028,6 +1067,82 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     return MKF_OK;
 }
 
+// the frame of a batch of short tracks: k_frame_small (indicator draw, slot update, resample, estimate) + the repair
+// kernel for flagged tracks (mkf_frame_small.cuh)
+static int update_device_small(mkf_batch* b, const double* d_meas, int meas_layout, const double* d_uind,
+                               const double* d_upost, const uint64_t* d_seeds, int seed_stride, int seed_off,
+                               cudaEvent_t* pe)
+{
+    const mkf_model* m = b->m;
+    if (pe) { // (no indicator / keys kernel: two empty intervals)
+        cudaEventRecord(pe[0], b->stream);
+        cudaEventRecord(pe[1], b->stream);
+        cudaEventRecord(pe[2], b->stream);
+    }
+    SlotArgs a{};
+    fill_slot_args(b, a, d_meas, meas_layout);
+    if (pe && b->prof_ts) a.ts = b->prof_ts + 2 * (size_t)b->prof_n;
+    SmallTailArgs s{};
+    s.u_ind = d_uind;
+    s.cw_hi = b->d_cw_hi;
+    s.cw_lo = b->d_cw_lo;
+    s.wprior = b->d_wprior;
+    s.wmax = m->prior_wmax;
+    s.bounds_out = b->bounds;
+    s.ind_tail_out = b->ind_tail;
+    s.clear_status = b->clear_status_next ? 1 : 0;
+    b->clear_status_next = false;
+    s.u_post = d_upost;
+    s.seeds = d_seeds;
+    s.seed_stride = seed_stride;
+    s.seed_off = seed_off;
+    s.parent_out = b->parent;
+    s.wsum = b->wsum;
+    s.unsorted_out = b->unsorted;
+    s.Dpose = m->D;
+    s.recon = b->d_recon;
+    s.pmean = b->d_pmean;
+    s.tinv = b->d_tinv;
+    // the estimate of the new set goes to the other slot (a host copy of the previous one may be in flight)
+    b->est_slot ^= 1;
+    if (b->est_used[b->est_slot]) CK(cudaStreamWaitEvent(b->stream, b->est_done[b->est_slot], 0));
+    s.est_xbar = b->est[b->est_slot];
+    s.est_pose = b->est[b->est_slot] + (size_t)b->T * m->d;
+    s.est_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
+    s.small_const = b->d_small_const;
+    s.small_const_bytes = b->small_const_bytes;
+    s.step = 1.0 / (double)b->N;
+    const size_t smem = b->small_const_bytes;
+    static std::atomic<uint64_t> seen{0};
+    if (smem > 48 * 1024 && first_on_this_device(seen)) {
+        CK(cudaFuncSetAttribute(k_frame_small<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(k_frame_small<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    }
+    const unsigned g = grid_for(b->T, 8); // 4 warps x 2 tracks
+    if (m->d == 12)
+        mkf_launch(k_frame_small<12>, g, 128, smem, b->stream, a, s);
+    else
+        mkf_launch(k_frame_small<10>, g, 128, smem, b->stream, a, s);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if (pe) cudaEventRecord(pe[3], b->stream);
+    if (m->d == 12)
+        mkf_launch(k_slot_update_repair<12, true>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last, s);
+    else
+        mkf_launch(k_slot_update_repair<10, true>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last, s);
+    MKF_LAUNCHED();
+    CK(cudaGetLastError());
+    if (pe) {
+        cudaEventRecord(pe[4], b->stream);
+        cudaEventRecord(pe[5], b->stream);
+    }
+    b->cur ^= 1;
+    b->shared = false;
+    b->est_valid = true;
+    if (b->pose_cache_on) b->pose_valid = true;
+    return MKF_OK;
+}
+
 // the frame pipeline on device pointers
 static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, const double* d_uind,
                          const double* d_upost, int u_stride, const uint64_t* d_seeds, int seed_stride, int seed_off)
@@ -1069,6 +1184,11 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
         b->run_mode = false;
     }
     b->est_valid = false;
+    if (b->small_fused && b->stage == 3 && !dedup && (meas_layout != MKF_MEAS_CAND || (b->cm_cand && b->cm_bins && b->cm_roi))) {
+        rc = update_device_small(b, d_meas, meas_layout, d_uind, d_upost, d_seeds, seed_stride, seed_off, pe);
+        if (prof && rc == MKF_OK) b->prof_n++;
+        return rc;
+    }
     if (prof) cudaEventRecord(pe[0], b->stream);
     if ((rc = launch_bounds_kernel(b, d_uind, b->clear_status_next ? 1 : 0))) return rc;
     b->clear_status_next = false;
@@ -1167,9 +1287,9 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
     if (prof) cudaEventRecord(pe[3], b->stream);
     // rare tracks (cv::Cholesky failure flagged, or unsorted parents in the literal alias mode) are redone
     if (m->d == 12)
-        mkf_launch(k_slot_update_repair<12>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last);
+        mkf_launch(k_slot_update_repair<12, false>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last, SmallTailArgs{});
     else
-        mkf_launch(k_slot_update_repair<10>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last);
+        mkf_launch(k_slot_update_repair<10, false>, grid_for(b->T, 128), 128, 0, b->stream, a, b->chain_last, SmallTailArgs{});
     MKF_LAUNCHED();
     CK(cudaGetLastError());
     if (prof) cudaEventRecord(pe[4], b->stream);
@@ -1356,7 +1476,7 @@ static bool launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose) // f
     const double2* st = b->st[b->cur];
     double* d_pose2 = b->pose_cache_on ? (double*)b->pose_cache.p : nullptr;
     const size_t coef_bytes = (size_t)(m->D + DD) * DD * sizeof(double);
-    if (b->run_mode && b->est_valid) { // k_resample_runs left the estimate of this set in the batch: copies only
+    if (b->est_valid) { // k_resample_runs / k_frame_small left the estimate of this set in the batch: copies only
         const double* ex = b->est[b->est_slot];
         const double* ep = ex + (size_t)b->T * DD;
         if (d_xbar) cudaMemcpyAsync(d_xbar, ex, (size_t)b->T * DD * 8, cudaMemcpyDeviceToDevice, b->stream);
@@ -1397,7 +1517,7 @@ static bool launch_estimate_d(mkf_batch* b, double* d_xbar, double* d_pose) // f
 }
 static int launch_estimate(mkf_batch* b, double* d_xbar, double* d_pose)
 {
-    if (b->aos && !(b->run_mode && b->est_valid)) { // the estimate kernels read tiles
+    if (b->aos && !b->est_valid) { // the estimate kernels read tiles
         int rc0 = relayout(b, false);
         if (rc0) return rc0;
     }
@@ -1418,8 +1538,8 @@ extern "C" int mkf_batch_estimate(mkf_batch* b, double* xbar, double* pose, int 
     const mkf_model* m = b->m;
     OutPtr<double> ox, op;
     int rc;
-    if (b->run_mode && b->est_valid) {
-        // run-length pipeline: k_resample_runs already left xbar / pose of the current set in the batch -- copies only
+    if (b->est_valid) {
+        // run-length pipeline / short tracks: the frame already left xbar / pose of the current set in the batch -- copies only
         const int sl = b->est_slot;
         const double* ex = b->est[sl];
         const double* ep = ex + (size_t)b->T * m->d;

@@ -216,7 +216,7 @@ extern "C" int mkf_batch_summaries(mkf_batch* b, int64_t rows, double* out, int 
     const int D = b->m->D, W = D + 2;
     int rc;
     const double* d_pose;
-    if (b->run_mode && b->est_valid) { // the pose k_resample_runs left in the batch
+    if (b->est_valid) { // the pose k_resample_runs / k_frame_small left in the batch
         d_pose = b->est[b->est_slot] + (size_t)b->T * b->m->d;
     } else {
         if ((rc = b->out_b.ensure((size_t)b->T * D * 8))) return rc;

@@ -90,9 +90,9 @@ extern "C" int mkf_kf_apply(const mkf_model* m, int n, const int32_t* comp, int 
         k_slot_update<10, false><<<grid_for(b->total, 128), 128, smem, b->stream>>>(a);
     MKF_LAUNCHED();
     if (m->d == 12)
-        k_slot_update_repair<12><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, nullptr);
+        k_slot_update_repair<12, false><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, nullptr, SmallTailArgs{});
     else
-        k_slot_update_repair<10><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, nullptr);
+        k_slot_update_repair<10, false><<<grid_for(b->T, 128), 128, 0, b->stream>>>(a, nullptr, SmallTailArgs{});
     MKF_LAUNCHED();
     if (cudaGetLastError() != cudaSuccess) {
         mkf_set_error("mkf_kf_apply: kernel launch failed");

@@ -1173,14 +1173,103 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_heads_direct(const SlotA
     MKF_TL_END(1, a.dbg_frame);
 }
 
+// what the tail of a short track's frame needs besides SlotArgs
+struct SmallTailArgs {
+    // indicator draw
+    const double* __restrict__ u_ind;
+    const double* __restrict__ cw_hi;
+    const double* __restrict__ cw_lo;
+    const double* __restrict__ wprior;
+    double wmax;
+    int32_t* __restrict__ bounds_out;
+    uint8_t* __restrict__ ind_tail_out;
+    int clear_status;
+    // posterior resample
+    const double* __restrict__ u_post;
+    const uint64_t* __restrict__ seeds;
+    int seed_stride, seed_off;
+    int32_t* __restrict__ parent_out; // == SlotArgs::parent (a track's row is read at the start and written at the
+                                      // end by the same half warp)
+    double* __restrict__ wsum;
+    uint32_t* __restrict__ unsorted_out;
+    // estimator
+    int Dpose;
+    const double* __restrict__ recon;
+    const double* __restrict__ pmean;
+    const double* __restrict__ tinv;
+    double* __restrict__ est_xbar;  // T x d
+    double* __restrict__ est_pose;  // T x Dpose
+    double* __restrict__ est_pose2; // the batch's pose cache for the next association step, or null
+    // k_frame_small only: [per-component constants K x CS | reconstruction coefficients [c][r], r < Dpose + d (rows of
+    // recon, then rows of tinv)] as one block for one TMA bulk copy, its size in bytes, and fl(1 / N)
+    const double* __restrict__ small_const;
+    unsigned small_const_bytes;
+    double step;
+};
+
+// The tail of ONE track by ONE thread, from global memory (k_slot_update_repair, after it has redone a flagged track):
+// same operations in the same order as the half-warp version below, except the estimate's summation order.
+template <int D>
+__device__ __noinline__ void mkf_small_tail_serial(const SlotArgs& a, const SmallTailArgs& s, const long long t)
+{
+    using L = SlotLay<D>;
+    const int N = a.N;
+    const double* __restrict__ w = a.w_raw + t * N;
+    double wsum = 0.0;
+    for (int i = 0; i < N; i++) wsum = __dadd_rn(wsum, w[i]);
+    s.wsum[t] = wsum;
+    double mw = 0.0;
+    for (int i = 0; i < N; i++) {
+        const double x = __ddiv_rn(w[i], wsum);
+        if (x > mw) mw = x;
+    }
+    int32_t* __restrict__ out = s.parent_out + t * N;
+    if (!(mw > 0.0)) {
+        atomicOr(a.status + t, MKF_ST_POST_DEGENERATE);
+        mkf_cvrng rng(s.seeds ? s.seeds[t * s.seed_stride + s.seed_off] : 1ull);
+        (void)rng.uniform_int(0, N);
+        for (int i = 0; i < N; i++) out[i] = rng.uniform_int(0, N);
+    } else {
+        mkf_resample_sequential([&](int i) { return __ddiv_rn(w[i], wsum); }, N, N, s.u_post[t],
+                                [&](int i, int idx) { out[i] = idx; });
+    }
+    if (s.unsorted_out) s.unsorted_out[t] = (mw > 0.0) ? 0u : 1u;
+    double acc[D];
+    for (int e = 0; e < D; e++) acc[e] = 0.0;
+    for (int i = 0; i < N; i++) {
+        const long long sp = t * N + out[i];
+        const double2* src = a.st_out + (sp >> 5) * (long long)L::TILE2 + (sp & 31) * L::H;
+        for (int p = 0; p < D / 2; p++) {
+            const double2 q = src[L::po(p)];
+            acc[2 * p] += q.x;
+            acc[2 * p + 1] += q.y;
+        }
+    }
+    const double inv_n = 1.0 / (double)N;
+    for (int e = 0; e < D; e++) acc[e] *= inv_n;
+    for (int r = 0; r < s.Dpose; r++) {
+        double sacc = 0.0;
+        for (int c = 0; c < D; c++) sacc = fma(s.recon[r * D + c], acc[c], sacc);
+        s.est_pose[t * s.Dpose + r] = sacc + s.pmean[r];
+        if (s.est_pose2) s.est_pose2[t * s.Dpose + r] = sacc + s.pmean[r];
+    }
+    for (int r = 0; r < D; r++) {
+        double sacc = 0.0;
+        for (int c = 0; c < D; c++) sacc = fma(s.tinv[r * D + c], acc[c], sacc);
+        s.est_xbar[t * D + r] = sacc;
+    }
+}
+
 // Rare tracks redone after k_slot_update: (i) a cv::Cholesky failure was flagged (literal failure semantics
 // through slot_math<SLOW>), (ii) literal alias mode with UNSORTED parents (after the degenerate random-index
 // fallback of src/pf2DRao.cpp:184-192 the slots sharing a parent are not adjacent).  One CTA scans 128
 // tracks' flags.  Independent mode: the CTA's threads stride over the track's slots.  Literal alias mode:
 // one thread walks the slots in order, each starting from the latest snapshot taken for its parent
 // (last: T x N scratch, -1 = none yet).  st_in is intact (ping-pong), so everything is recomputed from it.
-template <int D>
-__global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a, int32_t* __restrict__ last)
+// TAIL (after k_frame_small, mkf_frame_small.cuh): the redone track's resample and estimate follow, by one thread.
+template <int D, bool TAIL>
+__global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a, int32_t* __restrict__ last,
+                                                               const SmallTailArgs tl)
 {
     using L = SlotLay<D>;
     __shared__ uint32_t flags[128];
@@ -1236,6 +1325,7 @@ __global__ void __launch_bounds__(128, 2) k_slot_update_repair(const SlotArgs a,
             }
         }
         __syncthreads();
+        if (TAIL && threadIdx.x == 0) mkf_small_tail_serial<D>(a, tl, t);
     }
 }
 
@@ -1256,12 +1346,12 @@ __device__ __forceinline__ bool mkf_indicator_bounds_group(const long long t, co
                                                            const double* __restrict__ wprior, double wmax,
                                                            int32_t* __restrict__ bounds, uint32_t* __restrict__ status,
                                                            int clear_status, uint8_t* __restrict__ ind_tail, int& e_lo,
-                                                           int& e_hi)
+                                                           int& e_hi, const double step_in = 0.0)
 {
     // first kernel of a frame update: the track's status word starts from zero (no memset node in front of the
     // chain); the only writer of status in this kernel is this same thread, below
     if (clear_status && live && k == 0) status[t] = 0u;
-    const double step = __ddiv_rn(1.0, (double)N);
+    const double step = step_in != 0.0 ? step_in : __ddiv_rn(1.0, (double)N); // (step_in: the same quotient, from the host)
     const double beta0 = live ? __dmul_rn(u[t], step) : 0.0;
     const double tol = mkf_resample_tol(N, K, wmax, step);
     bool amb = false;

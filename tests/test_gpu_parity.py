@@ -378,11 +378,11 @@ def test_literal_alias_mode_matches_oracle_and_reference_sources(left_arm, N, dy
     assert differs_from_independent, "literal aliasing must change the result from frame 2 on"
 
 
-@pytest.mark.parametrize("alias", [0, 1])
-def test_degenerate_frame_then_recovery(left_arm, alias):
+@pytest.mark.parametrize("alias,N", [(0, 120), (1, 120), (0, 15)])  # N = 15: the cv::RNG branch inside k_frame_small
+def test_degenerate_frame_then_recovery(left_arm, alias, N):
     """all weights underflow (measurement far away) -> cv::RNG random-index fallback (unsorted parents, seeded);
     the following frames must still match the oracle in both alias modes"""
-    T, N = 4, 120
+    T = 4
     a = left_arm.arrays
     p = mk.default_params()
     p.alias_mode = alias
@@ -419,7 +419,8 @@ def test_degenerate_frame_then_recovery(left_arm, alias):
             assert rel_err(d["x"][t], xo) <= RTOL and rel_err(d["P"][t], Po) <= RTOL
 
 
-@pytest.mark.parametrize("N", [64, 200])  # 200: the two-launch record-sharing path (k_slot_update_heads_direct)
+@pytest.mark.parametrize("N", [15, 64, 200])  # 15: k_frame_small + the repair kernel's serial tail; 200: the two-launch
+                                              # record-sharing path (k_slot_update_heads_direct)
 def test_cholesky_failure_branch_matches_oracle(left_arm, rng, N):
     """S not positive definite: cv::Cholesky fails, chol() returns the partially factored clone and the
     reference carries on with LU inverses (src/pf2DRao.cpp:37,52; src/KF_model.cpp:21)"""
@@ -731,3 +732,40 @@ def test_record_sharing_variants_agree(left_arm, T, N, monkeypatch):
     for d in ds[1:]:
         for key in keys:
             assert np.array_equal(ds[0][key], d[key]), ("after the per-slot frame", key)
+
+
+@pytest.mark.parametrize("T,N,arm", [(301, 15, "right"), (9, 16, "left"), (70, 9, "left"), (1, 12, "left"), (1027, 15, "left")])
+def test_short_track_frame_variants_agree(left_arm, right_arm, T, N, arm, monkeypatch):
+    """Short tracks (9 <= N <= 16; BASELINE config 5 / bank mode): the whole frame in ONE launch (k_frame_small: a half
+    warp per track draws the indicators, updates the slots, resamples and estimates, mkf_frame_small.cuh) against the
+    five-launch per-slot frame (MKF_SMALL_FUSED=0: k_indicator_bounds, k_slot_update, k_slot_update_repair,
+    k_resample_small, k_estimate_small).  Same arithmetic in the same order, so EVERY download and the estimates agree
+    bit for bit over free-running frames with shared and per-slot measurement columns, on track counts that leave
+    half-empty warps and CTAs."""
+    model = (right_arm if arm == "right" else left_arm).mk
+    seed = 0x5EED0015
+    tracks = list(range(T))
+    u0 = synth_u_init(seed, tracks)
+
+    def make(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        b = mk.TrackBatch(model, T, N)  # the variant is fixed at creation
+        b.reset(u0)
+        return b
+
+    ref, fus = make({"MKF_SMALL_FUSED": "0"}), make({"MKF_SMALL_FUSED": "1"})
+    keys = ("parents", "indicators", "x", "P", "w_raw", "w_norm", "wsum", "status")
+    for fr in range(10):
+        m, ui, up = synth_frame(seed, tracks, fr, N if fr % 3 == 2 else None)
+        ref.update(m, ui, up)
+        fus.update(m, ui, up)
+        if fr % 2 == 0 or fr == 9:
+            er, ef = ref.estimate(), fus.estimate()
+            assert np.array_equal(er[0], ef[0]) and np.array_equal(er[1], ef[1]), fr
+        if fr in (0, 3, 4, 9):
+            dr, df = ref.download(), fus.download()
+            for key in keys:
+                assert np.array_equal(dr[key], df[key]), (fr, key)
+    # the output back-end reads the pose the frame left in the batch
+    assert np.array_equal(ref.pose3d(), fus.pose3d())
