@@ -10,6 +10,7 @@ reconstruction; the timed region ends with the gather of per-track summaries (nc
 Top-level legs of the same JSON line, each with ms_per_step, its own roofline {kernel, kernel_ms, frac} and clocks:
   config2_every_slot     config 2 with record sharing off (every slot computed: the roofline-facing figure)
   config2_literal_alias  config 2 in the reference binary's shallow-copy alias mode (quirk B3)
+  config2_bank           config 2's secondary shape: 15 slots per track (one per component), the frame in one launch
   config3                16 384 persons x 500 slots x 17 candidates per hand: association + both arm updates
   config4                256 tracks x 65 536 slots, per-slot measurement columns (+ config4_pf2d: the legacy plain
                          filter at the same size -> particle likelihoods/s)
@@ -471,11 +472,12 @@ def leg_config2(cx, args):
     batch.close()
 
     # ---------------- variants of the same frames on rank 0 (no collectives) ----------------
-    def variant(model_v, env, K2, label_kernel):
+    def variant(model_v, env, K2, label_kernel, slots=None):
+        N2 = slots or N
         for k, v in env.items():
             os.environ[k] = v  # read when a batch is created
         try:
-            b2 = mk.TrackBatch(model_v, T, N, device=cx.local, stream=cx.stream.cuda_stream)
+            b2 = mk.TrackBatch(model_v, T, N2, device=cx.local, stream=cx.stream.cuda_stream)
         finally:
             for k in env:
                 del os.environ[k]
@@ -503,12 +505,12 @@ def leg_config2(cx, args):
         ms2 = ea.elapsed_time(eb) / K2
         sm = stage_means(p2)
         return {"steps": K2, "ms_per_step": ms2, "value": T * 1e3 / ms2, "unit": UNIT,
-                "slot_updates_per_s": T * N * 1e3 / ms2, "stage_ms": sm, "status_flagged_tracks": bad,
-                "roofline": roofline_of(cx, label_kernel, T * N, sm["slot_kernel"], sm["samples"],
+                "slot_updates_per_s": T * N2 * 1e3 / ms2, "stage_ms": sm, "status_flagged_tracks": bad,
+                "roofline": roofline_of(cx, label_kernel, T * N2, sm["slot_kernel"], sm["samples"],
                                         span_ms=sm.get("slot_kernel_device_span")),
                 "clocks": cx.clk.defer(ta, tb)}
 
-    every_slot = literal = None
+    every_slot = literal = bank = None
     if rank == 0 and not args.headline_only:
         if os.environ.get("MKF_DEDUP", "1") != "0":
             every_slot = variant(model, {"MKF_DEDUP": "0"}, min(K, 48), "k_slot_update<12, 0>")
@@ -521,8 +523,14 @@ def leg_config2(cx, args):
                            "place (quirk B3, src/pf2DRao.cpp:153-156) -- what the reference binary and the CPU arm's "
                            "oracle/_ref compute; every slot is computed")
 
+        # config 2's secondary shape: the plain GMM-KF bank, one slot per component
+        bank = variant(model, {}, min(K, 100), "k_frame_small<12>" if T <= 16384 else "k_slot_update<12, 0>", slots=15)
+        bank["workload"] = f"config 2 (bank): {T} tracks x 15 slots, shared column"
+        bank["note"] = ("short tracks: the whole frame (indicator draw, slot update, resample, estimate) is ONE launch, half "
+                        "a warp per track; launch / latency bound at this size -- the roofline entry is the frame "
+                        "kernel's interval against 1500 B per slot-update")
     res = Ctx()
-    res.__dict__.update(T=T, N=N, K=K, W=W, ms=ms_med, ms_first=ms, ms_reps=reps, ms_e2e=ms_e2e, ms_e2e_sync=ms_e2e_sync,
+    res.__dict__.update(T=T, N=N, K=K, W=W, ms=ms_med, bank=bank, ms_first=ms, ms_reps=reps, ms_e2e=ms_e2e, ms_e2e_sync=ms_e2e_sync,
                         prof=prof, rec=rec, nslots=nslots, launches=launches, clocks=clocks, status_bad=status_bad,
                         rows_ok=rows_ok, pose_check=pose_check, gathered_rows=int(gathered.shape[0]),
                         every_slot=every_slot, literal=literal, prof_every=PROF_EVERY, model=model,
@@ -934,7 +942,7 @@ def main():
             "gathered_rows_match_local": c2.rows_ok,
             "nccl": {"version": nccl_version, "nranks": world, "debug": os.environ.get("NCCL_DEBUG"),
                      "comm": "mkf_comm_create (ncclCommInitRank) + torch.distributed process group"},
-            "config2_every_slot": c2.every_slot, "config2_literal_alias": c2.literal,
+            "config2_every_slot": c2.every_slot, "config2_literal_alias": c2.literal, "config2_bank": c2.bank,
             "config3": c3, "config4": c4, "config4_pf2d": pf, "config5": c5,
             "particle_likelihoods_per_s": pf["particle_likelihoods_per_s"] if pf else None,
         }
