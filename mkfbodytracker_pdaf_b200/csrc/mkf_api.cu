@@ -23,6 +23,7 @@
 #define MKF_PROF_EV 6
 static std::atomic<uint64_t> g_launches{0};
 extern "C" uint64_t mkf_launch_count(void) { return g_launches.load(); }
+
 #define MKF_LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 // Launch with the programmatic-stream-serialization attribute (PDL, see mkf_device.cuh): kernels of the per-frame
@@ -46,6 +47,9 @@ static int sm_count(int device)
     }
     return v;
 }
+// 0: the next mkf_launch calls of this thread go without the programmatic-launch attribute (update_device_runs, per kernel)
+static thread_local int g_pdl_override = -1;
+
 template <class... P, class... A>
 static void mkf_launch(void (*kern)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, A&&... args)
 {
@@ -58,7 +62,7 @@ static void mkf_launch(void (*kern)(P...), unsigned grid, unsigned block, size_t
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && g_pdl_override != 0) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...); // errors surface through cudaGetLastError()
 }
 
@@ -859,6 +863,15 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
                               cudaEvent_t* pe)
 {
     const mkf_model* m = b->m;
+    // which of the frame's four launches carry the programmatic-launch attribute (bit 0: k_frame_heads, 1: the slot
+    // kernel, 2: k_runs_repair, 3: k_resample_runs); MKF_PDL_MASK overrides for A/B runs.  The slot kernel goes WITHOUT:
+    // released early it starts 1.0 us after k_frame_heads instead of 3.5, but then lasts 62 us instead of 54 (device
+    // timeline of the pipelined loop at 4096 x 500, tools/tma_timeline.py: period 100.7 us with all four, 94.9 with this
+    // mask; profiles/r02_pdl_masks.txt)
+    static const int pdl_mask = [] {
+        const char* e = getenv("MKF_PDL_MASK");
+        return e ? atoi(e) : 13;
+    }();
     // MKF_FUSED=1: the single-launch frame kernel k_frame_fused instead of the three grid-wide kernels (k_frame_heads,
     // k_slot_update_heads_direct, k_resample_runs).  Measured at 4096 x 500: 0.147 ms per frame against 0.104 -- a warp
     // that owns its tracks walks their bookkeeping latency chains one after the other with only 8 warps per SM to hide
@@ -1008,12 +1021,21 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
             cudaEventRecord(pe[3], b->stream);
         }
     } else {
+        g_pdl_override = (pdl_mask & 1) ? -1 : 0;
         mkf_launch(k_frame_heads, grid_for(b->T, MKF_FH_WARPS), 32 * MKF_FH_WARPS, 0, b->stream, f);
+        g_pdl_override = (pdl_mask & 2) ? -1 : 0; // (the slot kernel)
         MKF_LAUNCHED();
         CK(cudaGetLastError());
         if (pe) cudaEventRecord(pe[2], b->stream);
         const unsigned hblock = (unsigned)heads_block();
         const unsigned hgrid = heads_grid(b, sm_count(b->device)) * (128 / hblock);
+        {
+            static const int late = [] {
+                const char* e = getenv("MKF_PDL_SLOT_LATE");
+                return (e && e[0] == '0') ? 0 : 1;
+            }();
+            a.pdl_late = late;
+        }
         snprintf(b->heads_kernel, sizeof b->heads_kernel,
                  use_tma ? "k_slot_update_heads_tma<%d, %d, %d, %d>" : "k_slot_update_heads_direct<%d>", m->d,
                  tma_cfg / 100, tma_cfg / 10 % 10, tma_cfg % 10);
@@ -1038,6 +1060,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         CK(cudaGetLastError());
         if (pe) cudaEventRecord(pe[3], b->stream);
     }
+    g_pdl_override = (pdl_mask & 4) ? -1 : 0;
     // flagged tracks (cv::Cholesky failure) are redone with the literal failure semantics; after the fused kernel, which
     // leaves them unresampled, their resample happens here too
     if (m->d == 12)
@@ -1051,6 +1074,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
     if (pe) cudaEventRecord(pe[4], b->stream);
     b->cur ^= 1;
     if (use_tma) b->lb_flip ^= 1;
+    g_pdl_override = (pdl_mask & 8) ? -1 : 0;
     if (!fused) {
         if (m->d == 12)
             mkf_launch(k_resample_runs<12>, grid_for(b->T, 4), 128, coef_bytes, b->stream, ra);
@@ -1059,6 +1083,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         MKF_LAUNCHED();
         CK(cudaGetLastError());
     }
+    g_pdl_override = -1;
     if (pe) cudaEventRecord(pe[5], b->stream);
     b->shared = true;
     b->slots_valid = false;

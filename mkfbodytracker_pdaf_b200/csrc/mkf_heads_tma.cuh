@@ -208,7 +208,11 @@ __global__ void __launch_bounds__(32 * (W + P), 1) k_slot_update_heads_tma(const
         mkf_mbar_expect_tx(&cbar, cbytes);
         mkf_tma_load_1d(cst, a.comp_const, cbytes, &cbar); // model constants: never written by the frame chain
     }
-    mkf_pdl_launch_dependents();
+    // Programmatic dependent launch: the dependents (k_runs_repair, and through it k_resample_runs) are released when a
+    // warp of every CTA has finished its steps, not at the start.  Released at the start, their CTAs take their places
+    // on the SMs during this kernel and it runs 63 us instead of 53 (device timeline of the pipelined loop, 4096 x 500:
+    // tools/tma_timeline.py); released late, the hand-over costs ~2 us more and the frame is shorter.
+    if (!a.pdl_late) mkf_pdl_launch_dependents();
     mkf_pdl_wait();
 
     const int n = *reinterpret_cast<const volatile int*>(a.head_count);
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(32 * (W + P), 1) k_slot_update_heads_tma(const
                 break;
             }
         }
+        if (a.pdl_late) mkf_pdl_launch_dependents();
         MKF_TL_END(1, a.dbg_frame);
         return;
     }
@@ -389,6 +394,7 @@ __global__ void __launch_bounds__(32 * (W + P), 1) k_slot_update_heads_tma(const
         step = step_n;
     }
     MKF_TP_FLUSH(nsteps);
+    if (a.pdl_late) mkf_pdl_launch_dependents();
     if (lane == 0) mkf_bulk_wait_all(); // shared memory must outlive the last store; the grid's end publishes it
     if (a.ts && lane == 0) atomicMax(a.ts + 1, mkf_globaltimer());
     MKF_TL_END(1, a.dbg_frame);

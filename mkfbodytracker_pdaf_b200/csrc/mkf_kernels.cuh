@@ -107,6 +107,9 @@ struct SlotArgs {
     const int* __restrict__ lbase_cur;  // ... its heads' records at lbase_cur[t]
     double2* __restrict__ xs;           // (aos) the heads' means again, tiled by list position (ResampleRunsArgs::xs)
     int dbg_frame;
+    // k_slot_update_heads_tma: 1 = let the dependent kernels' CTAs be scheduled when this kernel's warps END instead of
+    // at its start (see the kernel)
+    int pdl_late;
 };
 
 // record `sp` of a state buffer in either layout: pair p lives at mkf_rec<D>(st, sp, aos)[mkf_rec_off<D>(p, aos)]
@@ -127,10 +130,19 @@ __device__ __forceinline__ int mkf_rec_off(int p, int aos)
 // for the last 64 frames (mkf_debug_timeline); dbg_frame travels in the kernels' argument blocks
 #ifdef MKF_TIMELINE
 __device__ unsigned long long g_timeline[64][4][2];
+// (MKF_TL_LATEST_START: the slot kernel's entry holds the complement of its LATEST CTA start instead of the earliest)
+#ifdef MKF_TL_LATEST_START
+#define MKF_TL_START(k, fr)                                                                                            \
+    do {                                                                                                               \
+        if (threadIdx.x == 0)                                                                                          \
+            atomicMin(&g_timeline[(fr) & 63][k][0], (k) == 1 ? ~mkf_globaltimer() : mkf_globaltimer());               \
+    } while (0)
+#else
 #define MKF_TL_START(k, fr)                                                                                            \
     do {                                                                                                               \
         if (threadIdx.x == 0) atomicMin(&g_timeline[(fr) & 63][k][0], mkf_globaltimer());                             \
     } while (0)
+#endif
 #define MKF_TL_END(k, fr)                                                                                              \
     do {                                                                                                               \
         if ((threadIdx.x & 31) == 0) atomicMax(&g_timeline[(fr) & 63][k][1], mkf_globaltimer());                      \

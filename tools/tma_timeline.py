@@ -45,6 +45,8 @@ for f in range(40, F):
 torch.cuda.synchronize()
 lib.mkf_debug_timeline(buf.ctypes.data, 0)
 # frames 40..99 -> slots (frame & 63); order the 60 frames by the start of their first kernel
+if os.environ.get("MKF_LIB_VARIANT") == "tlskew":  # -DMKF_TL_LATEST_START: the slot kernel's start entry is ~(latest CTA start)
+    buf[:, 1, 0] = ~buf[:, 1, 0]
 fr = [buf[i].astype(np.int64) for i in range(64) if buf[i, 0, 1] > 0 and buf[i, 3, 1] > 0]
 fr.sort(key=lambda a: a[0, 0])
 fr = fr[5:-2]
