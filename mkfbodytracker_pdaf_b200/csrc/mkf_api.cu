@@ -1174,6 +1174,7 @@ static int update_device(mkf_batch* b, const double* d_meas, int meas_layout, co
 {
     const mkf_model* m = b->m;
     int rc;
+    g_pdl_override = -1; // (an error return inside update_device_runs may have left it cleared)
     if (u_stride != 1) {
         mkf_set_error("internal: strided u_ind unsupported");
         return MKF_E_INVALID;
