@@ -864,13 +864,18 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
 {
     const mkf_model* m = b->m;
     // which of the frame's four launches carry the programmatic-launch attribute (bit 0: k_frame_heads, 1: the slot
-    // kernel, 2: k_runs_repair, 3: k_resample_runs); MKF_PDL_MASK overrides for A/B runs.  The slot kernel goes WITHOUT:
-    // released early it starts 1.0 us after k_frame_heads instead of 3.5, but then lasts 62 us instead of 54 (device
-    // timeline of the pipelined loop at 4096 x 500, tools/tma_timeline.py: period 100.7 us with all four, 94.9 with this
-    // mask; profiles/r02_pdl_masks.txt)
+    // kernel, 2: k_runs_repair, 3: k_resample_runs); MKF_PDL_MASK overrides for A/B runs.  What matters is WHEN a kernel
+    // releases its dependents: the slot kernel released at the start of k_frame_heads starts 1.0 us after it instead of
+    // 3.5 but then lasts 62 us instead of 54 (device timeline of the pipelined loop at 4096 x 500, tools/tma_timeline.py:
+    // period 100.7 us; 94.9 without the attribute on the slot kernel); released while k_frame_heads writes its work list it
+    // starts as early and runs at its normal speed (93.9 us; profiles/r02_pdl_masks.txt)
     static const int pdl_mask = [] {
         const char* e = getenv("MKF_PDL_MASK");
-        return e ? atoi(e) : 13;
+        return e ? atoi(e) : 15;
+    }();
+    static const int heads_late = [] { // MKF_PDL_HEADS_LATE=0: k_frame_heads releases the slot kernel at its start
+        const char* e = getenv("MKF_PDL_HEADS_LATE");
+        return (e && e[0] == '0') ? 0 : 1;
     }();
     // MKF_FUSED=1: the single-launch frame kernel k_frame_fused instead of the three grid-wide kernels (k_frame_heads,
     // k_slot_update_heads_direct, k_resample_runs).  Measured at 4096 x 500: 0.147 ms per frame against 0.104 -- a warp
@@ -1022,6 +1027,7 @@ static int update_device_runs(mkf_batch* b, const double* d_meas, int meas_layou
         }
     } else {
         g_pdl_override = (pdl_mask & 1) ? -1 : 0;
+        f.pdl_late = heads_late;
         mkf_launch(k_frame_heads, grid_for(b->T, MKF_FH_WARPS), 32 * MKF_FH_WARPS, 0, b->stream, f);
         g_pdl_override = (pdl_mask & 2) ? -1 : 0; // (the slot kernel)
         MKF_LAUNCHED();

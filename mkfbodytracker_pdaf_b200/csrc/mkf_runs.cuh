@@ -95,6 +95,7 @@ struct FrameArgs {
     const int* __restrict__ lbase_prev;
     int* __restrict__ lbase_cur;
     int dbg_frame;
+    int pdl_late; // 1: the slot kernel's CTAs are released while the work list is written, not at this kernel's start
 };
 
 // component of slot j = number of cuts <= j (cuts sorted, nc <= 63): branch-free binary search
@@ -138,7 +139,10 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
     __shared__ int bcuts_s[MKF_FH_WARPS][32];
     __shared__ int nh_s[MKF_FH_WARPS];
     __shared__ int base_s;
-    mkf_pdl_launch_dependents();
+    // A dependent released at this kernel's START sits on the SMs for its whole duration and then runs slower (the slot
+    // kernel: 62 us instead of 54-55, profiles/r02_pdl_masks.txt); released while the work list is written it starts 1 us
+    // after this kernel's end and runs at its normal speed.
+    if (!f.pdl_late) mkf_pdl_launch_dependents();
     mkf_pdl_wait();
     MKF_TL_START(0, f.dbg_frame);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(32 * MKF_FH_WARPS) k_frame_heads(const FrameAr
         base_s = atomicAdd(f.head_count, tot);
     }
     __syncthreads();
+    if (f.pdl_late) mkf_pdl_launch_dependents();
     int lb = base_s;
     for (int w = 0; w < wid; w++) lb += nh_s[w];
     // where the parents' records lie: the track's stretch of the previous list, or its own N slots
