@@ -143,11 +143,7 @@ __device__ __forceinline__ void mkf_resample_sequential(WF w, int L, int N, doub
     for (int i = 0; i < N; i++) {
         while (beta > wi) {
             beta = __dsub_rn(beta, wi);
-#ifdef MKF_DBG_OLD_MOD
-            idx = (idx + 1) % L;
-#else
             idx = (idx + 1 == L) ? 0 : idx + 1; // (idx + 1) % L
-#endif
             wi = w(idx);
         }
         beta = __dadd_rn(beta, step);
