@@ -769,3 +769,29 @@ def test_short_track_frame_variants_agree(left_arm, right_arm, T, N, arm, monkey
                 assert np.array_equal(dr[key], df[key]), (fr, key)
     # the output back-end reads the pose the frame left in the batch
     assert np.array_equal(ref.pose3d(), fus.pose3d())
+
+
+def test_short_track_frame_is_two_launches_by_default(left_arm, monkeypatch):
+    """A batch of short tracks takes k_frame_small by default (<= 16384 tracks): one frame = k_frame_small + the repair
+    kernel, and the estimate is a copy out of the batch -- against four launches + the estimate kernel when forced off."""
+    T, N, seed = 64, 15, 0x5EED0015
+    tracks = list(range(T))
+    u0 = synth_u_init(seed, tracks)
+    counts = {}
+    for label, env in (("default", None), ("off", "0")):
+        if env is None:
+            monkeypatch.delenv("MKF_SMALL_FUSED", raising=False)
+        else:
+            monkeypatch.setenv("MKF_SMALL_FUSED", env)
+        b = mk.TrackBatch(left_arm.mk, T, N)
+        b.reset(u0)
+        m, ui, up = synth_frame(seed, tracks, 0)
+        b.update(m, ui, up)  # (first call: function attributes, buffers)
+        b.estimate()
+        n0 = mk.launch_count()
+        m, ui, up = synth_frame(seed, tracks, 1)
+        b.update(m, ui, up)
+        b.estimate()
+        counts[label] = mk.launch_count() - n0
+    assert counts["default"] == 2, counts
+    assert counts["off"] >= 5, counts  # bounds, slot update, repair, resample + the estimate kernel
