@@ -795,3 +795,52 @@ def test_short_track_frame_is_two_launches_by_default(left_arm, monkeypatch):
         counts[label] = mk.launch_count() - n0
     assert counts["default"] == 2, counts
     assert counts["off"] >= 5, counts  # bounds, slot update, repair, resample + the estimate kernel
+
+
+@pytest.mark.parametrize("K,d,N", [(25, 10, 14), (26, 12, 16), (31, 10, 9)])
+def test_short_track_frame_other_model_shapes(K, d, N, monkeypatch):
+    """k_frame_small with more components than lanes in a half warp (16 < K <= 32: two indicator boundaries per lane) and
+    with d = 10: against the oracle and, bit for bit, against the five-launch frame"""
+    rng = np.random.default_rng(K * 100 + d)
+    D = 22
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    proj = q[:d].astype(np.float32).astype(np.float64)
+    pmean = np.concatenate([[388, 281, 1.7, 390, 223, 1.8, 369, 158, 1.8, 324, 74.5, 1.8, 326, 128.6, 1.85],
+                            np.zeros(D - 15)])[:D]
+    means = rng.standard_normal((K, d)) * 40
+    covs = np.zeros((K, d, d))
+    for k in range(K):
+        a_ = rng.standard_normal((d, d))
+        covs[k] = 150.0 * (a_ @ a_.T / d + 0.05 * np.eye(d))
+    wts = rng.dirichlet(np.ones(K))
+    gam = rng.uniform(0.85, 0.99, K)
+    m = mk.Model.from_arrays(means, covs, wts, gam, proj, pmean)
+    om = orc.Model(means, covs, wts, gam, proj, pmean)
+    T = 37
+    u0 = rng.random(T)
+    fs = [orc.Filter(om, N) for _ in range(T)]
+    for f, u in zip(fs, u0):
+        f.reset(u=u)
+    monkeypatch.setenv("MKF_SMALL_FUSED", "0")
+    ref = mk.TrackBatch(m, T, N)
+    monkeypatch.setenv("MKF_SMALL_FUSED", "1")
+    fus = mk.TrackBatch(m, T, N)
+    ref.reset(u0)
+    fus.reset(u0)
+    keys = ("parents", "indicators", "x", "P", "w_raw", "w_norm", "wsum", "status")
+    for fr in range(6):
+        meas, ui, up = synth_frame(0x5EED0002, range(T), fr, N if fr % 2 else None)
+        res = [fs[t].update(meas[t], ui[t], up[t]) for t in range(T)]
+        ref.update(meas, ui, up)
+        fus.update(meas, ui, up)
+        stats, _ = compare_frame(fus, fs, res, check_state=True)
+        assert_parity(stats)
+        dr, df = ref.download(), fus.download()
+        for key in keys:
+            assert np.array_equal(dr[key], df[key]), (fr, key)
+        er, ef = ref.estimate(), fus.estimate()
+        assert np.array_equal(er[0], ef[0]) and np.array_equal(er[1], ef[1]), fr
+    xb, pose = fus.estimate()
+    for t in range(T):
+        xo, po = fs[t].estimate()
+        assert rel_err(xb[t], xo) <= RTOL and rel_err(pose[t], po) <= RTOL
